@@ -1,0 +1,974 @@
+// api.cu -- C-ABI entry points (include/b2m.h), context, HBM expert cache and prefetch scheduler.
+//
+// Host-side design:
+//  * one arena of fixed-size expert slots in HBM (blob layout == the reference's host blob, so staging an expert
+//    is one contiguous H2D copy); three 3-D TMA tensor maps {K, rows, slot} describe every slot at once;
+//  * device table slot_of[L][E] tells the grouped GEMM which slot holds which expert; it is re-uploaded in
+//    stream order only when the mapping of that layer changed;
+//  * when every expert fits (num_slots >= L*E) the hot call is sync-free and CUDA-graph capturable;
+//  * otherwise ("offload mode") the per-expert token counts are read back once per layer -- the same
+//    synchronisation the reference performs (expert_executor.py:34-39) -- misses are staged on a fetch stream,
+//    predicted experts on a prefetch stream, and the compute stream waits on per-expert events only.
+//  Cache policy (explicit): evict the resident, unpinned, not-in-use expert with the smallest
+//  in-cache visit count (core/parallel/expert_dispatcher.cpp:243-258), skipping protected prefetch candidates
+//  unless nothing else is evictable (core/prefetch/task_scheduler.cpp:288-296).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include <cudaTypedefs.h>
+
+#include "../../include/b2m.h"
+#include "b2m_internal.h"
+
+using namespace b2m;
+
+namespace {
+
+constexpr int NT_LIST[4] = {16, 32, 64, 128};
+constexpr int EVENT_RING = 64;
+constexpr int STAGE_RING = 8;
+
+std::string g_create_error;
+
+struct ExpertShape {
+  int H = 0, I = 0;
+  bool dual = true;
+  int act = ACT_SILU;
+  size_t off_gate = 0, off_up = 0, off_down = 0, bytes = 0;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t slot_bytes = 0;
+  int nslots = 0;
+  bool owned = false;
+  ExpertShape shape;
+  CUtensorMap tm_gate, tm_up, tm_down;
+};
+
+enum ExpertState : int { ST_UNREGISTERED = 0, ST_HOST = 1, ST_LOADING = 2, ST_RESIDENT = 3 };
+
+struct Expert {
+  const uint8_t* host = nullptr;
+  int state = ST_UNREGISTERED;
+  int slot = -1;
+  bool pinned = false;
+  bool prefetched_unused = false;
+  int visits = 0;               // incache_visit_count (model_topology.h:75-91)
+  uint64_t total_visits = 0;
+  cudaEvent_t ready = nullptr;  // H2D complete
+  bool ready_pending = false;   // compute stream has not yet been ordered after `ready`
+};
+
+struct Slot {
+  int owner = -1;
+  int last_use_ev = -1;  // index into the event ring
+};
+
+}  // namespace
+
+struct b2m_ctx {
+  b2m_config cfg;
+  std::string err;
+  int num_sms = 148;
+  size_t total_mem = 0;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+
+  Arena arena;         // routed experts
+  Arena shared_arena;  // DeepSeek shared experts: slot == layer, always resident
+  std::vector<uint8_t> shared_registered;
+  std::vector<Expert> experts;  // [L*E], id = layer*E + expert
+  std::vector<Slot> slots;
+  std::vector<int> free_slots;
+  bool offload = false;
+
+  // device tables
+  int* d_slot_of = nullptr;  // [L*E]
+  std::vector<int> h_slot_of;
+  std::vector<uint8_t> row_dirty;
+  int* h_stage = nullptr;  // pinned [STAGE_RING][E]
+  int stage_pos = 0;
+  std::vector<const void*> gate_w;  // per layer device pointers
+
+  // workspace
+  int cap_T = 0, cap_R = 0;
+  int* d_topk_idx = nullptr;
+  float* d_topk_w = nullptr;
+  int* d_row_of = nullptr;
+  int* d_perm_token = nullptr;
+  int* d_counts = nullptr;
+  int* d_offsets = nullptr;
+  int* d_chunk_counts = nullptr;
+  float* d_scores = nullptr;
+  void* d_logits = nullptr;
+  void* d_xp = nullptr;
+  void* d_hmid = nullptr;
+  float* d_y = nullptr;
+  void* d_hmid_s = nullptr;
+  float* d_y_s = nullptr;
+  int* h_counts = nullptr;  // pinned [E+1]
+  bool last_counts_valid = false;
+  CUtensorMap tm_xp[4], tm_hmid[4], tm_hmid_s[4];
+
+  // streams / events
+  cudaStream_t fetch_stream = nullptr, prefetch_stream = nullptr;
+  cudaEvent_t ev_ring[EVENT_RING];
+  int ev_pos = 0;
+  cudaEvent_t ev_route = nullptr;
+
+  // prefetch scheduler
+  std::unordered_set<int> protected_set;
+  std::deque<int> pending;
+  std::vector<int> inflight;
+  std::vector<int> last_active;
+
+  int cur_ksplit = 1, cur_nt = 16, cur_T = 0;
+  b2m_stats stats;
+};
+
+namespace {
+
+int fail(b2m_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(c, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail((c), B2M_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+int elem_size(int dtype) { return (dtype == B2M_DTYPE_F32) ? 4 : 2; }
+
+bool make_shape(int expert_type, int H, int I, ExpertShape* s) {
+  const size_t m = (size_t)H * I * 2;
+  s->H = H;
+  s->I = I;
+  switch (expert_type) {
+    case B2M_EXPERT_MIXTRAL_MOE_DENSE_ACT_DENSE:  // w1 | w2 | w3  (expert_module.cpp:139-145)
+      s->dual = true; s->act = ACT_SILU; s->off_gate = 0; s->off_down = m; s->off_up = 2 * m; s->bytes = 3 * m;
+      return true;
+    case B2M_EXPERT_DEEPSEEK_MOE_DENSE_ACT_DENSE:  // gate | up | down  (:185-191)
+      s->dual = true; s->act = ACT_SILU; s->off_gate = 0; s->off_up = m; s->off_down = 2 * m; s->bytes = 3 * m;
+      return true;
+    case B2M_EXPERT_SWITCH_DENSE_GATED_ACT_DENSE:  // wi_0 | wi_1 | wo  (:45-52)
+      s->dual = true; s->act = ACT_GELU; s->off_gate = 0; s->off_up = m; s->off_down = 2 * m; s->bytes = 3 * m;
+      return true;
+    case B2M_EXPERT_SWITCH_DENSE_ACT_DENSE:  // wi | wo  (:17-23)
+      s->dual = false; s->act = ACT_RELU; s->off_gate = 0; s->off_up = 0; s->off_down = m; s->bytes = 2 * m;
+      return true;
+    default:
+      return false;
+  }
+}
+
+int encode_map(b2m_ctx* c, CUtensorMap* tm, int dtype, void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+  cuuint64_t gdim[3];
+  cuuint64_t gstr[2];
+  cuuint32_t b[3], es[3];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapDataType dt = dtype == B2M_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = c->encode(tm, dt, (cuuint32_t)rank, base, gdim, gstr, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, B2M_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return B2M_OK;
+}
+
+int build_arena_maps(b2m_ctx* c, Arena* a) {
+  const ExpertShape& s = a->shape;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    const uint64_t dims[3] = {(uint64_t)s.H, (uint64_t)s.I, (uint64_t)a->nslots};
+    const uint64_t str[2] = {(uint64_t)s.H * 2, (uint64_t)a->slot_bytes};
+    int r = encode_map(c, &a->tm_gate, c->cfg.dtype, a->base + s.off_gate, 3, dims, str, box);
+    if (r) return r;
+    r = encode_map(c, &a->tm_up, c->cfg.dtype, a->base + s.off_up, 3, dims, str, box);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)s.I, (uint64_t)s.H, (uint64_t)a->nslots};
+    const uint64_t str[2] = {(uint64_t)s.I * 2, (uint64_t)a->slot_bytes};
+    int r = encode_map(c, &a->tm_down, c->cfg.dtype, a->base + s.off_down, 3, dims, str, box);
+    if (r) return r;
+  }
+  return B2M_OK;
+}
+
+int build_act_map(b2m_ctx* c, CUtensorMap* tm, void* base, int K, int rows, int nt) {
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  const uint64_t str[1] = {(uint64_t)K * 2};
+  const uint32_t box[2] = {64, (uint32_t)nt};
+  return encode_map(c, tm, c->cfg.dtype, base, 2, dims, str, box);
+}
+
+int nt_index(int nt) { return nt == 16 ? 0 : nt == 32 ? 1 : nt == 64 ? 2 : 3; }
+
+int pick_nt(int T) {
+  for (int i = 0; i < 4; ++i)
+    if (T <= NT_LIST[i]) return NT_LIST[i];
+  return 128;
+}
+
+// split-K for the down projection: enough tiles for ~6 waves, every split non-empty and >= 4 k-blocks
+int pick_ksplit(const b2m_ctx* c, int T, int M, int K, int E, int k, int nt) {
+  const int kblocks = (K + 63) / 64;
+  const long long rows = (long long)T * k;
+  const int active = (int)std::min<long long>(E, std::max<long long>(1, rows));
+  const long long n_tiles = std::max<long long>(1, (rows / std::max(1, active) + nt - 1) / nt);
+  const long long tiles = (long long)active * ((M + 127) / 128) * n_tiles;
+  int ks = (int)std::min<long long>(8, (6LL * c->num_sms + tiles - 1) / tiles);
+  ks = std::max(1, std::min(ks, kblocks / 4 > 0 ? kblocks / 4 : 1));
+  while (ks > 1) {
+    const int per = (kblocks + ks - 1) / ks;
+    if ((ks - 1) * per < kblocks) break;
+    --ks;
+  }
+  return ks;
+}
+
+cudaEvent_t next_ring_event(b2m_ctx* c, int* idx) {
+  *idx = c->ev_pos;
+  cudaEvent_t e = c->ev_ring[c->ev_pos];
+  c->ev_pos = (c->ev_pos + 1) % EVENT_RING;
+  return e;
+}
+
+// ---------------- cache policy ----------------
+int pick_victim(b2m_ctx* c, const std::vector<int>& in_use, bool allow_protected) {
+  const int L = c->cfg.num_layers, E = c->cfg.num_experts;
+  int best = -1, best_visits = INT32_MAX;
+  // expert-major scan, strict '<' : same tie order as expert_dispatcher.cpp:233-252
+  for (int e = 0; e < E; ++e) {
+    for (int l = 0; l < L; ++l) {
+      const int id = l * E + e;
+      const Expert& x = c->experts[id];
+      if (x.state != ST_RESIDENT || x.pinned || x.host == nullptr) continue;
+      if (!allow_protected && c->protected_set.count(id)) continue;
+      if (std::find(in_use.begin(), in_use.end(), id) != in_use.end()) continue;
+      if (x.visits < best_visits) { best = id; best_visits = x.visits; }
+    }
+  }
+  return best;
+}
+
+void evict(b2m_ctx* c, int id) {
+  Expert& x = c->experts[id];
+  const int slot = x.slot;
+  x.state = ST_HOST;
+  x.slot = -1;
+  x.prefetched_unused = false;
+  c->slots[slot].owner = -1;
+  c->h_slot_of[id] = -1;
+  c->row_dirty[id / c->cfg.num_experts] = 1;
+  c->free_slots.push_back(slot);
+  c->stats.evictions++;
+}
+
+int acquire_slot(b2m_ctx* c, const std::vector<int>& in_use, bool prefetch) {
+  if (c->free_slots.empty()) {
+    int v = pick_victim(c, in_use, false);
+    if (v < 0 && !prefetch) v = pick_victim(c, in_use, true);   // overflow: on-demand beats protection
+    if (v < 0) return -1;
+    evict(c, v);
+  }
+  const int s = c->free_slots.back();
+  c->free_slots.pop_back();
+  return s;
+}
+
+int issue_copy(b2m_ctx* c, int id, int slot, cudaStream_t st, bool do_copy) {
+  Expert& x = c->experts[id];
+  Slot& sl = c->slots[slot];
+  if (sl.last_use_ev >= 0) CK(c, cudaStreamWaitEvent(st, c->ev_ring[sl.last_use_ev], 0));
+  uint8_t* dst = c->arena.base + (size_t)slot * c->arena.slot_bytes;
+  if (do_copy) {
+    const size_t bytes = c->arena.shape.bytes;
+    const size_t chunk = c->cfg.h2d_chunk_bytes > 0 ? (size_t)c->cfg.h2d_chunk_bytes : bytes;
+    for (size_t off = 0; off < bytes; off += chunk)
+      CK(c, cudaMemcpyAsync(dst + off, x.host + off, std::min(chunk, bytes - off), cudaMemcpyHostToDevice, st));
+    c->stats.h2d_bytes += bytes;
+  }
+  if (!x.ready) CK(c, cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
+  CK(c, cudaEventRecord(x.ready, st));
+  x.ready_pending = true;
+  x.state = ST_LOADING;
+  x.slot = slot;
+  sl.owner = id;
+  c->h_slot_of[id] = slot;
+  c->row_dirty[id / c->cfg.num_experts] = 1;
+  return B2M_OK;
+}
+
+int pump(b2m_ctx* c) {
+  // retire finished prefetches
+  for (size_t i = 0; i < c->inflight.size();) {
+    Expert& x = c->experts[c->inflight[i]];
+    bool done = x.state != ST_LOADING;
+    if (!done) {
+      cudaError_t q = cudaEventQuery(x.ready);
+      if (q == cudaSuccess) { x.state = ST_RESIDENT; done = true; }
+      else if (q != cudaErrorNotReady) return fail(c, B2M_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
+    }
+    if (done) { c->inflight[i] = c->inflight.back(); c->inflight.pop_back(); } else ++i;
+  }
+  const int max_if = c->cfg.max_inflight_prefetch > 0 ? c->cfg.max_inflight_prefetch : 2;
+  while ((int)c->inflight.size() < max_if && !c->pending.empty()) {
+    const int id = c->pending.front();
+    c->pending.pop_front();
+    Expert& x = c->experts[id];
+    if (x.state != ST_HOST) continue;
+    const int slot = acquire_slot(c, c->last_active, true);
+    if (slot < 0) { c->pending.clear(); break; }   // nothing evictable without hurting protected experts
+    int r = issue_copy(c, id, slot, c->prefetch_stream, true);
+    if (r) return r;
+    x.prefetched_unused = true;
+    c->inflight.push_back(id);
+    c->stats.prefetch_issued++;
+  }
+  return B2M_OK;
+}
+
+int upload_row_if_dirty(b2m_ctx* c, int layer, cudaStream_t st) {
+  if (!c->row_dirty[layer]) return B2M_OK;
+  const int E = c->cfg.num_experts;
+  int* stage = c->h_stage + (size_t)c->stage_pos * E;
+  c->stage_pos = (c->stage_pos + 1) % STAGE_RING;
+  memcpy(stage, &c->h_slot_of[(size_t)layer * E], sizeof(int) * E);
+  CK(c, cudaMemcpyAsync(c->d_slot_of + (size_t)layer * E, stage, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+  c->row_dirty[layer] = 0;
+  return B2M_OK;
+}
+
+int check_layer(b2m_ctx* c, int layer) {
+  if (!c) return B2M_EINVAL;
+  if (layer < 0 || layer >= c->cfg.num_layers) return fail(c, B2M_EINVAL, "layer %d out of range", layer);
+  return B2M_OK;
+}
+
+RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int seq_len) {
+  RouteParams p;
+  memset(&p, 0, sizeof p);
+  const b2m_config& f = c->cfg;
+  p.x = x;
+  p.gate_w = c->gate_w[layer];
+  p.gate_dtype = f.gate_dtype;
+  p.T = T; p.H = f.hidden; p.E = f.num_experts; p.k = f.top_k;
+  p.dtype = f.dtype;
+  p.router = f.router;
+  p.n_group = f.n_group; p.topk_group = f.topk_group; p.norm_topk_prob = f.norm_topk_prob;
+  p.routed_scaling_factor = f.routed_scaling_factor;
+  p.seq_len = seq_len > 0 ? seq_len : T;
+  p.expert_capacity = f.expert_capacity;
+  p.scores = c->d_scores;
+  p.logits_out = c->d_logits;
+  p.topk_idx = c->d_topk_idx; p.topk_w = c->d_topk_w; p.row_of = c->d_row_of; p.perm_token = c->d_perm_token;
+  p.counts = c->d_counts; p.offsets = c->d_offsets; p.chunk_counts = c->d_chunk_counts;
+  p.xp = c->d_xp;
+  return p;
+}
+
+void plan_gemm(b2m_ctx* c, int T) {
+  c->cur_T = T;
+  c->cur_nt = pick_nt(T);
+  c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt);
+}
+
+int route_launch_count(int T, int router) {
+  if (T == 0) return 0;
+  if (T <= 256) return 1;
+  return router == B2M_ROUTER_SWITCH_TOP1 ? 5 : 3;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char* b2m_last_error(const b2m_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int b2m_version(void) { return B2M_VERSION; }
+
+int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, B2M_EINVAL, "null argument");
+  if (cfg->struct_size != (int)sizeof(b2m_config))
+    return fail(nullptr, B2M_EINVAL, "b2m_config size mismatch (%d vs %d)", cfg->struct_size, (int)sizeof(b2m_config));
+  if (cfg->dtype == B2M_DTYPE_FP8_E4M3 || cfg->dtype == B2M_DTYPE_F32)
+    return fail(nullptr, B2M_EUNSUPPORTED, "dtype %d: the tensor-core path supports bf16 and f16 experts", cfg->dtype);
+  if (cfg->dtype != B2M_DTYPE_BF16 && cfg->dtype != B2M_DTYPE_F16) return fail(nullptr, B2M_EINVAL, "bad dtype");
+  if (cfg->num_layers < 1 || cfg->num_experts < 1 || cfg->num_experts > 256 || cfg->top_k < 1 || cfg->top_k > 8 ||
+      cfg->top_k > cfg->num_experts || cfg->hidden < 64 || cfg->inter < 64 || cfg->hidden % 8 || cfg->inter % 8 ||
+      cfg->max_tokens < 1)
+    return fail(nullptr, B2M_EINVAL, "bad model dimensions");
+  ExpertShape shape;
+  if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape))
+    return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is not supported (bias experts are out of scope)", cfg->expert_type);
+  if (cfg->router < 0 || cfg->router > 3) return fail(nullptr, B2M_EINVAL, "bad router kind");
+  if (cfg->router == B2M_ROUTER_SWITCH_TOP1 && cfg->top_k != 1) return fail(nullptr, B2M_EINVAL, "switch router needs top_k=1");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, B2M_ECUDA, "no CUDA device: %s -- this library has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, B2M_EINVAL, "device %d out of range", cfg->device);
+
+  b2m_ctx* c = new (std::nothrow) b2m_ctx();
+  if (!c) return fail(nullptr, B2M_ENOMEM, "out of host memory");
+  c->cfg = *cfg;
+  memset(&c->stats, 0, sizeof c->stats);
+#define CKC(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      fail(nullptr, B2M_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      b2m_ctx_destroy(c);                                                                             \
+      return B2M_ECUDA;                                                                               \
+    }                                                                                                 \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    fail(nullptr, B2M_EUNSUPPORTED, "device sm_%d%d: this library is built for sm_100a (B200) only", prop.major, prop.minor);
+    b2m_ctx_destroy(c);
+    return B2M_EUNSUPPORTED;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->total_mem = prop.totalGlobalMem;
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      fail(nullptr, B2M_ECUDA, "cuTensorMapEncodeTiled not available in this driver");
+      b2m_ctx_destroy(c);
+      return B2M_ECUDA;
+    }
+    c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const int L = cfg->num_layers, E = cfg->num_experts, H = cfg->hidden, I = cfg->inter, k = cfg->top_k;
+  // ---- HBM slot arena: budget = ratio * total / expert bytes (memory_pool.cpp:150-158; expert_dispatcher.cpp:52-54)
+  c->arena.shape = shape;
+  c->arena.slot_bytes = shape.bytes;
+  long long nslots = cfg->num_slots;
+  if (nslots <= 0) {
+    const double ratio = cfg->device_memory_ratio > 0 ? cfg->device_memory_ratio : 0.9;
+    nslots = (long long)(ratio * (double)c->total_mem / (double)shape.bytes);
+  }
+  nslots = std::max<long long>(1, std::min<long long>(nslots, (long long)L * E));
+  c->arena.nslots = (int)nslots;
+  c->offload = nslots < (long long)L * E;
+  CKC(cudaMalloc((void**)&c->arena.base, (size_t)nslots * shape.bytes));
+  c->arena.owned = true;
+  int r = build_arena_maps(c, &c->arena);
+  if (r) { g_create_error = c->err; b2m_ctx_destroy(c); return r; }
+  if (cfg->shared_inter > 0) {
+    ExpertShape ss;
+    make_shape(B2M_EXPERT_DEEPSEEK_MOE_DENSE_ACT_DENSE, H, cfg->shared_inter, &ss);
+    c->shared_arena.shape = ss;
+    c->shared_arena.slot_bytes = ss.bytes;
+    c->shared_arena.nslots = L;
+    CKC(cudaMalloc((void**)&c->shared_arena.base, (size_t)L * ss.bytes));
+    c->shared_arena.owned = true;
+    r = build_arena_maps(c, &c->shared_arena);
+    if (r) { g_create_error = c->err; b2m_ctx_destroy(c); return r; }
+    c->shared_registered.assign(L, 0);
+  }
+  c->experts.assign((size_t)L * E, Expert());
+  c->slots.assign((size_t)nslots, Slot());
+  for (int s = (int)nslots - 1; s >= 0; --s) c->free_slots.push_back(s);
+  c->h_slot_of.assign((size_t)L * E, -1);
+  c->row_dirty.assign(L, 1);
+  c->gate_w.assign(L, nullptr);
+  CKC(cudaMalloc((void**)&c->d_slot_of, sizeof(int) * L * E));
+  CKC(cudaMemset(c->d_slot_of, 0xff, sizeof(int) * L * E));
+  CKC(cudaHostAlloc((void**)&c->h_stage, sizeof(int) * STAGE_RING * E, cudaHostAllocDefault));
+  CKC(cudaHostAlloc((void**)&c->h_counts, sizeof(int) * (E + 1), cudaHostAllocDefault));
+  // ---- workspace
+  const int T = cfg->max_tokens;
+  const size_t R = (size_t)T * k;
+  c->cap_T = T;
+  c->cap_R = (int)R;
+  CKC(cudaMalloc((void**)&c->d_topk_idx, sizeof(int) * R));
+  CKC(cudaMalloc((void**)&c->d_topk_w, sizeof(float) * R));
+  CKC(cudaMalloc((void**)&c->d_row_of, sizeof(int) * R));
+  CKC(cudaMalloc((void**)&c->d_perm_token, sizeof(int) * R));
+  CKC(cudaMalloc((void**)&c->d_counts, sizeof(int) * E));
+  CKC(cudaMalloc((void**)&c->d_offsets, sizeof(int) * (E + 1)));
+  CKC(cudaMemset(c->d_offsets, 0, sizeof(int) * (E + 1)));
+  CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
+  CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
+  CKC(cudaMalloc((void**)&c->d_logits, sizeof(float) * (size_t)T * E));
+  CKC(cudaMalloc(&c->d_xp, R * H * 2));
+  CKC(cudaMalloc(&c->d_hmid, R * I * 2));
+  CKC(cudaMalloc((void**)&c->d_y, R * H * sizeof(float)));
+  CKC(cudaMemset(c->d_xp, 0, R * H * 2));
+  CKC(cudaMemset(c->d_hmid, 0, R * I * 2));
+  if (cfg->shared_inter > 0) {
+    CKC(cudaMalloc(&c->d_hmid_s, (size_t)T * cfg->shared_inter * 2));
+    CKC(cudaMemset(c->d_hmid_s, 0, (size_t)T * cfg->shared_inter * 2));
+    CKC(cudaMalloc((void**)&c->d_y_s, (size_t)T * H * sizeof(float)));
+  }
+  for (int i = 0; i < 4; ++i) {
+    r = build_act_map(c, &c->tm_xp[i], c->d_xp, H, (int)R, NT_LIST[i]);
+    if (!r) r = build_act_map(c, &c->tm_hmid[i], c->d_hmid, I, (int)R, NT_LIST[i]);
+    if (!r && cfg->shared_inter > 0) r = build_act_map(c, &c->tm_hmid_s[i], c->d_hmid_s, cfg->shared_inter, T, NT_LIST[i]);
+    if (r) { g_create_error = c->err; b2m_ctx_destroy(c); return r; }
+  }
+  int lo = 0, hi = 0;
+  CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CKC(cudaStreamCreateWithPriority(&c->fetch_stream, cudaStreamNonBlocking, hi));
+  CKC(cudaStreamCreateWithPriority(&c->prefetch_stream, cudaStreamNonBlocking, lo));
+  for (int i = 0; i < EVENT_RING; ++i) CKC(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&c->ev_route, cudaEventDisableTiming));
+  c->stats.slots = (uint64_t)nslots;
+  c->stats.slot_bytes = shape.bytes;
+#undef CKC
+  *out = c;
+  return B2M_OK;
+}
+
+int b2m_ctx_destroy(b2m_ctx* c) {
+  if (!c) return B2M_OK;
+  cudaDeviceSynchronize();
+  if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
+  if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
+  void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
+                  c->d_chunk_counts, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
+  if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
+  if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
+  if (c->ev_route) {
+    for (int i = 0; i < EVENT_RING; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
+    cudaEventDestroy(c->ev_route);
+  }
+  delete c;
+  return B2M_OK;
+}
+
+int b2m_register_expert(b2m_ctx* c, int layer, int expert, const void* host_blob, size_t bytes) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
+  if (host_blob && bytes != c->arena.shape.bytes)
+    return fail(c, B2M_EINVAL, "expert blob is %zu bytes, expected %zu", bytes, c->arena.shape.bytes);
+  Expert& x = c->experts[(size_t)layer * c->cfg.num_experts + expert];
+  x.host = reinterpret_cast<const uint8_t*>(host_blob);
+  if (x.state == ST_UNREGISTERED) x.state = ST_HOST;
+  return B2M_OK;
+}
+
+int b2m_register_shared(b2m_ctx* c, int layer, const void* host_blob, size_t bytes) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (c->cfg.shared_inter <= 0) return fail(c, B2M_ESTATE, "context has no shared experts");
+  if (host_blob) {
+    if (bytes != c->shared_arena.shape.bytes)
+      return fail(c, B2M_EINVAL, "shared blob is %zu bytes, expected %zu", bytes, c->shared_arena.shape.bytes);
+    CK(c, cudaMemcpy(c->shared_arena.base + (size_t)layer * c->shared_arena.slot_bytes, host_blob, bytes, cudaMemcpyHostToDevice));
+  }
+  c->shared_registered[layer] = 1;
+  return B2M_OK;
+}
+
+int b2m_set_gate(b2m_ctx* c, int layer, const void* dev_gate_weight) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  c->gate_w[layer] = dev_gate_weight;
+  return B2M_OK;
+}
+
+int b2m_host_pin(b2m_ctx* c, void* host_ptr, size_t bytes) {
+  if (!c || !host_ptr) return B2M_EINVAL;
+  CK(c, cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+  return B2M_OK;
+}
+int b2m_host_unpin(b2m_ctx* c, void* host_ptr) {
+  if (!c || !host_ptr) return B2M_EINVAL;
+  CK(c, cudaHostUnregister(host_ptr));
+  return B2M_OK;
+}
+
+int b2m_make_resident(b2m_ctx* c, int layer, int expert, int flags, void* stream) {
+  (void)stream;
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
+  const int id = layer * c->cfg.num_experts + expert;
+  Expert& x = c->experts[id];
+  const bool no_copy = (flags & 2) != 0;
+  if (x.state == ST_UNREGISTERED) {
+    if (!no_copy) return fail(c, B2M_ESTATE, "expert (%d,%d) is not registered", layer, expert);
+    x.state = ST_HOST;
+  }
+  if (x.state == ST_HOST) {
+    if (!no_copy && !x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
+    std::vector<int> none;
+    const int slot = acquire_slot(c, none, false);
+    if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot for expert (%d,%d)", layer, expert);
+    r = issue_copy(c, id, slot, c->fetch_stream, !no_copy);
+    if (r) return r;
+  }
+  if (x.state == ST_LOADING) {
+    CK(c, cudaEventSynchronize(x.ready));
+    x.state = ST_RESIDENT;
+    x.ready_pending = false;
+  }
+  if (flags & 1) x.pinned = true;
+  if (!x.host) x.pinned = true;
+  return B2M_OK;
+}
+
+int b2m_expert_dev_ptr(b2m_ctx* c, int layer, int expert, void** dev_ptr) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts || !dev_ptr) return fail(c, B2M_EINVAL, "bad argument");
+  const Expert& x = c->experts[(size_t)layer * c->cfg.num_experts + expert];
+  *dev_ptr = x.slot >= 0 ? c->arena.base + (size_t)x.slot * c->arena.slot_bytes : nullptr;
+  return B2M_OK;
+}
+
+int b2m_shared_dev_ptr(b2m_ctx* c, int layer, void** dev_ptr) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (c->cfg.shared_inter <= 0 || !dev_ptr) return fail(c, B2M_ESTATE, "context has no shared experts");
+  *dev_ptr = c->shared_arena.base + (size_t)layer * c->shared_arena.slot_bytes;
+  return B2M_OK;
+}
+
+int b2m_ws_ptr(b2m_ctx* c, int which, void** p) {
+  if (!c || !p) return B2M_EINVAL;
+  switch (which) {
+    case B2M_WS_TOPK_IDX: *p = c->d_topk_idx; break;
+    case B2M_WS_TOPK_W: *p = c->d_topk_w; break;
+    case B2M_WS_ROW_OF: *p = c->d_row_of; break;
+    case B2M_WS_PERM_TOKEN: *p = c->d_perm_token; break;
+    case B2M_WS_COUNTS: *p = c->d_counts; break;
+    case B2M_WS_OFFSETS: *p = c->d_offsets; break;
+    case B2M_WS_XP: *p = c->d_xp; break;
+    case B2M_WS_HMID: *p = c->d_hmid; break;
+    case B2M_WS_Y: *p = c->d_y; break;
+    case B2M_WS_SCORES: *p = c->d_scores; break;
+    case B2M_WS_LOGITS: *p = c->d_logits; break;
+    default: return fail(c, B2M_EINVAL, "unknown workspace id %d", which);
+  }
+  return B2M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+int b2m_route(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T, int seq_len,
+              void* stream) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (T < 0 || T > c->cap_T) return fail(c, B2M_EINVAL, "T=%d exceeds workspace capacity %d", T, c->cap_T);
+  if (!x && T > 0) return fail(c, B2M_EINVAL, "x is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  RouteParams p = base_route_params(c, layer, x, T, seq_len);
+  if (kind == 0) {
+    if (!p.gate_w) return fail(c, B2M_ESTATE, "layer %d has no gate weight (b2m_set_gate) and no router input", layer);
+  } else {
+    if (!router_in) return fail(c, B2M_EINVAL, "router_in is null");
+    p.logits = router_in;
+    p.logits_dtype = in_dtype;
+    p.logits_are_scores = (kind == 2);
+    if (kind == 2 && in_dtype != B2M_DTYPE_F32) return fail(c, B2M_EINVAL, "scores must be fp32");
+  }
+  if (c->cfg.router == B2M_ROUTER_SWITCH_TOP1 && (p.seq_len <= 0 || T % p.seq_len))
+    return fail(c, B2M_EINVAL, "T=%d is not a multiple of seq_len=%d", T, p.seq_len);
+  plan_gemm(c, T);
+  if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
+  CK(c, launch_route(p, st));
+  c->stats.kernel_launches += route_launch_count(T, c->cfg.router);
+  c->last_counts_valid = false;
+  return B2M_OK;
+}
+
+int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mask, int T, void* stream) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (T < 0 || T > c->cap_T) return fail(c, B2M_EINVAL, "T=%d exceeds workspace capacity %d", T, c->cap_T);
+  cudaStream_t st = (cudaStream_t)stream;
+  RouteParams p = base_route_params(c, layer, x, T, T);
+  p.scores = nullptr;
+  p.logits_out = nullptr;
+  plan_gemm(c, T);
+  if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
+  CK(c, launch_route_from_mask(p, mask, st));
+  c->stats.kernel_launches += T == 0 ? 0 : (T <= 256 ? 1 : 4);
+  c->last_counts_valid = false;
+  return B2M_OK;
+}
+
+static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, const CUtensorMap& tm_b_up,
+                               const CUtensorMap& tm_b_down, const void* b_up, int ldb_up, const void* b_down,
+                               void* hmid, float* y, int nt, int ksplit, cudaStream_t st) {
+  const b2m_config& f = c->cfg;
+  const ExpertShape& s = a.shape;
+  GemmParams up = base;
+  up.M = s.I; up.K = s.H; up.ksplit = 1; up.epi = EPI_ACT16; up.act = s.act;
+  up.mimic = f.numerics == B2M_NUMERICS_REFERENCE; up.out = hmid; up.ld_out = s.I;
+  GemmParams dn = base;
+  dn.M = s.H; dn.K = s.I; dn.ksplit = ksplit; dn.epi = EPI_LINEAR_F32; dn.act = ACT_NONE; dn.mimic = 0;
+  dn.out = y; dn.ld_out = s.H;
+  if (f.gemm_impl == 1) {
+    const size_t slot_elems = a.slot_bytes / 2;
+    CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_gate / 2, s.off_up / 2, b_up, ldb_up, up, s.dual, st));
+    dn.ksplit = 1;
+    CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
+  } else {
+    CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
+    CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+  }
+  c->stats.kernel_launches += 2;
+  return B2M_OK;
+}
+
+int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (T != c->cur_T) return fail(c, B2M_ESTATE, "b2m_run_experts(T=%d) does not follow a routing call with the same T (%d)", T, c->cur_T);
+  if (T == 0) return B2M_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int E = c->cfg.num_experts;
+  r = pump(c);
+  if (r) return r;
+  std::vector<int> active;
+  if (c->offload) {
+    // on-demand path: read the per-expert counts back (the reference's .cpu() in dispatch_local)
+    CK(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->stats.host_syncs++;
+    c->last_counts_valid = true;
+    for (int e = 0; e < E; ++e)
+      if (c->h_counts[e] > 0) active.push_back(layer * E + e);
+  } else {
+    for (int e = 0; e < E; ++e) active.push_back(layer * E + e);
+  }
+  // residency
+  for (int id : active) {
+    Expert& x = c->experts[id];
+    if (x.state == ST_UNREGISTERED) return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
+    if (c->offload) {
+      c->stats.dispatches++;
+      x.visits += 1;            // incache_visit_count += 1 for every dispatched expert (expert_dispatcher.cpp:264)
+      x.total_visits += 1;
+    }
+    if (x.state == ST_RESIDENT || x.state == ST_LOADING) {
+      if (c->offload) {
+        c->stats.hits++;
+        if (x.prefetched_unused) { c->stats.prefetch_useful++; x.prefetched_unused = false; }
+      }
+    } else {
+      if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
+      if (c->offload) c->stats.misses++;
+      const int slot = acquire_slot(c, active, false);
+      if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot: %d experts active, %d slots", (int)active.size(), c->arena.nslots);
+      r = issue_copy(c, id, slot, c->fetch_stream, true);
+      if (r) return r;
+    }
+  }
+  for (int id : active) {
+    Expert& x = c->experts[id];
+    if (x.ready_pending) {
+      CK(c, cudaStreamWaitEvent(st, x.ready, 0));
+      x.ready_pending = false;
+    }
+    if (x.state == ST_LOADING) x.state = ST_RESIDENT;   // every later use is stream-ordered after the wait above
+  }
+  r = upload_row_if_dirty(c, layer, st);
+  if (r) return r;
+
+  GemmParams base;
+  memset(&base, 0, sizeof base);
+  base.offsets = c->d_offsets;
+  base.slot_of = c->d_slot_of + (size_t)layer * E;
+  base.E = E;
+  base.single_n = -1;
+  const int ni = nt_index(c->cur_nt);
+  r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid, c->d_hmid,
+                          c->d_y, c->cur_nt, c->cur_ksplit, st);
+  if (r) return r;
+  if (c->offload) {
+    int evi;
+    cudaEvent_t ev = next_ring_event(c, &evi);
+    CK(c, cudaEventRecord(ev, st));
+    for (int id : active) c->slots[c->experts[id].slot].last_use_ev = evi;
+    c->last_active = active;
+  }
+  return B2M_OK;
+}
+
+static int run_shared(b2m_ctx* c, int layer, const void* x, int T, cudaStream_t st) {
+  if (!c->shared_registered[layer]) return fail(c, B2M_ESTATE, "shared expert of layer %d not registered", layer);
+  const int nt = pick_nt(T);
+  const int ks = pick_ksplit(c, T, c->cfg.hidden, c->cfg.shared_inter, 1, 1, nt);
+  CUtensorMap tm_x;
+  int r = build_act_map(c, &tm_x, const_cast<void*>(x), c->cfg.hidden, T, nt);
+  if (r) return r;
+  if (ks > 1) CK(c, cudaMemsetAsync(c->d_y_s, 0, (size_t)T * c->cfg.hidden * sizeof(float), st));
+  GemmParams base;
+  memset(&base, 0, sizeof base);
+  base.E = 1;
+  base.single_n = T;
+  base.single_slot = layer;
+  return launch_expert_gemms(c, c->shared_arena, base, tm_x, c->tm_hmid_s[nt_index(nt)], x, c->cfg.hidden, c->d_hmid_s,
+                             c->d_hmid_s, c->d_y_s, nt, ks, st);
+}
+
+int b2m_combine(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (T == 0) return B2M_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const b2m_config& f = c->cfg;
+  CombineParams p;
+  memset(&p, 0, sizeof p);
+  p.y = c->d_y;
+  p.x = x;
+  p.topk_idx = c->d_topk_idx; p.topk_w = c->d_topk_w; p.row_of = c->d_row_of;
+  p.out = out;
+  p.T = T; p.H = f.hidden; p.k = f.top_k; p.dtype = f.dtype;
+  if (f.router == B2M_ROUTER_SWITCH_TOP1) p.mode = COMBINE_SWITCH;
+  else if (f.numerics == B2M_NUMERICS_FP32) p.mode = COMBINE_FP32;
+  else p.mode = f.router == B2M_ROUTER_MIXTRAL ? COMBINE_MIXTRAL : COMBINE_DEEPSEEK;
+  if (f.shared_inter > 0) {
+    r = run_shared(c, layer, x, T, st);
+    if (r) return r;
+    p.y_shared = c->d_y_s;
+  }
+  CK(c, launch_combine(p, st));
+  c->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+int b2m_moe_forward(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T,
+                    int seq_len, void* out, void* stream) {
+  int r = b2m_route(c, layer, x, router_in, kind, in_dtype, T, seq_len, stream);
+  if (r) return r;
+  r = b2m_run_experts(c, layer, T, stream);
+  if (r) return r;
+  return b2m_combine(c, layer, x, T, out, stream);
+}
+
+int b2m_expert_outputs(b2m_ctx* c, int T, void* out_rows, int* offsets_host, void* stream) {
+  if (!c) return B2M_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)T * c->cfg.top_k * c->cfg.hidden;
+  if (out_rows && T > 0) {
+    CK(c, launch_cast_rows(c->d_y, out_rows, n, c->cfg.dtype, st));
+    c->stats.kernel_launches += 1;
+  }
+  if (offsets_host) {
+    CK(c, cudaMemcpyAsync(offsets_host, c->d_offsets, sizeof(int) * (c->cfg.num_experts + 1), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+  }
+  return B2M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+int b2m_replace_cache_candidates(b2m_ctx* c, int n, const int32_t* pairs) {
+  if (!c || (n > 0 && !pairs)) return B2M_EINVAL;
+  const int L = c->cfg.num_layers, E = c->cfg.num_experts;
+  c->protected_set.clear();
+  for (int i = 0; i < n; ++i) {
+    const int l = pairs[2 * i], e = pairs[2 * i + 1];
+    if (l < 0 || l >= L || e < 0 || e >= E) return fail(c, B2M_EINVAL, "candidate (%d,%d) out of range", l, e);
+    c->protected_set.insert(l * E + e);
+  }
+  c->pending.clear();   // ArcherTaskPool::ReplaceCacheCandidates clears queued prefetches (task_scheduler.h:76-78)
+  return B2M_OK;
+}
+
+int b2m_enqueue_prefetch(b2m_ctx* c, int layer, int expert) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
+  const int id = layer * c->cfg.num_experts + expert;
+  Expert& x = c->experts[id];
+  if (x.state == ST_UNREGISTERED || !x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
+  if (x.state == ST_HOST && std::find(c->pending.begin(), c->pending.end(), id) == c->pending.end())
+    c->pending.push_back(id);   // dedupe (task_scheduler.cpp:86-104)
+  return pump(c);
+}
+
+int b2m_prefetch_hint(b2m_ctx* c, int n, const int32_t* pairs, const float* scores) {
+  if (!c || (n > 0 && (!pairs || !scores))) return B2M_EINVAL;
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return scores[a] > scores[b]; });
+  std::vector<int32_t> sorted(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) { sorted[2 * i] = pairs[2 * order[i]]; sorted[2 * i + 1] = pairs[2 * order[i] + 1]; }
+  int r = b2m_replace_cache_candidates(c, n, sorted.data());
+  if (r) return r;
+  for (int i = 0; i < n; ++i) {
+    const int id = sorted[2 * i] * c->cfg.num_experts + sorted[2 * i + 1];
+    Expert& x = c->experts[id];
+    if (x.state == ST_HOST && x.host) c->pending.push_back(id);
+  }
+  return pump(c);
+}
+
+int b2m_prefetch_pump(b2m_ctx* c) { return c ? pump(c) : B2M_EINVAL; }
+
+int b2m_prefetch_drain(b2m_ctx* c) {
+  if (!c) return B2M_EINVAL;
+  for (int guard = 0; guard < 1 << 20; ++guard) {
+    CK(c, cudaStreamSynchronize(c->prefetch_stream));
+    CK(c, cudaStreamSynchronize(c->fetch_stream));
+    int r = pump(c);
+    if (r) return r;
+    if (c->inflight.empty() && c->pending.empty()) break;
+  }
+  return B2M_OK;
+}
+
+int b2m_clear_expert_cache_counts(b2m_ctx* c) {
+  if (!c) return B2M_EINVAL;
+  for (auto& x : c->experts) x.visits = 0;
+  return B2M_OK;
+}
+
+int b2m_is_resident(b2m_ctx* c, int layer, int expert) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
+  const Expert& x = c->experts[(size_t)layer * c->cfg.num_experts + expert];
+  return (x.state == ST_RESIDENT || x.state == ST_LOADING) ? 1 : 0;
+}
+
+int b2m_stats_get(b2m_ctx* c, b2m_stats* out) {
+  if (!c || !out) return B2M_EINVAL;
+  uint64_t res = 0;
+  for (auto& x : c->experts) res += (x.state == ST_RESIDENT || x.state == ST_LOADING) ? 1 : 0;
+  c->stats.resident = res;
+  *out = c->stats;
+  return B2M_OK;
+}
+
+int b2m_last_counts(b2m_ctx* c, int32_t* counts_host) {
+  if (!c || !counts_host) return B2M_EINVAL;
+  if (!c->last_counts_valid) return fail(c, B2M_ESTATE, "last call ran sync-free; counts were not read back");
+  memcpy(counts_host, c->h_counts, sizeof(int) * c->cfg.num_experts);
+  return B2M_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// b2m_internal.h -- declarations shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b2m {
+
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GELU = 3 };
+enum : int { EPI_ACT16 = 0, EPI_LINEAR_F32 = 1 };
+
+// router kinds (which reference routing function is restated)
+enum : int {
+  ROUTER_MIXTRAL = 0,          // moe_infinity/models/mixtral.py:48-54
+  ROUTER_DEEPSEEK_GREEDY = 1,  // modeling_deepseek.py:467-483,508-512
+  ROUTER_DEEPSEEK_GROUP = 2,   // modeling_deepseek.py:484-505
+  ROUTER_SWITCH_TOP1 = 3,      // HF 4.x SwitchTransformersTop1Router (switch_transformers.py:76)
+};
+// combine kinds (which reference combine loop is restated)
+enum : int {
+  COMBINE_MIXTRAL = 0,   // mixtral.py:96-101 (weights in model dtype, product and += rounded to model dtype)
+  COMBINE_DEEPSEEK = 1,  // deepseek.py:123-128 (+133-136 shared experts); fp32 weights
+  COMBINE_SWITCH = 2,    // switch_transformers.py:99-109
+  COMBINE_FP32 = 3,      // fast path: fp32 accumulate, single rounding
+};
+
+struct GemmParams {
+  const int* offsets;   // [E+1] first permuted row of each expert
+  const int* slot_of;   // [E]   HBM slot of each expert of this layer (-1: not resident -> skipped)
+  int E;
+  int M;                // weight rows per expert
+  int K;                // reduction length
+  int ksplit;           // split-K factor (EPI_LINEAR_F32 only)
+  int epi;              // EPI_*
+  int act;              // ACT_*
+  int mimic;            // replay the reference's per-op rounding to the model dtype
+  void* out;
+  int ld_out;
+  int single_n;         // >= 0: one expert (E must be 1) with single_n rows in slot single_slot; offsets/slot_of unused
+  int single_slot;
+};
+
+cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
+                                   const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_elems, size_t offA0, size_t offA1,
+                                     const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st);
+int gemm_tc_smem_bytes(int nt, bool dual);
+
+// ---- routing / permutation / combine (route.cu) -----------------------------------------
+struct RouteParams {
+  // inputs
+  const void* x;             // [T,H] model dtype
+  const void* gate_w;        // [E,H] router weight (model dtype for Mixtral, any of bf16/f16/f32 otherwise) or null
+  const void* logits;        // optional precomputed router logits/scores [T,E]
+  int logits_dtype;          // DT_* of `logits`
+  int logits_are_scores;     // 1: `logits` already holds fp32 softmax scores (DeepSeek parity tests)
+  int gate_dtype;            // DT_* of gate_w
+  int T, H, E, k;
+  int dtype;                 // model dtype
+  int router;                // ROUTER_*
+  int n_group, topk_group, norm_topk_prob;
+  float routed_scaling_factor;
+  int seq_len, expert_capacity;   // Switch only
+  // outputs (workspace)
+  float* scores;             // [T,E] fp32 softmax probabilities (optional, may be null)
+  void* logits_out;          // [T,E] router logits in their natural dtype (optional)
+  int* topk_idx;             // [T,k]
+  float* topk_w;             // [T,k]
+  int* row_of;               // [T,k] permuted row of (t,j); -1 if dropped
+  int* perm_token;           // [T*k] source token of each permuted row
+  int* counts;               // [E]
+  int* offsets;              // [E+1]
+  int* chunk_counts;         // [ceil(T/32), E]
+  void* xp;                  // [T*k, H] gathered activations
+  float* y_zero;             // optional fp32 buffer to clear (split-K accumulator), y_zero_elems floats
+  size_t y_zero_elems;
+};
+cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
+// routing from a caller-supplied dense mask (reference compat: ExpertDispatcher::SetInputs + per-expert gather,
+// core/parallel/expert_dispatcher.h:66-70, expert_dispatcher.cpp:274-285)
+cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask /*[T,E]*/, cudaStream_t st);
+
+struct CombineParams {
+  const float* y;          // [rows, H] fp32 expert outputs (permuted row order)
+  const float* y_shared;   // [T, H] fp32 shared-expert output or null
+  const void* x;           // [T,H] (Switch pass-through) or null
+  const int* topk_idx;     // [T,k]
+  const float* topk_w;     // [T,k]
+  const int* row_of;       // [T,k]
+  void* out;               // [T,H] model dtype
+  int T, H, k, dtype, mode;
+};
+cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
+
+// fp32 [rows,H] -> model dtype [rows,H] (compat path: per-expert outputs handed back to Python)
+cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st);
+
+}  // namespace b2m

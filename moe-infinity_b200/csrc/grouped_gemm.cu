@@ -1,0 +1,403 @@
+// grouped_gemm.cu -- K3/K4: grouped (per-expert segmented) expert GEMMs on tcgen05 tensor cores.
+//
+// Replaces the per-expert ATen loop of the reference, core/parallel/expert_module.cpp:171-175 (Mixtral),
+// :200-203 (DeepSeek), :31-35 (Switch): `matmul(act(matmul(x, w1^T)) * matmul(x, w3^T), w2^T)` issued as
+// 3 cuBLAS GEMMs + 2 elementwise kernels per expert from C++ worker threads
+// (core/parallel/expert_dispatcher.cpp:309-395).
+//
+// Design (decode-first, "swap-AB"): the expert weight matrix [M rows, K] (nn.Linear layout, K-major) is the
+// UMMA *A* operand (M = 128 rows per tile, streamed once from HBM by TMA), the expert's tokens
+// [n_e, K] are the UMMA *B* operand (N = NT in {16,32,64,128} tokens).  D[128, NT] accumulates in TMEM.
+// One persistent CTA per SM walks a device-side tile list derived from the per-expert token offsets the
+// routing kernel produced -- no host sync.  Warp roles: w0 TMA producer, w1 MMA issuer (one lane),
+// w2 TMEM allocator, w4..7 epilogue (tcgen05.ld -> activation -> global).
+//   DUAL  = gate and up projections share the token tile and are fused with act(g)*u in the epilogue.
+//   !DUAL = single projection: activation epilogue (Switch wi + ReLU) or linear fp32 output
+//           (down projection), optionally split-K with fp32 red.add.
+#include "b2m_common.cuh"
+#include "b2m_internal.h"
+
+namespace b2m {
+
+constexpr int BLOCK_M = 128;   // weight rows per tile  (UMMA M)
+constexpr int BLOCK_K = 64;    // 64 x 16-bit = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int GEMM_THREADS = 256;
+constexpr int MAX_E = 256;
+constexpr int SMEM_BUDGET = 216 * 1024;
+
+template <int NT, bool DUAL>
+struct GemmCfg {
+  static constexpr int B_TILE_BYTES = NT * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (DUAL ? 2 : 1) * A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
+  static constexpr int ACC_COLS = (DUAL ? 2 : 1) * NT;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    (MAX_E + 1) * 4 * 2 /*tile_start, offsets*/ + MAX_E * 4 /*slots*/;
+  static_assert(TMEM_COLS_RAW <= 512, "TMEM overflow");
+  static_assert(STAGES >= 2, "need >=2 stages");
+};
+
+struct TileInfo {
+  int e, slot, m0, row0, ncols, kb_begin, kb_end;
+};
+
+// Per-CTA tile walker: tile ids ascend, so the expert cursor only moves forward.
+struct TileWalker {
+  const int* tile_start;  // smem [E+1]
+  const int* offs;        // smem [E+1]
+  const int* slots;       // smem [E]
+  int E, NTv, ksplit, kblocks, e_cur;
+  __device__ __forceinline__ bool get(int tile, TileInfo& t) {
+    if (tile >= tile_start[E]) return false;
+    while (tile >= tile_start[e_cur + 1]) ++e_cur;
+    const int e = e_cur;
+    const int n_e = offs[e + 1] - offs[e];
+    const int n_tiles = (n_e + NTv - 1) / NTv;
+    int local = tile - tile_start[e];
+    const int per_m = n_tiles * ksplit;
+    const int m = local / per_m;
+    local -= m * per_m;
+    const int n = local / ksplit;
+    const int s = local - n * ksplit;
+    const int kb_per = (kblocks + ksplit - 1) / ksplit;
+    t.e = e;
+    t.slot = slots[e];
+    t.m0 = m * BLOCK_M;
+    t.row0 = offs[e] + n * NTv;
+    t.ncols = min(NTv, n_e - n * NTv);
+    t.kb_begin = s * kb_per;
+    t.kb_end = min(kblocks, t.kb_begin + kb_per);
+    return true;
+  }
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_SILU) return x / (1.0f + expf(-x));
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return x;
+}
+
+template <int NT, bool DUAL, int DT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                       const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<NT, DUAL>;
+  extern __shared__ uint8_t smem_raw[];
+  // carve shared memory: [stages | barriers | tmem ptr | tile tables]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + Cfg::ACC_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::ACC_STAGES);
+  int* tile_start = reinterpret_cast<int*>(tmem_ptr_smem + 2);
+  int* offs = tile_start + (MAX_E + 1);
+  int* slots = offs + (MAX_E + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int E = p.E;
+  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+
+  // ---- one-time setup -------------------------------------------------------------
+  if (p.single_n >= 0) {
+    if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
+  } else {
+    for (int i = threadIdx.x; i <= E; i += GEMM_THREADS) offs[i] = p.offsets[i];
+    for (int i = threadIdx.x; i < E; i += GEMM_THREADS) slots[i] = p.slot_of[i];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (DUAL) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      tile_start[e] = acc;
+      const int n_e = offs[e + 1] - offs[e];
+      if (n_e > 0 && slots[e] >= 0) acc += m_tiles * ((n_e + NT - 1) / NT) * p.ksplit;
+    }
+    tile_start[E] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0};
+  TileInfo t;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA0 = stage_base + stage * Cfg::STAGE_BYTES;
+          uint8_t* sA1 = sA0 + A_TILE_BYTES;
+          uint8_t* sB = sA0 + (DUAL ? 2 : 1) * A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          // weights are streamed exactly once per (tile): evict-first; tokens are re-read by every m-tile: keep
+          tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, CACHE_EVICT_FIRST);
+          if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0, t.slot, CACHE_EVICT_FIRST);
+          tma_load_2d(&tmB, &full_bar[stage], sB, kb * BLOCK_K, t.row0, CACHE_EVICT_LAST);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    constexpr uint32_t idesc = make_idesc_f16(DT, BLOCK_M, NT);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * Cfg::ACC_COLS;
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint32_t a1 = a0 + A_TILE_BYTES;
+          const uint32_t b = a0 + (DUAL ? 2 : 1) * A_TILE_BYTES;
+          const uint64_t da0 = make_kmajor_sw128_desc(a0);
+          const uint64_t da1 = make_kmajor_sw128_desc(a1);
+          const uint64_t db = make_kmajor_sw128_desc(b);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t accum = (kb > t.kb_begin || k > 0) ? 1u : 0u;
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance start address inside the SW128 atom
+            tc_mma_f16(d0, da0 + koff, db + koff, idesc, accum);
+            if (DUAL) tc_mma_f16(d0 + NT, da1 + koff, db + koff, idesc, accum);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;         // weight row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
+      const int m = t.m0 + r;
+      const bool row_ok = m < p.M;
+      for (int c0 = 0; c0 < t.ncols; c0 += 16) {   // warp-uniform trip count
+        uint32_t vg[16], vu[16];
+        tmem_ld_x16(taddr + c0, vg);
+        if (DUAL) tmem_ld_x16(taddr + NT + c0, vu);
+        tmem_ld_wait();
+        if (p.epi == EPI_LINEAR_F32) {
+          float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (row_ok && c0 + j < t.ncols) {
+              float* dst = out + (size_t)(t.row0 + c0 + j) * p.ld_out + m;
+              const float v = __uint_as_float(vg[j]);
+              if (p.ksplit > 1) atomicAdd(dst, v); else *dst = v;
+            }
+          }
+        } else {
+          uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (row_ok && c0 + j < t.ncols) {
+              float g = __uint_as_float(vg[j]);
+              float h;
+              if (DUAL) {
+                float u = __uint_as_float(vu[j]);
+                if (p.mimic) {   // reference rounding chain: each ATen op rounds to the model dtype
+                  g = round_dt<DT>(g);
+                  u = round_dt<DT>(u);
+                  h = round_dt<DT>(act_apply(g, p.act)) * u;
+                } else {
+                  h = act_apply(g, p.act) * u;
+                }
+              } else {
+                if (p.mimic) g = round_dt<DT>(g);
+                h = act_apply(g, p.act);
+              }
+              out[(size_t)(t.row0 + c0 + j) * p.ld_out + m] = Half16<DT>::from_f(h);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Plain CUDA-core grouped GEMM with identical semantics (debug / bring-up cross-check only;
+// selected with B2M_GEMM_IMPL=simt).  One warp per output element.
+// --------------------------------------------------------------------------------------
+template <int DT>
+__global__ void grouped_gemm_simt_kernel(const uint16_t* __restrict__ arena, size_t slot_elems, size_t offA0,
+                                         size_t offA1, const uint16_t* __restrict__ B, int ldb, GemmParams p,
+                                         int dual) {
+  const bool single = p.single_n >= 0;
+  const int total_rows = single ? p.single_n : p.offsets[p.E];
+  const long long nout = (long long)total_rows * p.M;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long o = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); o < nout;
+       o += (long long)gridDim.x * warps_per_block) {
+    const int row = (int)(o / p.M);
+    const int m = (int)(o % p.M);
+    int e = 0;
+    if (!single) while (e + 1 < p.E && row >= p.offsets[e + 1]) ++e;
+    const int slot = single ? p.single_slot : p.slot_of[e];
+    if (slot < 0) continue;
+    const uint16_t* a0 = arena + (size_t)slot * slot_elems + offA0 + (size_t)m * p.K;
+    const uint16_t* a1 = arena + (size_t)slot * slot_elems + offA1 + (size_t)m * p.K;
+    const uint16_t* b = B + (size_t)row * ldb;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = lane; k < p.K; k += 32) {
+      const float x = Half16<DT>::to_f(b[k]);
+      s0 += Half16<DT>::to_f(a0[k]) * x;
+      if (dual) s1 += Half16<DT>::to_f(a1[k]) * x;
+    }
+    for (int d = 16; d; d >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    }
+    if (lane == 0) {
+      if (p.epi == EPI_LINEAR_F32) {
+        reinterpret_cast<float*>(p.out)[(size_t)row * p.ld_out + m] = s0;
+      } else {
+        float g = s0, h;
+        if (dual) {
+          float u = s1;
+          if (p.mimic) { g = round_dt<DT>(g); u = round_dt<DT>(u); h = round_dt<DT>(act_apply(g, p.act)) * u; }
+          else h = act_apply(g, p.act) * u;
+        } else {
+          if (p.mimic) g = round_dt<DT>(g);
+          h = act_apply(g, p.act);
+        }
+        reinterpret_cast<uint16_t*>(p.out)[(size_t)row * p.ld_out + m] = Half16<DT>::from_f(h);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// host launchers
+// --------------------------------------------------------------------------------------
+template <int NT, bool DUAL, int DT>
+static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+                             int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<NT, DUAL>;
+  auto kern = grouped_gemm_tc_kernel<NT, DUAL, DT>;
+  static bool attr_done = false;   // per-instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, p);
+  return cudaGetLastError();
+}
+
+template <int DT>
+static cudaError_t dispatch_nt(int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                               const GemmParams& p, int grid, cudaStream_t st) {
+#define B2M_CASE(N)                                                                 \
+  case N:                                                                           \
+    return dual ? launch_tc<N, true, DT>(a0, a1, b, p, grid, st) : launch_tc<N, false, DT>(a0, a1, b, p, grid, st);
+  switch (nt) {
+    B2M_CASE(16)
+    B2M_CASE(32)
+    B2M_CASE(64)
+    B2M_CASE(128)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef B2M_CASE
+}
+
+cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
+                                   const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st) {
+  if (p.E > MAX_E) return cudaErrorInvalidValue;
+  if (dtype == DT_BF16) return dispatch_nt<DT_BF16>(nt, dual, a0, a1, b, p, grid, st);
+  if (dtype == DT_F16) return dispatch_nt<DT_F16>(nt, dual, a0, a1, b, p, grid, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_elems, size_t offA0, size_t offA1,
+                                     const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st) {
+  const int grid = 148 * 8;
+  if (dtype == DT_BF16)
+    grouped_gemm_simt_kernel<DT_BF16><<<grid, 256, 0, st>>>((const uint16_t*)arena, slot_elems, offA0, offA1,
+                                                             (const uint16_t*)B, ldb, p, dual ? 1 : 0);
+  else if (dtype == DT_F16)
+    grouped_gemm_simt_kernel<DT_F16><<<grid, 256, 0, st>>>((const uint16_t*)arena, slot_elems, offA0, offA1,
+                                                            (const uint16_t*)B, ldb, p, dual ? 1 : 0);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+int gemm_tc_smem_bytes(int nt, bool dual) {
+  switch (nt) {
+    case 16: return dual ? GemmCfg<16, true>::SMEM_BYTES : GemmCfg<16, false>::SMEM_BYTES;
+    case 32: return dual ? GemmCfg<32, true>::SMEM_BYTES : GemmCfg<32, false>::SMEM_BYTES;
+    case 64: return dual ? GemmCfg<64, true>::SMEM_BYTES : GemmCfg<64, false>::SMEM_BYTES;
+    case 128: return dual ? GemmCfg<128, true>::SMEM_BYTES : GemmCfg<128, false>::SMEM_BYTES;
+  }
+  return -1;
+}
+
+}  // namespace b2m

@@ -1,0 +1,716 @@
+// route.cu -- K0/K1/K2/K5: router gate, fused softmax+top-k, token index sort/permute, weighted combine.
+//
+// Replaces, with zero host synchronisation:
+//   * moe_infinity/models/mixtral.py:46-65        gate GEMM, softmax, topk, renorm, dense [T,E] mask build
+//   * modeling_deepseek.py:463-512 + deepseek.py:76-91   MoEGate and its mask build
+//   * distributed/expert_executor.py:34-44         per-expert token counts (.cpu() sync in the reference)
+//   * core/parallel/expert_dispatcher.cpp:274-285  per-expert boolean-mask gather (nonzero + index_select)
+//   * mixtral.py:96-101 / deepseek.py:123-136 / switch_transformers.py:99-109   per-expert masked combine
+// Instead of dense masks the kernels emit: top-k ids/weights, per-expert counts + offsets, a stable
+// (ascending token order inside each expert, the reference's gather order) permutation, and the gathered
+// activation rows, written with 16-byte vector stores.
+#include "b2m_common.cuh"
+#include "b2m_internal.h"
+
+namespace b2m {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int CHUNK = 32;                      // tokens per ranking chunk (one warp, lane == token)
+constexpr int TOK_PER_BLOCK = CHUNK * RT_WARPS;  // 256
+constexpr int MAX_K = 8;
+constexpr int MAX_PL = 8;                      // experts per lane  -> E <= 256
+constexpr int FUSED_MAX_T = TOK_PER_BLOCK;     // single-CTA fused path
+
+__device__ __forceinline__ float load_as_float(const void* p, size_t i, int dt) {
+  if (dt == DT_F32) return reinterpret_cast<const float*>(p)[i];
+  const uint16_t b = reinterpret_cast<const uint16_t*>(p)[i];
+  return dt == DT_BF16 ? Half16<DT_BF16>::to_f(b) : Half16<DT_F16>::to_f(b);
+}
+__device__ __forceinline__ float round_to(float f, int dt) {
+  if (dt == DT_BF16) return round_dt<DT_BF16>(f);
+  if (dt == DT_F16) return round_dt<DT_F16>(f);
+  return f;
+}
+
+// (value desc, index asc) arg-max across the warp; every lane returns the winner.
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, d);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// --------------------------------------------------------------------------------------
+// K0: router gate for one token (one warp): logits[e] = <x[t], Wg[e]> with fp32 accumulation.
+// Mixtral: nn.Linear in model dtype -> result rounded to the model dtype (mixtral.py:46).
+// DeepSeek/Switch: fp32 linear on upcast operands (modeling_deepseek.py:467-471).
+// --------------------------------------------------------------------------------------
+__device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[E] smem, this warp*/) {
+  const int lane = threadIdx.x & 31;
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
+  for (int e0 = 0; e0 < p.E; e0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int h = lane * 8; h < p.H; h += 32 * 8) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(x + h);
+      const uint16_t* xs = reinterpret_cast<const uint16_t*>(&xv);
+      float xf[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xf[j] = p.dtype == DT_BF16 ? Half16<DT_BF16>::to_f(xs[j]) : Half16<DT_F16>::to_f(xs[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (e0 + i < p.E) {
+          const size_t wo = (size_t)(e0 + i) * p.H + h;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], load_as_float(p.gate_w, wo + j, p.gate_dtype), acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (lane == 0 && e0 + i < p.E) s_logits[e0 + i] = (p.router == ROUTER_MIXTRAL) ? round_to(s, p.dtype) : s;
+    }
+  }
+  __syncwarp();
+}
+
+// --------------------------------------------------------------------------------------
+// K1: softmax + top-k (+renorm) for one token (one warp, lane owns experts lane, lane+32, ...)
+// --------------------------------------------------------------------------------------
+__device__ void route_token_warp(const RouteParams& p, int t, const float* s_in /*[E] logits or scores (smem)*/,
+                                 bool in_are_scores, float* s_scr /*[E] smem scratch*/, int* out_idx, float* out_w) {
+  const int lane = threadIdx.x & 31;
+  const int E = p.E;
+  float v[MAX_PL];
+  // --- softmax in fp32: exp(x - max) / sum  (F.softmax(dtype=float), mixtral.py:48; modeling_deepseek.py:473)
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAX_PL; ++i) {
+    const int e = lane + 32 * i;
+    v[i] = e < E ? s_in[e] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  if (!in_are_scores) {
+    m = warp_max(m);
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane + 32 * i;
+      v[i] = e < E ? expf(v[i] - m) : 0.f;
+      z += v[i];
+    }
+    z = warp_sum(z);
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) v[i] = __fdiv_rn(v[i], z);
+  }
+  if (p.scores) {
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane + 32 * i;
+      if (e < E) p.scores[(size_t)t * E + e] = v[i];
+    }
+  }
+  if (p.router == ROUTER_SWITCH_TOP1) {
+    // router_probs are cast to the input dtype before argmax/max (HF 4.x Top1Router._compute_router_probabilities)
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) v[i] = round_to(v[i], p.dtype);
+  }
+  if (p.router == ROUTER_DEEPSEEK_GROUP) {
+    // modeling_deepseek.py:484-505: keep the topk_group groups with the largest max score, zero the rest
+    const int gsz = E / p.n_group;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane + 32 * i;
+      if (e < E) s_scr[e] = v[i];
+    }
+    __syncwarp();
+    float gmax = -INFINITY;
+    if (lane < p.n_group)
+      for (int j = 0; j < gsz; ++j) gmax = fmaxf(gmax, s_scr[lane * gsz + j]);
+    uint32_t allowed = 0;
+    for (int r = 0; r < p.topk_group; ++r) {
+      float bv = gmax;
+      int bi = lane < p.n_group ? lane : 0x7fffffff;
+      if (lane >= p.n_group) bv = -INFINITY;
+      warp_argmax(bv, bi);
+      allowed |= 1u << bi;
+      if (lane == bi) gmax = -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane + 32 * i;
+      if (e < E && !((allowed >> (e / gsz)) & 1u)) v[i] = 0.0f;   // masked_fill(~score_mask, 0.0)
+    }
+    __syncwarp();
+  }
+  // --- top-k, ties -> lowest expert index
+  uint32_t taken = 0;
+  float sel_v[MAX_K];
+  int sel_i[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) {
+    if (j < p.k) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < MAX_PL; ++i) {
+        const int e = lane + 32 * i;
+        if (e < E && !((taken >> i) & 1u) && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = e; }
+      }
+      warp_argmax(bv, bi);
+      sel_v[j] = bv;
+      sel_i[j] = bi;
+      if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
+    }
+  }
+  // --- weights
+  float denom = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j)
+    if (j < p.k) denom = __fadd_rn(denom, sel_v[j]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) {
+      if (j < p.k) {
+        float w;
+        if (p.router == ROUTER_MIXTRAL) {
+          w = round_to(__fdiv_rn(sel_v[j], denom), p.dtype);                       // mixtral.py:52-54
+        } else if (p.router == ROUTER_SWITCH_TOP1) {
+          w = sel_v[j];
+        } else if (p.k > 1 && p.norm_topk_prob) {
+          w = __fdiv_rn(sel_v[j], __fadd_rn(denom, 1e-20f));                        // modeling_deepseek.py:508-510
+        } else {
+          w = __fmul_rn(sel_v[j], p.routed_scaling_factor);                        // :512
+        }
+        out_idx[j] = sel_i[j];
+        out_w[j] = w;
+      }
+    }
+  }
+}
+
+// lane == token: does this lane's token route to expert e ?
+__device__ __forceinline__ bool lane_has(const int (&idx)[MAX_K], int k, int e) {
+  bool h = false;
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) h |= (j < k && idx[j] == e);
+  return h;
+}
+
+// Per-chunk per-expert counts (lane == token).  counts_out[e] for e in [0,E)
+__device__ void chunk_count_warp(const int* topk_idx, int t0, int T, int k, int E, int* counts_out) {
+  const int lane = threadIdx.x & 31;
+  const int t = t0 + lane;
+  int idx[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < T && j < k) ? topk_idx[(size_t)t * k + j] : -1;
+  for (int e0 = 0; e0 < E; e0 += 32) {
+    int mine = 0;
+    for (int ee = 0; ee < 32 && e0 + ee < E; ++ee) {
+      const uint32_t b = __ballot_sync(0xffffffffu, lane_has(idx, k, e0 + ee));
+      if (lane == ee) mine = __popc(b);
+    }
+    if (e0 + lane < E) counts_out[e0 + lane] = mine;
+  }
+}
+
+// Destination rows for the tokens of one chunk (lane == token), stable inside each expert.
+// base_of(e) = first permuted row available to this chunk for expert e.
+template <class BaseFn>
+__device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, int* s_rows /*[CHUNK*k] smem*/) {
+  const int lane = threadIdx.x & 31;
+  const int t = t0 + lane;
+  const int k = p.k;
+  int idx[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < p.T && j < k) ? p.topk_idx[(size_t)t * k + j] : -1;
+  int dest[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) dest[j] = -1;
+  for (int e = 0; e < p.E; ++e) {
+    const bool h = lane_has(idx, k, e);
+    const uint32_t b = __ballot_sync(0xffffffffu, h);
+    if (b == 0) continue;
+    if (h) {
+      const int row = base_of(e) + __popc(b & ((1u << lane) - 1u));
+#pragma unroll
+      for (int j = 0; j < MAX_K; ++j)
+        if (j < k && idx[j] == e) dest[j] = row;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) {
+    if (j < k) {
+      s_rows[lane * k + j] = dest[j];
+      if (t < p.T) {
+        p.row_of[(size_t)t * k + j] = dest[j];
+        if (dest[j] >= 0) p.perm_token[dest[j]] = t;
+      }
+    }
+  }
+}
+
+// Copy gathered rows x[t] -> xp[row] with 16-byte vectors; `nrows` (token,slot) pairs starting at token t0.
+__device__ void copy_rows_block(const RouteParams& p, int t0, int npairs, const int* s_rows, int warp0, int nwarps) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) - warp0;
+  const int vec_per_row = p.H / 8;   // uint4 = 8 x 16-bit
+  for (int i = warp; i < npairs; i += nwarps) {
+    const int row = s_rows[i];
+    const int t = t0 + i / p.k;
+    if (row < 0 || t >= p.T) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+    int v = lane;
+    for (; v + 96 < vec_per_row; v += 128) {   // 4 independent 16 B loads in flight per lane
+      const uint4 a = src[v], b = src[v + 32], c = src[v + 64], d = src[v + 96];
+      dst[v] = a; dst[v + 32] = b; dst[v + 64] = c; dst[v + 96] = d;
+    }
+    for (; v < vec_per_row; v += 32) dst[v] = src[v];
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Multi-CTA path (large T): route -> scan -> permute
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_THREADS) route_topk_kernel(const RouteParams p) {
+  __shared__ float s_logits[RT_WARPS][MAX_PL * 32];
+  __shared__ float s_scr[RT_WARPS][MAX_PL * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tb = blockIdx.x * TOK_PER_BLOCK;
+  for (int i = warp; i < TOK_PER_BLOCK; i += RT_WARPS) {
+    const int t = tb + i;
+    if (t >= p.T) break;
+    bool scores_in = false;
+    if (p.logits) {
+      for (int e = lane; e < p.E; e += 32) s_logits[warp][e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
+      scores_in = p.logits_are_scores != 0;
+      __syncwarp();
+    } else {
+      gate_token_warp(p, t, s_logits[warp]);
+    }
+    if (p.logits_out && !scores_in) {
+      for (int e = lane; e < p.E; e += 32) {
+        const float lv = s_logits[warp][e];
+        if (p.router == ROUTER_MIXTRAL) {
+          reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
+              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
+        } else {
+          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
+        }
+      }
+    }
+    route_token_warp(p, t, s_logits[warp], scores_in, s_scr[warp], p.topk_idx + (size_t)t * p.k,
+                     p.topk_w + (size_t)t * p.k);
+    __syncwarp();
+  }
+  if (p.router == ROUTER_SWITCH_TOP1) return;   // capacity pass + counts run in a separate kernel
+  __threadfence_block();
+  __syncthreads();
+  // per-chunk counts
+  const int chunk = blockIdx.x * RT_WARPS + warp;
+  const int t0 = chunk * CHUNK;
+  if (t0 < p.T) chunk_count_warp(p.topk_idx, t0, p.T, p.k, p.E, p.chunk_counts + (size_t)chunk * p.E);
+}
+
+// Switch capacity (cumsum priority <= capacity, per batch row), then per-chunk counts.  One block per batch row.
+__global__ void __launch_bounds__(RT_THREADS) switch_capacity_kernel(const RouteParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int S = p.seq_len;
+  // warp w handles experts w, w+8, ...; walks the row in token order
+  for (int e = warp; e < p.E; e += RT_WARPS) {
+    int running = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const int t = b * S + s;
+      const bool h = s < S && p.topk_idx[t] == e;
+      const uint32_t m = __ballot_sync(0xffffffffu, h);
+      if (h) {
+        const int prio = running + __popc(m & ((1u << lane) - 1u)) + 1;   // cumsum is 1-based
+        if (prio > p.expert_capacity) p.topk_idx[t] = -1;                 // dropped: passes through unchanged
+      }
+      running += __popc(m);
+    }
+  }
+}
+__global__ void __launch_bounds__(RT_THREADS) chunk_count_kernel(const RouteParams p) {
+  const int warp = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RT_WARPS + warp;
+  const int t0 = chunk * CHUNK;
+  if (t0 < p.T) chunk_count_warp(p.topk_idx, t0, p.T, p.k, p.E, p.chunk_counts + (size_t)chunk * p.E);
+}
+
+// dense mask -> per-token expert list (ascending expert id, -1 padded), weights = 1
+__global__ void __launch_bounds__(RT_THREADS) mask_to_topk_kernel(const RouteParams p, const uint8_t* __restrict__ mask) {
+  const int t = blockIdx.x * RT_THREADS + threadIdx.x;
+  if (t >= p.T) return;
+  int n = 0;
+  for (int e = 0; e < p.E; ++e) {
+    if (mask[(size_t)t * p.E + e] && n < p.k) {
+      p.topk_idx[(size_t)t * p.k + n] = e;
+      p.topk_w[(size_t)t * p.k + n] = 1.0f;
+      ++n;
+    }
+  }
+  for (; n < p.k; ++n) {
+    p.topk_idx[(size_t)t * p.k + n] = -1;
+    p.topk_w[(size_t)t * p.k + n] = 0.0f;
+  }
+}
+
+// exclusive scan: chunk_counts[c][e] -> first row of (chunk c, expert e) relative to the expert start;
+// counts[e], offsets[e].  Single block, thread == expert.
+__global__ void __launch_bounds__(256) route_scan_kernel(const RouteParams p, int nchunks) {
+  __shared__ int s_tot[MAX_PL * 32];
+  const int e = threadIdx.x;
+  if (e < p.E) {
+    int run = 0;
+    int c = 0;
+    for (; c + 8 <= nchunks; c += 8) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p.chunk_counts[(size_t)(c + u) * p.E + e];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        p.chunk_counts[(size_t)(c + u) * p.E + e] = run;
+        run += v[u];
+      }
+    }
+    for (; c < nchunks; ++c) {
+      const int v = p.chunk_counts[(size_t)c * p.E + e];
+      p.chunk_counts[(size_t)c * p.E + e] = run;
+      run += v;
+    }
+    s_tot[e] = run;
+    p.counts[e] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < p.E; ++i) {
+      p.offsets[i] = acc;
+      acc += s_tot[i];
+    }
+    p.offsets[p.E] = acc;
+  }
+}
+
+// one block per group of RT_WARPS chunks; warp w ranks chunk w, then all warps copy that block's rows
+__global__ void __launch_bounds__(RT_THREADS) route_permute_kernel(const RouteParams p) {
+  __shared__ int s_rows[RT_WARPS][CHUNK * MAX_K];
+  const int warp = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * RT_WARPS + warp;
+  const int t0 = chunk * CHUNK;
+  if (t0 < p.T) {
+    const int* cb = p.chunk_counts + (size_t)chunk * p.E;
+    chunk_rank_warp(p, t0, [&](int e) { return p.offsets[e] + cb[e]; }, s_rows[warp]);
+  }
+  __syncthreads();
+  for (int w = 0; w < RT_WARPS; ++w) {
+    const int tw = (blockIdx.x * RT_WARPS + w) * CHUNK;
+    if (tw >= p.T) break;
+    copy_rows_block(p, tw, CHUNK * p.k, s_rows[w], 0, RT_WARPS);
+  }
+  // clear the split-K accumulator (grid-stride over the whole grid)
+  if (p.y_zero) {
+    float4* z = reinterpret_cast<float4*>(p.y_zero);
+    const size_t n4 = p.y_zero_elems / 4;
+    for (size_t i = (size_t)blockIdx.x * RT_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * RT_THREADS)
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Fused single-CTA path (decode, T <= 256): gate + softmax/top-k + counts + scan + permute in ONE launch
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_THREADS) route_fused_kernel(const RouteParams p, const uint8_t* __restrict__ mask) {
+  __shared__ float s_logits[RT_WARPS][MAX_PL * 32];
+  __shared__ float s_scr[RT_WARPS][MAX_PL * 32];
+  __shared__ int s_cnt[RT_WARPS][MAX_PL * 32];   // per-chunk counts -> exclusive bases
+  __shared__ int s_off[MAX_PL * 32 + 1];
+  __shared__ int s_rows[RT_WARPS][CHUNK * MAX_K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.T + CHUNK - 1) / CHUNK;
+
+  if (mask) {
+    // compat path: routing decisions come from the caller's dense mask
+    for (int t = threadIdx.x; t < p.T; t += RT_THREADS) {
+      int n = 0;
+      for (int e = 0; e < p.E; ++e)
+        if (mask[(size_t)t * p.E + e] && n < p.k) {
+          p.topk_idx[(size_t)t * p.k + n] = e;
+          p.topk_w[(size_t)t * p.k + n] = 1.0f;
+          ++n;
+        }
+      for (; n < p.k; ++n) { p.topk_idx[(size_t)t * p.k + n] = -1; p.topk_w[(size_t)t * p.k + n] = 0.0f; }
+    }
+  } else {
+    for (int t = warp; t < p.T; t += RT_WARPS) {
+      bool scores_in = false;
+      if (p.logits) {
+        for (int e = lane; e < p.E; e += 32) s_logits[warp][e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
+        scores_in = p.logits_are_scores != 0;
+        __syncwarp();
+      } else {
+        gate_token_warp(p, t, s_logits[warp]);
+      }
+      if (p.logits_out && !scores_in) {
+        for (int e = lane; e < p.E; e += 32) {
+          const float lv = s_logits[warp][e];
+          if (p.router == ROUTER_MIXTRAL)
+            reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
+                p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
+          else
+            reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
+        }
+      }
+      route_token_warp(p, t, s_logits[warp], scores_in, s_scr[warp], p.topk_idx + (size_t)t * p.k,
+                       p.topk_w + (size_t)t * p.k);
+      __syncwarp();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (p.router == ROUTER_SWITCH_TOP1 && !mask) {
+    // capacity: one batch row after another (T <= 256: cheap)
+    const int S = p.seq_len;
+    const int B = p.T / S;
+    for (int b = 0; b < B; ++b) {
+      for (int e = warp; e < p.E; e += RT_WARPS) {
+        int running = 0;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+          const int s = s0 + lane;
+          const int t = b * S + s;
+          const bool h = s < S && p.topk_idx[t] == e;
+          const uint32_t m = __ballot_sync(0xffffffffu, h);
+          if (h && running + __popc(m & ((1u << lane) - 1u)) + 1 > p.expert_capacity) p.topk_idx[t] = -1;
+          running += __popc(m);
+        }
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (warp < nchunks) chunk_count_warp(p.topk_idx, warp * CHUNK, p.T, p.k, p.E, s_cnt[warp]);
+  __syncthreads();
+  if (threadIdx.x < p.E) {
+    const int e = threadIdx.x;
+    int run = 0;
+    for (int c = 0; c < nchunks; ++c) { const int v = s_cnt[c][e]; s_cnt[c][e] = run; run += v; }
+    s_scr[0][e] = __int_as_float(run);
+    p.counts[e] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < p.E; ++e) { s_off[e] = acc; p.offsets[e] = acc; acc += __float_as_int(s_scr[0][e]); }
+    s_off[p.E] = acc;
+    p.offsets[p.E] = acc;
+  }
+  __syncthreads();
+  if (warp < nchunks) {
+    const int* cb = s_cnt[warp];
+    chunk_rank_warp(p, warp * CHUNK, [&](int e) { return s_off[e] + cb[e]; }, s_rows[warp]);
+  }
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) copy_rows_block(p, c * CHUNK, CHUNK * p.k, s_rows[c], 0, RT_WARPS);
+  if (p.y_zero) {
+    float4* z = reinterpret_cast<float4*>(p.y_zero);
+    const size_t n4 = p.y_zero_elems / 4;
+    for (size_t i = threadIdx.x; i < n4; i += RT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+static bool route_args_ok(const RouteParams& p) {
+  return p.E >= 1 && p.E <= MAX_PL * 32 && p.k >= 1 && p.k <= MAX_K && p.k <= p.E && p.H % 8 == 0 && p.T >= 0 &&
+         (p.router != ROUTER_DEEPSEEK_GROUP || (p.n_group >= 1 && p.n_group <= 32 && p.E % p.n_group == 0 &&
+                                                 p.topk_group >= 1 && p.topk_group <= p.n_group)) &&
+         (p.router != ROUTER_SWITCH_TOP1 || (p.k == 1 && p.seq_len > 0 && p.T % p.seq_len == 0));
+}
+
+cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
+  if (!route_args_ok(p)) return cudaErrorInvalidValue;
+  if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
+  if (p.T <= FUSED_MAX_T) {
+    route_fused_kernel<<<1, RT_THREADS, 0, st>>>(p, nullptr);
+    return cudaGetLastError();
+  }
+  const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
+  const int nchunks = (p.T + CHUNK - 1) / CHUNK;
+  route_topk_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  if (p.router == ROUTER_SWITCH_TOP1) {
+    switch_capacity_kernel<<<p.T / p.seq_len, RT_THREADS, 0, st>>>(p);
+    chunk_count_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  }
+  route_scan_kernel<<<1, 256, 0, st>>>(p, nchunks);
+  route_permute_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cudaStream_t st) {
+  if (!route_args_ok(p) || mask == nullptr) return cudaErrorInvalidValue;
+  if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
+  if (p.T <= FUSED_MAX_T) {
+    route_fused_kernel<<<1, RT_THREADS, 0, st>>>(p, mask);
+    return cudaGetLastError();
+  }
+  const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
+  const int nchunks = (p.T + CHUNK - 1) / CHUNK;
+  mask_to_topk_kernel<<<(p.T + RT_THREADS - 1) / RT_THREADS, RT_THREADS, 0, st>>>(p, mask);
+  chunk_count_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  route_scan_kernel<<<1, 256, 0, st>>>(p, nchunks);
+  route_permute_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// K5: un-permute + weighted combine.  One warp-group of lanes shares a token's (row, weight) list by
+// warp shuffle; every lane owns 8 consecutive hidden elements (2 x 16 B fp32 loads per expert row,
+// one 16 B store).  Experts are applied in ascending expert id (the oracle's fixed order).
+// --------------------------------------------------------------------------------------
+constexpr int CB_THREADS = 256;
+
+template <int DT>
+__global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams p) {
+  const int t = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int k = p.k;
+  // each warp loads the token's routing list into lanes 0..k-1 and sorts it by expert id via shuffles
+  int my_e = 0x7fffffff, my_row = -1;
+  float my_w = 0.f;
+  if (lane < k) {
+    my_e = p.topk_idx[(size_t)t * k + lane];
+    my_w = p.topk_w[(size_t)t * k + lane];
+    my_row = p.row_of[(size_t)t * k + lane];
+    if (my_e < 0 || my_row < 0) { my_e = 0x7ffffff0 + lane; my_row = -1; }
+  }
+  int rank = 0;
+  for (int j = 0; j < k; ++j) {
+    const int oe = __shfl_sync(0xffffffffu, my_e, j);
+    rank += (oe < my_e) ? 1 : 0;
+  }
+  int rows[MAX_K];
+  float ws[MAX_K];
+#pragma unroll
+  for (int r = 0; r < MAX_K; ++r) {
+    rows[r] = -1;
+    ws[r] = 0.f;
+    if (r < k) {
+      const uint32_t who = __ballot_sync(0xffffffffu, lane < k && rank == r);
+      const int src = __ffs(who) - 1;
+      rows[r] = __shfl_sync(0xffffffffu, my_row, src);
+      ws[r] = __shfl_sync(0xffffffffu, my_w, src);
+    }
+  }
+  const int H = p.H;
+  for (int h = (blockIdx.y * CB_THREADS + threadIdx.x) * 8; h < H; h += gridDim.y * CB_THREADS * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < MAX_K; ++r) {
+      if (r < k && rows[r] >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)rows[r] * H + h);
+        const float4 a = src[0], b = src[1];
+        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float w = ws[r];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (p.mode == COMBINE_FP32) {
+            acc[i] = fmaf(y[i], w, acc[i]);
+          } else if (p.mode == COMBINE_MIXTRAL) {
+            // out (model dtype) * weight (model dtype) -> rounded; final += -> rounded  (mixtral.py:98-101)
+            const float prod = round_dt<DT>(__fmul_rn(round_dt<DT>(y[i]), w));
+            acc[i] = any ? round_dt<DT>(__fadd_rn(acc[i], prod)) : prod;
+          } else if (p.mode == COMBINE_DEEPSEEK) {
+            // out (model dtype) * weight (fp32) -> fp32; final(model dtype) += fp32 -> rounded (deepseek.py:125-128)
+            const float prod = __fmul_rn(round_dt<DT>(y[i]), w);
+            acc[i] = round_dt<DT>(__fadd_rn(acc[i], prod));
+          } else {  // COMBINE_SWITCH: next_states[idx] = out (switch_transformers.py:99-101)
+            acc[i] = round_dt<DT>(y[i]);
+          }
+        }
+        any = true;
+      }
+    }
+    if (p.mode == COMBINE_SWITCH) {
+      // dropped tokens keep their input; hidden = router_probs * next_states (switch_transformers.py:81,109)
+      const uint4 xv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * H + h);
+      const uint16_t* xs = reinterpret_cast<const uint16_t*>(&xv);
+      const float prob = p.topk_w[(size_t)t * k];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float nxt = any ? acc[i] : Half16<DT>::to_f(xs[i]);
+        acc[i] = __fmul_rn(prob, nxt);
+      }
+    }
+    if (p.y_shared) {
+      const float4* src = reinterpret_cast<const float4*>(p.y_shared + (size_t)t * H + h);
+      const float4 a = src[0], b = src[1];
+      const float s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (p.mode == COMBINE_FP32) acc[i] += s[i];
+        else acc[i] = round_dt<DT>(__fadd_rn(acc[i], round_dt<DT>(s[i])));   // final + shared_experts(identity), deepseek.py:133-136
+      }
+    }
+    uint4 o;
+    uint16_t* os = reinterpret_cast<uint16_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) os[i] = Half16<DT>::from_f(acc[i]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)t * H + h) = o;
+  }
+}
+
+cudaError_t launch_combine(const CombineParams& p, cudaStream_t st) {
+  if (p.T == 0) return cudaSuccess;
+  if (p.k > MAX_K || p.H % 8 != 0) return cudaErrorInvalidValue;
+  int gy = (p.H + CB_THREADS * 8 - 1) / (CB_THREADS * 8);
+  dim3 grid(p.T, gy);
+  if (p.dtype == DT_BF16) combine_kernel<DT_BF16><<<grid, CB_THREADS, 0, st>>>(p);
+  else if (p.dtype == DT_F16) combine_kernel<DT_F16><<<grid, CB_THREADS, 0, st>>>(p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+template <int DT>
+__global__ void cast_rows_kernel(const float* __restrict__ y, uint16_t* __restrict__ out, size_t n) {
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (size_t)gridDim.x * blockDim.x * 8) {
+    const float4 a = *reinterpret_cast<const float4*>(y + i), b = *reinterpret_cast<const float4*>(y + i + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 o;
+    uint16_t* os = reinterpret_cast<uint16_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) os[j] = Half16<DT>::from_f(v[j]);
+    *reinterpret_cast<uint4*>(out + i) = o;
+  }
+}
+
+cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (n % 8) return cudaErrorInvalidValue;
+  const int blocks = (int)((n / 8 + 255) / 256 < 148 * 8 ? (n / 8 + 255) / 256 : 148 * 8);
+  if (dtype == DT_BF16) cast_rows_kernel<DT_BF16><<<blocks, 256, 0, st>>>(y, (uint16_t*)out, n);
+  else if (dtype == DT_F16) cast_rows_kernel<DT_F16><<<blocks, 256, 0, st>>>(y, (uint16_t*)out, n);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace b2m
