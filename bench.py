@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s + p50 per-token latency of the MoE dispatch hot path, Mixtral-8x7B shapes.
+
+Contract (see task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.
+
+Workload (N=1, BASELINE.json configs[1]): Mixtral-8x7B bf16, random-init N(0,0.02^2) weights, 32 MoE layers,
+8 experts, top-2, H=4096, I=14336; decode batch 8 => T=8 tokens enter every MoE block per step; all 256
+experts HBM resident (90.2 GB).  A "step" = one pass of the hot path (router gate + softmax/top-k + permute +
+grouped gate/up GEMM with fused SwiGLU + grouped down GEMM + weighted combine) over the 32 layers for one batch
+of synthetic hidden states (the attention between MoE blocks is outside the path).
+  value : whole-job tokens/s with inputs resident in HBM, the 32-layer step replayed as one CUDA graph.
+  e2e   : same metric through the public Python API (MoEEngine.forward per layer) with HOST buffers: the step's
+          inputs are copied from pinned host memory and its outputs copied back inside the timed region.
+  roofline : dominant kernel = grouped gate/up GEMM (K3, 2/3 of the weight bytes), timed with CUDA events on
+          its launch stream; algorithmic bytes counted from the actual routing of the timed inputs.
+  cpu_baseline : the oracle port (oracle/moe_oracle.py, the reference's per-expert ATen loop) on the host cores
+          for a bounded sample (one full-size layer, repeated) -- also used as a full-size parity check.
+--impl reference times that oracle port only (kind "port": the reference's own native engine needs libtorch +
+a GPU and its Python package does not import in this image).
+N>1: expert parallel over N ranks (expert e -> rank e % N), weak scaling (batch 8 per rank), fixed-capacity
+all-to-all token dispatch over NCCL (moe_infinity_b200.ep).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "moe-infinity_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+MIXTRAL = dict(L=32, E=8, H=4096, I=14336, k=2)
+BATCH = 8
+METRIC = "decode tokens/sec + p50 per-token latency, Mixtral-8x7B MoE dispatch path"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, if any."""
+    path = os.path.join(ROOT, "profiles", "r01_k3_dram_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("traffic_bytes_per_launch")
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_layer(weights_cpu, gate_cpu, x_cpu, k, repeat_s=12.0, min_reps=2):
+    """Time the oracle port of one full-size layer on the host cores.  Returns (sec_per_layer, reps, out)."""
+    from oracle import moe_oracle as O
+    out = None
+    t0 = time.perf_counter()
+    reps = 0
+    with torch.no_grad():
+        while True:
+            out, logits, r = O.mixtral_block(x_cpu, gate_cpu, weights_cpu, k)
+            reps += 1
+            el = time.perf_counter() - t0
+            if reps >= min_reps and el >= repeat_s or el > 4 * repeat_s:
+                break
+    return el / reps, reps, out, logits, r
+
+
+def make_cpu_layer(E, H, I, dtype, seed):
+    """Full-size layer weights on the host.  randn on 1.4 G elements is slow on CPU, so draw uniform blocks with
+    matching variance (std 0.02) -- the CPU baseline only needs realistic sizes/values, not a named checkpoint."""
+    g = torch.Generator().manual_seed(seed)
+    experts = []
+    a = 0.02 * (3 ** 0.5)
+    for _ in range(E):
+        ws = []
+        for shape in ((I, H), (H, I), (I, H)):
+            w = torch.empty(shape, dtype=torch.float32).uniform_(-a, a, generator=g).to(dtype)
+            ws.append(w)
+        experts.append(ws)
+    return experts
+
+
+def run_reference(args):
+    """--impl reference: the oracle port of the reference's path on the host cores (all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = MIXTRAL
+    dtype = torch.bfloat16
+    L_sample = 1
+    experts = make_cpu_layer(cfg["E"], cfg["H"], cfg["I"], dtype, 1234)
+    g = torch.Generator().manual_seed(7)
+    gate = (torch.randn(cfg["E"], cfg["H"], generator=g) * 0.02).to(dtype)
+    x = torch.randn(1, BATCH, cfg["H"], generator=g).to(dtype)
+    from oracle import moe_oracle as O
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup // 3)):
+            O.mixtral_block(x, gate, experts, cfg["k"])
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            O.mixtral_block(x, gate, experts, cfg["k"])
+            times.append(time.perf_counter() - t0)
+    per_layer = sum(times) / len(times)
+    step_s = per_layer * cfg["L"]
+    value = BATCH / step_s
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "p50_token_latency_ms": sorted(times)[len(times) // 2] * cfg["L"] * 1e3,
+        "config": {"workload": "Mixtral-8x7B MoE path decode batch 8 (T=8), bf16, 32 layers; CPU oracle port; "
+                               "each step = 1 of the 32 full-size layers, scaled x32", "inputs": "host memory"},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x one full-size Mixtral layer (2.8 GB bf16 weights, T=8), x32 layers"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def algorithmic_bytes(counts_per_layer, T, cfg):
+    """per layer A*3*H*I*2 (weights of distinct activated experts) + 2*T*H*2 + T*E*2 + T*k*8."""
+    H, I, E, k = cfg["H"], cfg["I"], cfg["E"], cfg["k"]
+    total, k3 = 0, 0
+    for c in counts_per_layer:
+        A = sum(1 for v in c if v > 0)
+        total += A * 3 * H * I * 2 + 2 * T * H * 2 + T * E * 2 + T * k * 8
+        k3 += A * 2 * H * I * 2 + T * k * H * 2 + T * k * I * 2   # gate+up weights, gathered rows in, h out
+    return total, k3
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from moe_infinity_b200 import MoEEngine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from moe_infinity_b200 import ep
+        return ep.bench_ep(args, MIXTRAL, BATCH, METRIC, load_peaks, ClockSampler)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = dict(MIXTRAL)
+    if args.layers:
+        cfg["L"] = args.layers
+    L, E, H, I, k = cfg["L"], cfg["E"], cfg["H"], cfg["I"], cfg["k"]
+    T = BATCH
+    dtype = torch.bfloat16
+    t_setup = time.perf_counter()
+    eng = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype, max_tokens=max(T, 16),
+                    num_slots=L * E)
+    torch.manual_seed(0)
+    for l in range(L):
+        for e in range(E):
+            v = eng.load_expert(l, e)            # flat bf16 view of the HBM slot
+            v.normal_(0.0, 0.02)
+        eng.set_gate(l, torch.randn(E, H, device=dev) * 0.02)
+    x_dev = torch.randn(L, T, H, device=dev).to(dtype)
+    out_dev = torch.empty_like(x_dev)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    def step_device():
+        for l in range(L):
+            eng.forward(l, x_dev[l], out=out_dev[l])
+
+    # ---- eager warm-up (also sets kernel attributes outside of graph capture)
+    for _ in range(2):
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = eng.stats()["kernel_launches"]
+    step_device()
+    launches_per_step = eng.stats()["kernel_launches"] - launches0
+    # routing actually taken by the timed inputs -> algorithmic bytes
+    counts = []
+    for l in range(L):
+        eng.route(l, x_dev[l])
+        counts.append(eng.ws("counts", T).cpu().tolist())
+    bytes_step, bytes_k3_step = algorithmic_bytes(counts, T, cfg)
+    # ---- CUDA graph of one 32-layer step
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step_device()
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(graph):
+        step_device()
+    for _ in range(args.warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    evs[0].record()
+    for i in range(args.steps):
+        graph.replay()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    total_ms = evs[0].elapsed_time(evs[-1])
+    ms_per_step = total_ms / args.steps
+    value = BATCH * args.steps / (total_ms * 1e-3)
+    p50 = sorted(step_ms)[len(step_ms) // 2]
+
+    # ---- dominant kernel (K3) timed on its launch stream with CUDA events
+    st = torch.cuda.current_stream()
+    k3_ms = []
+    for it in range(3 + min(args.steps, 10)):
+        acc = 0.0
+        for l in range(L):
+            eng.route(l, x_dev[l])
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            eng.run_experts(l, T, phases=1)
+            b.record(st)
+            eng.run_experts(l, T, phases=2)
+            eng.combine(l, x_dev[l], out=out_dev[l])
+            b.synchronize()
+            acc += a.elapsed_time(b)
+        if it >= 3:
+            k3_ms.append(acc / L)
+    k3_avg_ms = sum(k3_ms) / len(k3_ms)
+    peak, peak_src = load_peaks()
+    k3_bytes = bytes_k3_step / L
+    achieved = k3_bytes / (k3_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "grouped_gemm_tc_kernel<16,dual> (gate/up + SwiGLU, K3)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "avg_launch_ms": k3_avg_ms, "algorithmic_bytes_per_launch": k3_bytes,
+                "traffic": load_traffic(),
+                "step": {"algorithmic_bytes": bytes_step, "achieved": bytes_step / (ms_per_step * 1e-3) / 1e9,
+                         "frac": bytes_step / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- e2e: public API per layer, HOST buffers, copies inside the timed region
+    x_host = x_dev.cpu().pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    x_in = torch.empty_like(x_dev)
+
+    def step_e2e():
+        x_in.copy_(x_host, non_blocking=True)
+        for l in range(L):
+            eng.forward(l, x_in[l], out=out_dev[l])
+        out_host.copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(3, args.warmup // 2)):
+        step_e2e()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    e2e = {"value": BATCH * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s",
+           "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2,
+           "ms_per_step": e2e_ms / args.steps, "api": "MoEEngine.forward per layer (ctypes -> b2m_moe_forward)"}
+
+    # ---- cpu baseline on a bounded sample + full-size parity of layer 0
+    cpu = None
+    parity = None
+    if not args.no_cpu:
+        w0 = []
+        for e in range(E):
+            flat = eng.expert_device_view(0, e).cpu()
+            m = H * I
+            w0.append([flat[0:m].view(I, H), flat[m:2 * m].view(H, I), flat[2 * m:3 * m].view(I, H)])
+        gate0 = eng._gates[0].cpu()
+        x0 = x_dev[0].cpu().unsqueeze(0)
+        sec, reps, ref_out, ref_logits, r = cpu_oracle_layer(w0, gate0, x0, k, repeat_s=args.cpu_seconds)
+        cores = torch.get_num_threads()
+        cpu = {"value": BATCH / (sec * L), "unit": "tokens/s", "cores": cores, "kind": "port",
+               "sample": f"{reps} x layer 0 at full size (8 experts x 352 MB bf16, T=8) on {cores} threads, x{L} layers"}
+        # full-size parity: same weights, same inputs, router logits from the oracle
+        got = eng.forward(0, x_dev[0], router_logits=ref_logits.to(dev)).float().cpu()
+        idx = eng.ws("topk_idx", T).cpu().long()
+        ref = ref_out.reshape(T, H).float()
+        rms = ref.pow(2).mean().sqrt().item()
+        parity = {"expert_index_equal": bool(torch.equal(idx, r.topk_idx)),
+                  "max_abs_diff": (got - ref).abs().max().item(), "ref_rms": rms,
+                  "frac_bit_identical": (got == ref).float().mean().item()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "p50_token_latency_ms": p50, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Mixtral-8x7B MoE dispatch path, decode batch {BATCH} (T={T} tokens/layer/step), "
+                               f"{L} layers x 8 experts top-2, H=4096 I=14336, bf16 random-init, all {L*E} experts "
+                               f"HBM-resident ({L*E*3*H*I*2/1e9:.1f} GB); context 2048 affects attention only "
+                               "(outside the path)",
+                   "global_batch": BATCH, "layers": L, "parallelism": "single GPU",
+                   "l2": "inputs larger than L2: each step streams ~%.1f GB of distinct expert weights" % (bytes_step / 1e9),
+                   "numerics": "reference rounding chain", "timed_region": "CUDA graph replay of the 32-layer step"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step), "clocks": clocks, "full_size_parity_layer0": parity,
+        "setup_s": setup_s,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (invalid as a bench value)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path only"}))
+        sys.exit(2)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

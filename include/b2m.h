@@ -158,6 +158,9 @@ int b2m_route_from_mask(b2m_ctx* ctx, int layer, const void* x, const uint8_t* m
 /* replaces EnqueueExpert*n + GPUFetchFunc/GPUExecFunc (expert_dispatcher.cpp:111-395) for the routed tokens
  * currently in the workspace: residency (on demand fetch + eviction) and both grouped GEMMs */
 int b2m_run_experts(b2m_ctx* ctx, int layer, int T, void* stream);
+/* same, restricted to phases: bit0 = residency + gate/up GEMM (K3), bit1 = down GEMM (K4); used by bench.py to
+ * time the dominant kernel on its own stream with CUDA events */
+int b2m_run_experts_ex(b2m_ctx* ctx, int layer, int T, int phases, void* stream);
 int b2m_combine(b2m_ctx* ctx, int layer, const void* x, int T, void* out, void* stream);
 /* replaces OutputFunc/Wait (expert_dispatcher.cpp:397-450): expert outputs in the model dtype, rows grouped by
  * ascending expert id, ascending token order inside an expert; `offsets_host` (E+1 ints) may be NULL */

@@ -720,7 +720,7 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
 
 static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, const CUtensorMap& tm_b_up,
                                const CUtensorMap& tm_b_down, const void* b_up, int ldb_up, const void* b_down,
-                               void* hmid, float* y, int nt, int ksplit, cudaStream_t st) {
+                               void* hmid, float* y, int nt, int ksplit, cudaStream_t st, int phases = 3) {
   const b2m_config& f = c->cfg;
   const ExpertShape& s = a.shape;
   GemmParams up = base;
@@ -731,18 +731,22 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
   dn.out = y; dn.ld_out = s.H;
   if (f.gemm_impl == 1) {
     const size_t slot_elems = a.slot_bytes / 2;
-    CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_gate / 2, s.off_up / 2, b_up, ldb_up, up, s.dual, st));
+    if (phases & 1)
+      CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_gate / 2, s.off_up / 2, b_up, ldb_up, up, s.dual, st));
     dn.ksplit = 1;
-    CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
+    if (phases & 2)
+      CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
   } else {
-    CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
-    CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+    if (phases & 1) CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
+    if (phases & 2) CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
   }
-  c->stats.kernel_launches += 2;
+  c->stats.kernel_launches += ((phases & 1) ? 1 : 0) + ((phases & 2) ? 1 : 0);
   return B2M_OK;
 }
 
-int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) {
+int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) { return b2m_run_experts_ex(c, layer, T, 3, stream); }
+
+int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   int r = check_layer(c, layer);
   if (r) return r;
   if (T != c->cur_T) return fail(c, B2M_ESTATE, "b2m_run_experts(T=%d) does not follow a routing call with the same T (%d)", T, c->cur_T);
@@ -752,7 +756,10 @@ int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) {
   r = pump(c);
   if (r) return r;
   std::vector<int> active;
-  if (c->offload) {
+  const bool do_residency = (phases & 1) != 0;
+  if (!do_residency) {
+    active = c->last_active;
+  } else if (c->offload) {
     // on-demand path: read the per-expert counts back (the reference's .cpu() in dispatch_local)
     CK(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
@@ -765,6 +772,7 @@ int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) {
   }
   // residency
   for (int id : active) {
+    if (!do_residency) break;
     Expert& x = c->experts[id];
     if (x.state == ST_UNREGISTERED) return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
     if (c->offload) {
@@ -805,14 +813,14 @@ int b2m_run_experts(b2m_ctx* c, int layer, int T, void* stream) {
   base.single_n = -1;
   const int ni = nt_index(c->cur_nt);
   r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid, c->d_hmid,
-                          c->d_y, c->cur_nt, c->cur_ksplit, st);
+                          c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
   if (r) return r;
-  if (c->offload) {
+  if (do_residency) c->last_active = active;
+  if (c->offload && (phases & 2)) {
     int evi;
     cudaEvent_t ev = next_ring_event(c, &evi);
     CK(c, cudaEventRecord(ev, st));
     for (int id : active) c->slots[c->experts[id].slot].last_use_ev = evi;
-    c->last_active = active;
   }
   return B2M_OK;
 }

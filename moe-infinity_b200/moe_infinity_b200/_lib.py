@@ -58,6 +58,7 @@ SYMBOLS = [
     ("b2m_route", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
     ("b2m_route_from_mask", _I, [_VP, _I, _VP, _VP, _I, _VP]),
     ("b2m_run_experts", _I, [_VP, _I, _I, _VP]),
+    ("b2m_run_experts_ex", _I, [_VP, _I, _I, _I, _VP]),
     ("b2m_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
     ("b2m_expert_outputs", _I, [_VP, _I, _VP, C.POINTER(C.c_int), _VP]),
     ("b2m_ws_ptr", _I, [_VP, _I, C.POINTER(_VP)]),

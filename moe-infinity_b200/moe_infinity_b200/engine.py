@@ -201,8 +201,8 @@ class MoEEngine:
                                               x2.shape[0], C.c_void_p(_stream_ptr())))
         return x2.shape[0]
 
-    def run_experts(self, layer: int, T: int):
-        self._ck(self.lib.b2m_run_experts(self._h, layer, T, C.c_void_p(_stream_ptr())))
+    def run_experts(self, layer: int, T: int, phases: int = 3):
+        self._ck(self.lib.b2m_run_experts_ex(self._h, layer, T, phases, C.c_void_p(_stream_ptr())))
 
     def combine(self, layer: int, x: torch.Tensor, out: Optional[torch.Tensor] = None):
         x2 = self._check_x(x)
