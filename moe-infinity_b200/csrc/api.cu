@@ -393,7 +393,7 @@ void plan_gemm(b2m_ctx* c, int T) {
 
 int route_launch_count(int T, int router) {
   if (T == 0) return 0;
-  if (T <= 256) return 1;
+  if (T <= 256) return 2;
   return router == B2M_ROUTER_SWITCH_TOP1 ? 5 : 3;
 }
 
@@ -713,7 +713,7 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
   plan_gemm(c, T);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
   CK(c, launch_route_from_mask(p, mask, st));
-  c->stats.kernel_launches += T == 0 ? 0 : (T <= 256 ? 1 : 4);
+  c->stats.kernel_launches += T == 0 ? 0 : (T <= 256 ? 2 : 4);
   c->last_counts_valid = false;
   return B2M_OK;
 }

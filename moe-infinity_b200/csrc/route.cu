@@ -54,37 +54,52 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // --------------------------------------------------------------------------------------
-// K0: router gate for one token (one warp): logits[e] = <x[t], Wg[e]> with fp32 accumulation.
+// K0: router gate.  logits[e] = <x[t], Wg[e]> with fp32 accumulation, 16-byte vector loads.
 // Mixtral: nn.Linear in model dtype -> result rounded to the model dtype (mixtral.py:46).
 // DeepSeek/Switch: fp32 linear on upcast operands (modeling_deepseek.py:467-471).
 // --------------------------------------------------------------------------------------
-__device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[E] smem, this warp*/) {
+__device__ __forceinline__ void unpack8(const uint4& v, int dt, float (&f)[8]) {
+  const uint16_t* s = reinterpret_cast<const uint16_t*>(&v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = dt == DT_BF16 ? Half16<DT_BF16>::to_f(s[j]) : Half16<DT_F16>::to_f(s[j]);
+}
+// one warp: dot product of x[t] (model dtype) with gate row e (gate dtype); result in every lane
+__device__ float gate_dot_warp(const RouteParams& p, int t, int e) {
   const int lane = threadIdx.x & 31;
   const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
-  for (int e0 = 0; e0 < p.E; e0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int h = lane * 8; h < p.H; h += 32 * 8) {
+  float acc = 0.f;
+  if (p.gate_dtype == DT_F32) {
+    const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)e * p.H;
+#pragma unroll 4
+    for (int h = lane * 8; h < p.H; h += 256) {
       const uint4 xv = *reinterpret_cast<const uint4*>(x + h);
-      const uint16_t* xs = reinterpret_cast<const uint16_t*>(&xv);
+      const float4 w0 = *reinterpret_cast<const float4*>(w + h), w1 = *reinterpret_cast<const float4*>(w + h + 4);
       float xf[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xf[j] = p.dtype == DT_BF16 ? Half16<DT_BF16>::to_f(xs[j]) : Half16<DT_F16>::to_f(xs[j]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (e0 + i < p.E) {
-          const size_t wo = (size_t)(e0 + i) * p.H + h;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], load_as_float(p.gate_w, wo + j, p.gate_dtype), acc[i]);
-        }
-      }
+      unpack8(xv, p.dtype, xf);
+      acc = fmaf(xf[0], w0.x, acc); acc = fmaf(xf[1], w0.y, acc); acc = fmaf(xf[2], w0.z, acc); acc = fmaf(xf[3], w0.w, acc);
+      acc = fmaf(xf[4], w1.x, acc); acc = fmaf(xf[5], w1.y, acc); acc = fmaf(xf[6], w1.z, acc); acc = fmaf(xf[7], w1.w, acc);
     }
+  } else {
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)e * p.H;
+#pragma unroll 4
+    for (int h = lane * 8; h < p.H; h += 256) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(x + h);
+      const uint4 wv = *reinterpret_cast<const uint4*>(w + h);
+      float xf[8], wf[8];
+      unpack8(xv, p.dtype, xf);
+      unpack8(wv, p.gate_dtype, wf);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = warp_sum(acc[i]);
-      if (lane == 0 && e0 + i < p.E) s_logits[e0 + i] = (p.router == ROUTER_MIXTRAL) ? round_to(s, p.dtype) : s;
+      for (int j = 0; j < 8; ++j) acc = fmaf(xf[j], wf[j], acc);
     }
+  }
+  acc = warp_sum(acc);
+  return (p.router == ROUTER_MIXTRAL) ? round_to(acc, p.dtype) : acc;
+}
+__device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[E] smem, this warp*/) {
+  const int lane = threadIdx.x & 31;
+  for (int e = 0; e < p.E; ++e) {
+    const float v = gate_dot_warp(p, t, e);
+    if (lane == 0) s_logits[e] = v;
   }
   __syncwarp();
 }
@@ -232,13 +247,15 @@ __device__ void chunk_count_warp(const int* topk_idx, int t0, int T, int k, int 
 // Destination rows for the tokens of one chunk (lane == token), stable inside each expert.
 // base_of(e) = first permuted row available to this chunk for expert e.
 template <class BaseFn>
-__device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, int* s_rows /*[CHUNK*k] smem*/) {
+__device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, int* s_rows /*[CHUNK*k] smem*/,
+                                const int* idx_src = nullptr, bool write_global = true) {
   const int lane = threadIdx.x & 31;
   const int t = t0 + lane;
   const int k = p.k;
+  if (!idx_src) idx_src = p.topk_idx;
   int idx[MAX_K];
 #pragma unroll
-  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < p.T && j < k) ? p.topk_idx[(size_t)t * k + j] : -1;
+  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < p.T && j < k) ? idx_src[(size_t)t * k + j] : -1;
   int dest[MAX_K];
 #pragma unroll
   for (int j = 0; j < MAX_K; ++j) dest[j] = -1;
@@ -257,7 +274,7 @@ __device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, in
   for (int j = 0; j < MAX_K; ++j) {
     if (j < k) {
       s_rows[lane * k + j] = dest[j];
-      if (t < p.T) {
+      if (t < p.T && write_global) {
         p.row_of[(size_t)t * k + j] = dest[j];
         if (dest[j] >= 0) p.perm_token[dest[j]] = t;
       }
@@ -339,11 +356,12 @@ __global__ void __launch_bounds__(RT_THREADS) switch_capacity_kernel(const Route
     for (int s0 = 0; s0 < S; s0 += 32) {
       const int s = s0 + lane;
       const int t = b * S + s;
-      const bool h = s < S && p.topk_idx[t] == e;
+      const int raw = s < S ? p.topk_idx[t] : -1;
+      const bool h = s < S && (raw >= 0 ? raw : -(raw + 2)) == e;
       const uint32_t m = __ballot_sync(0xffffffffu, h);
       if (h) {
         const int prio = running + __popc(m & ((1u << lane) - 1u)) + 1;   // cumsum is 1-based
-        if (prio > p.expert_capacity) p.topk_idx[t] = -1;                 // dropped: passes through unchanged
+        if (prio > p.expert_capacity) p.topk_idx[t] = -(e + 2);           // dropped: passes through unchanged
       }
       running += __popc(m);
     }
@@ -437,104 +455,123 @@ __global__ void __launch_bounds__(RT_THREADS) route_permute_kernel(const RoutePa
 }
 
 // --------------------------------------------------------------------------------------
-// Fused single-CTA path (decode, T <= 256): gate + softmax/top-k + counts + scan + permute in ONE launch
+// Small-T path (decode, T <= 256): two launches, both multi-CTA.
+//   gate_topk_small_kernel : one CTA per token -- the E gate dot products are spread over the CTA's warps,
+//                            warp 0 then does softmax + top-k (+renorm).
+//   permute_small_kernel   : every CTA redundantly ranks the (tiny) routing table in shared memory, CTA 0
+//                            publishes counts/offsets/row maps, and the gathered rows are copied one row per CTA
+//                            with 16-byte vectors.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT_THREADS) route_fused_kernel(const RouteParams p, const uint8_t* __restrict__ mask) {
-  __shared__ float s_logits[RT_WARPS][MAX_PL * 32];
-  __shared__ float s_scr[RT_WARPS][MAX_PL * 32];
+__global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const RouteParams p) {
+  __shared__ float s_logits[MAX_PL * 32];
+  __shared__ float s_scr[MAX_PL * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  bool scores_in = false;
+  if (p.logits) {
+    for (int e = threadIdx.x; e < p.E; e += RT_THREADS) s_logits[e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
+    scores_in = p.logits_are_scores != 0;
+  } else {
+    for (int e = warp; e < p.E; e += RT_WARPS) {
+      const float v = gate_dot_warp(p, t, e);
+      if (lane == 0) s_logits[e] = v;
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  if (p.logits_out && !scores_in) {
+    for (int e = lane; e < p.E; e += 32) {
+      const float lv = s_logits[e];
+      if (p.router == ROUTER_MIXTRAL)
+        reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
+            p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
+      else
+        reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
+    }
+  }
+  route_token_warp(p, t, s_logits, scores_in, s_scr, p.topk_idx + (size_t)t * p.k, p.topk_w + (size_t)t * p.k);
+}
+
+__global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RouteParams p) {
+  __shared__ int s_idx[FUSED_MAX_T * MAX_K];
   __shared__ int s_cnt[RT_WARPS][MAX_PL * 32];   // per-chunk counts -> exclusive bases
   __shared__ int s_off[MAX_PL * 32 + 1];
-  __shared__ int s_rows[RT_WARPS][CHUNK * MAX_K];
+  __shared__ int s_tot[MAX_PL * 32];
+  __shared__ int s_rows[FUSED_MAX_T * MAX_K];    // destination row of (t, j), index t*k + j
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
-
-  if (mask) {
-    // compat path: routing decisions come from the caller's dense mask
-    for (int t = threadIdx.x; t < p.T; t += RT_THREADS) {
-      int n = 0;
-      for (int e = 0; e < p.E; ++e)
-        if (mask[(size_t)t * p.E + e] && n < p.k) {
-          p.topk_idx[(size_t)t * p.k + n] = e;
-          p.topk_w[(size_t)t * p.k + n] = 1.0f;
-          ++n;
-        }
-      for (; n < p.k; ++n) { p.topk_idx[(size_t)t * p.k + n] = -1; p.topk_w[(size_t)t * p.k + n] = 0.0f; }
-    }
-  } else {
-    for (int t = warp; t < p.T; t += RT_WARPS) {
-      bool scores_in = false;
-      if (p.logits) {
-        for (int e = lane; e < p.E; e += 32) s_logits[warp][e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
-        scores_in = p.logits_are_scores != 0;
-        __syncwarp();
-      } else {
-        gate_token_warp(p, t, s_logits[warp]);
-      }
-      if (p.logits_out && !scores_in) {
-        for (int e = lane; e < p.E; e += 32) {
-          const float lv = s_logits[warp][e];
-          if (p.router == ROUTER_MIXTRAL)
-            reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
-                p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
-          else
-            reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
-        }
-      }
-      route_token_warp(p, t, s_logits[warp], scores_in, s_scr[warp], p.topk_idx + (size_t)t * p.k,
-                       p.topk_w + (size_t)t * p.k);
-      __syncwarp();
-    }
-  }
-  __threadfence_block();
+  const int npairs = p.T * p.k;
+  for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx[i] = p.topk_idx[i];
   __syncthreads();
-  if (p.router == ROUTER_SWITCH_TOP1 && !mask) {
-    // capacity: one batch row after another (T <= 256: cheap)
+  if (p.router == ROUTER_SWITCH_TOP1) {
+    // capacity (cumsum priority <= capacity, per batch row): dropped tokens get expert -1
     const int S = p.seq_len;
     const int B = p.T / S;
-    for (int b = 0; b < B; ++b) {
-      for (int e = warp; e < p.E; e += RT_WARPS) {
-        int running = 0;
-        for (int s0 = 0; s0 < S; s0 += 32) {
-          const int s = s0 + lane;
-          const int t = b * S + s;
-          const bool h = s < S && p.topk_idx[t] == e;
-          const uint32_t m = __ballot_sync(0xffffffffu, h);
-          if (h && running + __popc(m & ((1u << lane) - 1u)) + 1 > p.expert_capacity) p.topk_idx[t] = -1;
-          running += __popc(m);
-        }
+    for (int pe = warp; pe < B * p.E; pe += RT_WARPS) {
+      const int b = pe / p.E, e = pe % p.E;
+      int running = 0;
+      for (int s0 = 0; s0 < S; s0 += 32) {
+        const int sidx = s0 + lane;
+        const int t = b * S + sidx;
+        // dropped entries are stored as -(e+2): the pass is idempotent, so CTAs that read indices another CTA
+        // has already rewritten reach the same result
+        const int raw = sidx < S ? s_idx[t] : -1;
+        const bool h = sidx < S && (raw >= 0 ? raw : -(raw + 2)) == e;
+        const uint32_t m = __ballot_sync(0xffffffffu, h);
+        if (h && running + __popc(m & ((1u << lane) - 1u)) + 1 > p.expert_capacity) s_idx[t] = -(e + 2);
+        running += __popc(m);
       }
     }
-    __threadfence_block();
     __syncthreads();
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < npairs; i += RT_THREADS) p.topk_idx[i] = s_idx[i];
   }
-  if (warp < nchunks) chunk_count_warp(p.topk_idx, warp * CHUNK, p.T, p.k, p.E, s_cnt[warp]);
+  if (warp < nchunks) chunk_count_warp(s_idx, warp * CHUNK, p.T, p.k, p.E, s_cnt[warp]);
   __syncthreads();
   if (threadIdx.x < p.E) {
     const int e = threadIdx.x;
     int run = 0;
     for (int c = 0; c < nchunks; ++c) { const int v = s_cnt[c][e]; s_cnt[c][e] = run; run += v; }
-    s_scr[0][e] = __int_as_float(run);
-    p.counts[e] = run;
+    s_tot[e] = run;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int e = 0; e < p.E; ++e) { s_off[e] = acc; p.offsets[e] = acc; acc += __float_as_int(s_scr[0][e]); }
+    for (int e = 0; e < p.E; ++e) { s_off[e] = acc; acc += s_tot[e]; }
     s_off[p.E] = acc;
-    p.offsets[p.E] = acc;
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x <= p.E) {
+    p.offsets[threadIdx.x] = s_off[threadIdx.x];
+    if (threadIdx.x < p.E) p.counts[threadIdx.x] = s_tot[threadIdx.x];
+  }
   if (warp < nchunks) {
     const int* cb = s_cnt[warp];
-    chunk_rank_warp(p, warp * CHUNK, [&](int e) { return s_off[e] + cb[e]; }, s_rows[warp]);
+    chunk_rank_warp(p, warp * CHUNK, [&](int e) { return s_off[e] + cb[e]; }, s_rows + warp * CHUNK * p.k, s_idx,
+                    blockIdx.x == 0);
   }
   __syncthreads();
-  for (int c = 0; c < nchunks; ++c) copy_rows_block(p, c * CHUNK, CHUNK * p.k, s_rows[c], 0, RT_WARPS);
+  // gather: CTA b copies rows b, b+grid, ...; the whole CTA moves one row (H*2 bytes) with 16 B vectors
+  const int vec_per_row = p.H / 8;
+  for (int i = blockIdx.x; i < npairs; i += gridDim.x) {
+    const int row = s_rows[i];
+    if (row < 0) continue;
+    const int t = i / p.k;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+    for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
+  }
   if (p.y_zero) {
     float4* z = reinterpret_cast<float4*>(p.y_zero);
     const size_t n4 = p.y_zero_elems / 4;
-    for (size_t i = threadIdx.x; i < n4; i += RT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = (size_t)blockIdx.x * RT_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * RT_THREADS)
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+static int small_permute_grid(const RouteParams& p) {
+  const int pairs = p.T * p.k;
+  return pairs < 1 ? 1 : (pairs > 128 ? 128 : pairs);
 }
 
 static bool route_args_ok(const RouteParams& p) {
@@ -548,7 +585,8 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   if (!route_args_ok(p)) return cudaErrorInvalidValue;
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
-    route_fused_kernel<<<1, RT_THREADS, 0, st>>>(p, nullptr);
+    gate_topk_small_kernel<<<p.T, RT_THREADS, 0, st>>>(p);
+    permute_small_kernel<<<small_permute_grid(p), RT_THREADS, 0, st>>>(p);
     return cudaGetLastError();
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
@@ -567,7 +605,10 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
   if (!route_args_ok(p) || mask == nullptr) return cudaErrorInvalidValue;
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
-    route_fused_kernel<<<1, RT_THREADS, 0, st>>>(p, mask);
+    mask_to_topk_kernel<<<(p.T + RT_THREADS - 1) / RT_THREADS, RT_THREADS, 0, st>>>(p, mask);
+    RouteParams q = p;
+    q.router = ROUTER_MIXTRAL;   // routing decisions already taken: no capacity pass
+    permute_small_kernel<<<small_permute_grid(q), RT_THREADS, 0, st>>>(q);
     return cudaGetLastError();
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;

@@ -44,9 +44,10 @@ def hidden_close(y, y_ref, y32, dtype, what=""):
         # fp32 accumulation orders in the GEMMs; a one-ulp flip of an intermediate can surface as a 2-ulp
         # difference of the final fp16 value (rel. 1e-3..2e-3 just above a power of two).  Allow that on at most
         # 1e-4 of the elements, never more than 2 fp16 ulp; everything else obeys the 1e-3 bound.
-        ulp2 = 2 * torch.finfo(torch.float16).eps * y_ref.abs().clamp_min(rms)
+        ulp2 = 2.05 * torch.finfo(torch.float16).eps * y_ref.abs().clamp_min(rms)   # >= 2 ulp(y) (+ float slack)
         assert bool((diff[bad] <= ulp2[bad]).all()) and int(bad.sum()) <= max(1, int(1e-4 * bad.numel())), (
-            f"{what}: {int(bad.sum())}/{bad.numel()} elements beyond 1e-3, max diff {diff.max().item():.3e}")
+            f"{what}: {int(bad.sum())}/{bad.numel()} elements beyond 1e-3, max diff {diff.max().item():.3e}, "
+            f"worst ratio to 2ulp {(diff[bad] / ulp2[bad]).max().item():.3f}")
         bad = torch.zeros_like(bad)
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; "
                                  f"max diff {diff.max().item():.3e}, rms {rms:.3e}")
