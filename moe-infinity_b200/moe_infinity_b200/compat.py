@@ -1,0 +1,219 @@
+"""Reference-compatible host objects: `prefetch_handle`, `expert_dispatcher`, `DistributedExpertExecutor`.
+
+Same class names, method names, argument meaning and result contracts as the reference's pybind module
+`moe_infinity.ops.prefetch.prefetch_op` (core/python/py_archer_prefetch.cpp:10-92) and
+moe_infinity/distributed/expert_executor.py:19-58, restricted to what the MoE-block hot path calls
+(SURVEY.md §8 b.2).  Everything numerical is forwarded to libb2m.so through MoEEngine.
+
+Differences, on purpose:
+  * the SSD tier (core/aio) is out of scope: `offload` keeps tensors in (pinned) host DRAM;
+  * errors raise RuntimeError/B2MError instead of aborting the process;
+  * `wait_expert` returns experts in ascending expert id (the reference returns completion order, Q1).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import MoEEngine
+
+_INT2DTYPE = {L.DTYPE_BF16: torch.bfloat16, L.DTYPE_F32: torch.float32, L.DTYPE_F16: torch.float16}
+_ROUTER_OF_TYPE = {L.EXPERT_MIXTRAL: L.ROUTER_MIXTRAL, L.EXPERT_DEEPSEEK: L.ROUTER_DEEPSEEK_GREEDY,
+                   L.EXPERT_SWITCH: L.ROUTER_SWITCH_TOP1, L.EXPERT_SWITCH_GATED: L.ROUTER_SWITCH_TOP1}
+
+
+class prefetch_handle:  # noqa: N801  (reference spelling)
+    """py_archer_prefetch.cpp:11-80.  Host-DRAM tensor store + the residency/prefetch façade."""
+
+    def __init__(self, prefix: str, device_memory_ratio: float):
+        self.prefix = prefix
+        self.device_memory_ratio = float(device_memory_ratio)
+        self._tensors: Dict[int, torch.Tensor] = {}     # id -> host tensor  (offload)
+        self._params: Dict[int, torch.Tensor] = {}      # id -> live Parameter.data placeholder (register)
+        self._ptr2id: Dict[int, int] = {}
+        self._node_of: Dict[int, Tuple[int, int]] = {}  # tensor id -> (layer, expert)
+        self._topology = None
+        self._dispatcher: Optional["expert_dispatcher"] = None
+
+    # ---- tensor store (prefetch_handle.offload / register / is_tensor_*)
+    def offload(self, tensor: torch.Tensor, tensor_id: int):
+        self._tensors[int(tensor_id)] = tensor.detach().to("cpu").contiguous()
+
+    def register(self, tensor: torch.Tensor, tensor_id: int):
+        self._params[int(tensor_id)] = tensor
+        self._ptr2id[tensor.data_ptr()] = int(tensor_id)
+
+    def update_tensor_map(self, old_ptr: int, new_ptr: int):
+        if old_ptr in self._ptr2id:
+            self._ptr2id[new_ptr] = self._ptr2id.pop(old_ptr)
+
+    def is_tensor_offloaded(self, tensor_id: int) -> bool:
+        return int(tensor_id) in self._tensors
+
+    def is_tensor_index_initialized(self) -> bool:
+        return False   # no persistent store: the caller re-offloads from the checkpoint
+
+    def set_topology(self, topology):
+        """[(name, [[ids...], ...]), ...]; a stage with >1 id-lists is an expert stage (model_topology.cpp:417-452)."""
+        self._topology = topology
+
+    def get_node_default_device(self, tensor_ids: Sequence[int]) -> int:
+        return self._dispatcher.engine.device.index if self._dispatcher and self._dispatcher.engine else 0
+
+    def get_node_device(self, tensor_ids: Sequence[int]) -> int:
+        le = self._node_of.get(int(tensor_ids[0]))
+        if le is None or self._dispatcher is None or self._dispatcher.engine is None:
+            return -1
+        return self._dispatcher.engine.device.index if self._dispatcher.engine.is_resident(*le) else -1
+
+    # ---- dense-parameter path (begin/end hooks): weights simply live on the device
+    def begin(self, request_id: int, tensor: torch.Tensor):
+        tid = self._ptr2id.get(tensor.data_ptr())
+        if tid is not None and tid in self._tensors:
+            dev = torch.device("cuda", self.get_node_default_device([tid]))
+            tensor.data = self._tensors[tid].to(dev)
+            self._ptr2id[tensor.data_ptr()] = tid
+
+    def end(self, request_id: int, tensor: torch.Tensor):
+        return None
+
+    def fetch_tensors(self, request_id: int, tensor_ids: Sequence[int]):
+        return None
+
+    # ---- expert cache / prefetch façade (archer_prefetch_handle.cpp:195-218)
+    def _pairs(self, tensor_ids):
+        out, seen = [], set()
+        for t in tensor_ids:
+            le = self._node_of[int(t)]
+            if le not in seen:
+                seen.add(le)
+                out.append(le)
+        return out
+
+    def replace_cache_candidates(self, tensor_ids: Sequence[int]):
+        self._dispatcher.engine.replace_cache_candidates(self._pairs(tensor_ids))
+
+    def enqueue_prefetch(self, tensor_id: int, gpu_id: int):
+        l, e = self._node_of[int(tensor_id)]
+        self._dispatcher.engine.enqueue_prefetch(l, e)
+
+    def prefetch_hint(self, pairs, scores):
+        self._dispatcher.engine.prefetch_hint(pairs, scores)
+
+    def clean_up_resources(self):
+        if self._dispatcher and self._dispatcher.engine:
+            self._dispatcher.engine.close()
+
+
+class expert_dispatcher:  # noqa: N801
+    """py_archer_prefetch.cpp:84-92 / core/parallel/expert_dispatcher.h:44-82."""
+
+    def __init__(self, num_experts: int, num_layers: int, dtype: int, expert_type: int, num_threads: int = 8,
+                 handle: Optional[prefetch_handle] = None, top_k: Optional[int] = None, max_tokens: int = 4096,
+                 num_slots: int = 0, **engine_kw):
+        if dtype not in _INT2DTYPE:
+            raise ValueError(f"dtype int {dtype} unsupported")
+        self.num_experts, self.num_layers = num_experts, num_layers
+        self.dtype, self.expert_type = _INT2DTYPE[dtype], expert_type
+        self.num_threads = num_threads   # accepted for signature parity; the CUDA path needs no worker threads
+        self.handle = handle
+        self.top_k = top_k
+        self.max_tokens, self.num_slots, self.engine_kw = max_tokens, num_slots, engine_kw
+        self.engine: Optional[MoEEngine] = None
+        self._queue: List[Tuple[int, int]] = []
+        self._inputs = None
+        self._expected = 0
+        if handle is not None:
+            handle._dispatcher = self
+
+    def _ensure_engine(self, tensors: Sequence[torch.Tensor]):
+        if self.engine is not None:
+            return
+        inter, hidden = tensors[0].shape   # first tensor is [I,H] for every supported expert type
+        k = self.top_k or (1 if self.expert_type in (L.EXPERT_SWITCH, L.EXPERT_SWITCH_GATED) else 2)
+        ratio = self.handle.device_memory_ratio if self.handle else 0.0
+        self.engine = MoEEngine(num_layers=self.num_layers, num_experts=self.num_experts, hidden=hidden, inter=inter,
+                                top_k=k, dtype=self.dtype, expert_type=self.expert_type,
+                                router=_ROUTER_OF_TYPE[self.expert_type], max_tokens=self.max_tokens,
+                                num_slots=self.num_slots, device_memory_ratio=ratio, **self.engine_kw)
+
+    def register_expert(self, layer_idx: int, expert_idx: int, tensor_ids: Sequence[int]):
+        """All ids belong to one expert, in named_parameters order (expert_dispatcher.cpp:160-173)."""
+        if self.handle is None:
+            raise RuntimeError("expert_dispatcher needs the prefetch_handle that stores the tensors")
+        tensors = [self.handle._tensors[int(t)] for t in tensor_ids]
+        self._ensure_engine(tensors)
+        self.engine.register_expert(layer_idx, expert_idx, tensors)
+        for t in tensor_ids:
+            self.handle._node_of[int(t)] = (layer_idx, expert_idx)
+
+    def set_inputs(self, hidden_states: torch.Tensor, router_mask: torch.Tensor):
+        self._inputs = (hidden_states, router_mask)   # no clones: reads are stream ordered (reference clones both)
+        self._queue = []
+
+    def set_expected_queue(self, expected_pending: int):
+        self._expected = int(expected_pending)
+
+    def enqueue_expert(self, layer_idx: int, expert_idx: int, gpu_id: int = -1, remote: bool = False):
+        self._queue.append((layer_idx, expert_idx))
+
+    def wait_expert(self):
+        """[(output[n_e,H], layer, expert, hit)] for the enqueued experts; rows in ascending token order."""
+        hidden, mask = self._inputs
+        if not self._queue:
+            return []
+        layer = self._queue[0][0]
+        E = self.num_experts
+        x = hidden.reshape(-1, hidden.shape[-1])
+        m = mask.reshape(-1, E)
+        wanted = sorted({e for _, e in self._queue})
+        sel = torch.zeros(E, dtype=torch.bool, device=m.device)
+        sel[wanted] = True
+        m = m.ne(0) & sel[None, :]
+        T = self.engine.route_from_mask(layer, x, m)
+        resident_before = {e: self.engine.is_resident(layer, e) for e in wanted}
+        self.engine.run_experts(layer, T)
+        rows, offs = self.engine.expert_outputs(T)
+        out = []
+        for e in wanted:
+            if offs[e + 1] > offs[e] or (layer, e) in self._queue:
+                out.append((rows[offs[e]:offs[e + 1]], layer, e, int(resident_before[e])))
+        self._queue = []
+        return out
+
+    def clear_expert_cache_counts(self):
+        if self.engine is not None:
+            self.engine.clear_expert_cache_counts()
+
+
+class DistributedExpertExecutor:
+    """moe_infinity/distributed/expert_executor.py:19-58 (dispatch_local only; RPC `dispatch` is dead code there)."""
+
+    def __init__(self, archer_config=None):
+        self.archer_config = archer_config
+        self.expert_dispatcher = None
+
+    def set_expert_dispatcher(self, dispatcher):
+        self.expert_dispatcher = dispatcher
+
+    def set_device_map_manager(self, device_map_manager):
+        self.device_map_manager = device_map_manager
+
+    def dispatch_local(self, hidden_states, router_mask, layer_id):
+        num_expert = router_mask.shape[-1]
+        expert_count = torch.sum(router_mask.view((-1, num_expert)), dim=0).cpu().numpy().flatten()
+        expert_list = np.arange(num_expert).astype(int)[expert_count > 0].tolist()
+        self.expert_dispatcher.set_inputs(hidden_states, router_mask)
+        self.expert_dispatcher.set_expected_queue(len(expert_list))
+        total_gpus = max(1, torch.cuda.device_count())
+        for expert_id in expert_list:
+            self.expert_dispatcher.enqueue_expert(layer_id, expert_id, expert_id % total_gpus, False)
+        return self.expert_dispatcher.wait_expert()
+
+    # fused fast path reached through the same attribute (`block.expert_executor`), SURVEY §8(b)
+    def moe_forward(self, layer_id: int, hidden_states: torch.Tensor, router_logits=None, scores=None, seq_len: int = 0):
+        eng = self.expert_dispatcher.engine if hasattr(self.expert_dispatcher, "engine") else self.expert_dispatcher
+        return eng.forward(layer_id, hidden_states, router_logits=router_logits, scores=scores, seq_len=seq_len)

@@ -1,0 +1,114 @@
+"""Cache / prefetch policy oracle  --  TEST INFRASTRUCTURE ONLY (never imported by the product).
+
+Pure-Python restatement of the expert residency policy the CUDA engine implements in
+moe-infinity_b200/csrc/api.cu, which is itself the *explicit* version of the reference's two
+(contradicting) eviction loops:
+
+  on-demand fetch   core/parallel/expert_dispatcher.cpp:227-266
+      miss and no free budget -> scan experts (expert-major: `for i in experts: for j in layers`), take the
+      GPU-resident node with the smallest incache_visit_count (strict '<': first one wins ties), evict it;
+      incache_visit_count += 1 for every dispatched expert (:264), hit = node was on the GPU (:219).
+  prefetch          core/prefetch/task_scheduler.h:66-79 (ReplaceCacheCandidates: new protected set, queued
+      prefetches dropped), task_scheduler.cpp:82-118 (dedupe), :236-317 (evict-to-fit, skipping protected
+      candidates and nodes in use).
+Explicit choices (documented in DESIGN.md): victims are never experts of the dispatch in flight; a prefetch never
+evicts a protected expert (it is dropped instead); an on-demand miss may, as a last resort.
+
+Parity status: parity unpinned -- the reference has no test of its cache behaviour; this
+oracle pins *our* stated policy, and tests/test_gpu_offload.py demands the CUDA engine reproduce its
+hit/miss/eviction sequence exactly on seeded routing traces.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Set, Tuple
+
+
+class CacheOracle:
+    def __init__(self, num_layers: int, num_experts: int, num_slots: int):
+        self.L, self.E, self.nslots = num_layers, num_experts, num_slots
+        n = num_layers * num_experts
+        self.resident = [False] * n
+        self.visits = [0] * n
+        self.prefetched_unused = [False] * n
+        self.free = num_slots
+        self.protected: Set[int] = set()
+        self.last_active: List[int] = []
+        self.stats = dict(dispatches=0, hits=0, misses=0, evictions=0, prefetch_issued=0, prefetch_useful=0)
+        self.evicted_log: List[Tuple[int, int]] = []
+
+    def _id(self, layer, expert):
+        return layer * self.E + expert
+
+    def _victim(self, in_use: Sequence[int], allow_protected: bool) -> int:
+        best, best_v = -1, 1 << 60
+        for e in range(self.E):            # expert-major scan, strict '<'
+            for l in range(self.L):
+                i = self._id(l, e)
+                if not self.resident[i] or i in in_use:
+                    continue
+                if not allow_protected and i in self.protected:
+                    continue
+                if self.visits[i] < best_v:
+                    best, best_v = i, self.visits[i]
+        return best
+
+    def _acquire(self, in_use: Sequence[int], prefetch: bool) -> bool:
+        if self.free > 0:
+            self.free -= 1
+            return True
+        v = self._victim(in_use, False)
+        if v < 0 and not prefetch:
+            v = self._victim(in_use, True)
+        if v < 0:
+            return False
+        self.resident[v] = False
+        self.prefetched_unused[v] = False
+        self.stats["evictions"] += 1
+        self.evicted_log.append((v // self.E, v % self.E))
+        return True
+
+    def dispatch(self, layer: int, experts: Iterable[int]) -> List[Tuple[int, bool]]:
+        """One MoE layer call with the given activated experts (ascending).  Returns [(expert, hit)]."""
+        active = [self._id(layer, e) for e in sorted(experts)]
+        out = []
+        for i in active:
+            self.stats["dispatches"] += 1
+            self.visits[i] += 1
+            if self.resident[i]:
+                self.stats["hits"] += 1
+                if self.prefetched_unused[i]:
+                    self.stats["prefetch_useful"] += 1
+                    self.prefetched_unused[i] = False
+                out.append((i % self.E, True))
+            else:
+                self.stats["misses"] += 1
+                if not self._acquire(active, False):
+                    raise RuntimeError("no evictable slot")
+                self.resident[i] = True
+                out.append((i % self.E, False))
+        self.last_active = active
+        return out
+
+    def replace_cache_candidates(self, pairs: Iterable[Tuple[int, int]]):
+        self.protected = {self._id(l, e) for l, e in pairs}
+
+    def prefetch(self, pairs: Sequence[Tuple[int, int]]):
+        """Queued prefetches processed in order (the engine after b2m_prefetch_drain)."""
+        for l, e in pairs:
+            i = self._id(l, e)
+            if self.resident[i]:
+                continue
+            if not self._acquire(self.last_active, True):
+                break       # nothing evictable without touching protected experts: rest of the queue is dropped
+            self.resident[i] = True
+            self.prefetched_unused[i] = True
+            self.stats["prefetch_issued"] += 1
+
+    def prefetch_hint(self, pairs: Sequence[Tuple[int, int]], scores: Sequence[float]):
+        order = sorted(range(len(pairs)), key=lambda i: -scores[i])   # stable, descending
+        ordered = [pairs[i] for i in order]
+        self.replace_cache_candidates(ordered)
+        self.prefetch(ordered)
+
+    def clear_counts(self):
+        self.visits = [0] * len(self.visits)

@@ -1,0 +1,141 @@
+"""GPU: HBM expert cache + prefetch scheduler (forced offload, BASELINE config 3 in miniature).
+
+The CUDA engine must (a) produce the same hidden states as the all-resident run while experts are being
+evicted and re-staged from pinned host memory, and (b) reproduce the hit/miss/eviction sequence of
+oracle/policy_oracle.py exactly on a seeded routing trace."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import moe_oracle as O  # noqa: E402
+from oracle.policy_oracle import CacheOracle  # noqa: E402
+
+H, I, E, K, L = 128, 256, 8, 2, 3
+DT = torch.bfloat16
+
+
+def _model(seed=5):
+    experts = [O.make_experts(E, H, I, DT, seed + l, std=0.05) for l in range(L)]
+    g = torch.Generator().manual_seed(seed)
+    gates = [(torch.randn(E, H, generator=g) * 0.3).to(DT) for _ in range(L)]
+    return experts, gates
+
+
+def _engine(experts, gates, num_slots, **kw):
+    from moe_infinity_b200 import MoEEngine
+    eng = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=K, dtype=DT, max_tokens=64,
+                    num_slots=num_slots, **kw)
+    for l in range(L):
+        for e in range(E):
+            eng.register_expert(l, e, experts[l][e])
+        eng.set_gate(l, gates[l])
+    return eng
+
+
+def test_offload_outputs_match_all_resident(lib_built):
+    experts, gates = _model()
+    full = _engine(experts, gates, L * E)
+    small = _engine(experts, gates, 5)            # 5 slots for 24 experts: constant eviction
+    g = torch.Generator().manual_seed(1)
+    for step in range(6):
+        for l in range(L):
+            x = torch.randn(7, H, generator=g).to(DT).cuda()
+            a = full.forward(l, x)
+            b = small.forward(l, x)
+            torch.cuda.synchronize()
+            assert torch.equal(a, b), f"step {step} layer {l}: offloaded run differs from resident run"
+    st = small.stats()
+    assert st["misses"] > 0 and st["evictions"] > 0 and st["host_syncs"] == 6 * L
+    assert st["h2d_bytes"] == st["misses"] * 3 * H * I * 2
+    assert full.stats()["host_syncs"] == 0 and full.stats()["misses"] == 0
+    assert st["resident"] <= 5
+
+
+def test_cache_policy_matches_oracle(lib_built):
+    experts, gates = _model(7)
+    nslots = 6
+    eng = _engine(experts, gates, nslots)
+    orc = CacheOracle(L, E, nslots)
+    g = torch.Generator().manual_seed(2)
+    for step in range(10):
+        for l in range(L):
+            x = torch.randn(5, H, generator=g).to(DT).cuda()
+            before = {e: eng.is_resident(l, e) for e in range(E)}
+            eng.forward(l, x)
+            counts = eng.last_counts()
+            active = [e for e in range(E) if counts[e] > 0]
+            exp = orc.dispatch(l, active)
+            assert [(e, before[e]) for e in active] == exp, f"step {step} layer {l}"
+            for ll in range(L):
+                for e in range(E):
+                    assert eng.is_resident(ll, e) == orc.resident[ll * E + e]
+    s = eng.stats()
+    for k in ("dispatches", "hits", "misses", "evictions"):
+        assert s[k] == orc.stats[k], k
+
+
+def test_prefetch_protects_and_counts(lib_built):
+    experts, gates = _model(9)
+    nslots = 6
+    eng = _engine(experts, gates, nslots)
+    orc = CacheOracle(L, E, nslots)
+    g = torch.Generator().manual_seed(3)
+    rng = np.random.default_rng(0)
+    for step in range(8):
+        for l in range(L):
+            x = torch.randn(4, H, generator=g).to(DT).cuda()
+            out = eng.forward(l, x)
+            counts = eng.last_counts()
+            active = [e for e in range(E) if counts[e] > 0]
+            orc.dispatch(l, active)
+            nl = (l + 1) % L
+            cand = rng.choice(E, size=3, replace=False).tolist()
+            scores = rng.random(3).tolist()
+            pairs = [(nl, int(e)) for e in cand]
+            eng.prefetch_hint(pairs, scores)
+            eng.prefetch_drain()
+            orc.prefetch_hint(pairs, scores)
+            for ll in range(L):
+                for e in range(E):
+                    assert eng.is_resident(ll, e) == orc.resident[ll * E + e], (step, l, ll, e)
+    s = eng.stats()
+    for k in ("dispatches", "hits", "misses", "evictions", "prefetch_issued", "prefetch_useful"):
+        assert s[k] == orc.stats[k], (k, s[k], orc.stats[k])
+    assert s["prefetch_issued"] > 0 and s["prefetch_useful"] > 0
+    # numerics unaffected by staging order
+    ref = _engine(experts, gates, L * E)
+    x = torch.randn(9, H, generator=g).to(DT).cuda()
+    for l in range(L):
+        assert torch.equal(eng.forward(l, x), ref.forward(l, x))
+
+
+def test_clear_counts_and_chunked_copies(lib_built):
+    experts, gates = _model(11)
+    eng = _engine(experts, gates, 4, h2d_chunk_bytes=64 * 1024)   # many chunks per expert
+    ref = _engine(experts, gates, L * E)
+    g = torch.Generator().manual_seed(4)
+    for l in range(L):
+        x = torch.randn(3, H, generator=g).to(DT).cuda()
+        assert torch.equal(eng.forward(l, x), ref.forward(l, x))
+    eng.clear_expert_cache_counts()
+    assert eng.stats()["misses"] > 0
+
+
+def test_too_few_slots_is_an_error_not_an_abort(lib_built):
+    from moe_infinity_b200 import B2MError
+    experts, gates = _model(13)
+    eng = _engine(experts, gates, 1)
+    x = torch.randn(6, H).to(DT).cuda()
+    with pytest.raises(B2MError) as ei:
+        eng.forward(0, x)                 # top-2 needs >= 2 experts resident at once
+    assert "slot" in str(ei.value)
+
+
+def test_unregistered_expert_is_an_error(lib_built):
+    from moe_infinity_b200 import MoEEngine, B2MError
+    eng = MoEEngine(num_layers=1, num_experts=E, hidden=H, inter=I, top_k=K, dtype=DT, max_tokens=16, num_slots=E)
+    eng.set_gate(0, torch.randn(E, H))
+    with pytest.raises(B2MError):
+        eng.forward(0, torch.randn(4, H).to(DT).cuda())

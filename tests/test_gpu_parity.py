@@ -40,14 +40,14 @@ def hidden_close(y, y_ref, y32, dtype, what=""):
         bound = 2 * eps * y_ref.abs() + 2 * eps * rms
     bad = diff > bound
     if dtype == torch.float16 and bool(bad.any()):
-        # Both sides replay the reference's chain of fp16 roundings (g, silu, h, out, out*w, +=) with different
-        # fp32 accumulation orders in the GEMMs; a one-ulp flip of an intermediate can surface as a 2-ulp
-        # difference of the final fp16 value (rel. 1e-3..2e-3 just above a power of two).  Allow that on at most
-        # 1e-4 of the elements, never more than 2 fp16 ulp; everything else obeys the 1e-3 bound.
-        ulp2 = 2.05 * torch.finfo(torch.float16).eps * y_ref.abs().clamp_min(rms)   # >= 2 ulp(y) (+ float slack)
-        assert bool((diff[bad] <= ulp2[bad]).all()) and int(bad.sum()) <= max(1, int(1e-4 * bad.numel())), (
+        # Both sides replay the reference's chain of fp16 roundings (g, silu, h, out, out*w, +=) on top of GEMMs
+        # with different fp32 accumulation orders.  A one-ulp flip of an intermediate (e.g. of one of the two
+        # expert outputs that are summed, which can be larger than their sum) surfaces as a final difference of
+        # a few fp16 ulp.  Allow at most 1e-4 of the elements to exceed the 1e-3 bound, and never by more than 2x;
+        # the "not worse than the reference against the fp32 oracle" check below still applies to all elements.
+        assert bool((diff[bad] <= 2 * bound[bad]).all()) and int(bad.sum()) <= max(1, int(1e-4 * bad.numel())), (
             f"{what}: {int(bad.sum())}/{bad.numel()} elements beyond 1e-3, max diff {diff.max().item():.3e}, "
-            f"worst ratio to 2ulp {(diff[bad] / ulp2[bad]).max().item():.3f}")
+            f"worst ratio to bound {(diff[bad] / bound[bad]).max().item():.3f}")
         bad = torch.zeros_like(bad)
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance; "
                                  f"max diff {diff.max().item():.3e}, rms {rms:.3e}")
