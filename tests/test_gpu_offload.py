@@ -37,7 +37,7 @@ def _engine(experts, gates, num_slots, **kw):
 def test_offload_outputs_match_all_resident(lib_built):
     experts, gates = _model()
     full = _engine(experts, gates, L * E)
-    small = _engine(experts, gates, 5)            # 5 slots for 24 experts: constant eviction
+    small = _engine(experts, gates, 9)            # 9 slots for 24 experts (>= E: one layer's active set must fit)
     g = torch.Generator().manual_seed(1)
     for step in range(6):
         for l in range(L):
@@ -50,12 +50,12 @@ def test_offload_outputs_match_all_resident(lib_built):
     assert st["misses"] > 0 and st["evictions"] > 0 and st["host_syncs"] == 6 * L
     assert st["h2d_bytes"] == st["misses"] * 3 * H * I * 2
     assert full.stats()["host_syncs"] == 0 and full.stats()["misses"] == 0
-    assert st["resident"] <= 5
+    assert st["resident"] <= 9
 
 
 def test_cache_policy_matches_oracle(lib_built):
     experts, gates = _model(7)
-    nslots = 6
+    nslots = 10
     eng = _engine(experts, gates, nslots)
     orc = CacheOracle(L, E, nslots)
     g = torch.Generator().manual_seed(2)
@@ -78,7 +78,7 @@ def test_cache_policy_matches_oracle(lib_built):
 
 def test_prefetch_protects_and_counts(lib_built):
     experts, gates = _model(9)
-    nslots = 6
+    nslots = 11
     eng = _engine(experts, gates, nslots)
     orc = CacheOracle(L, E, nslots)
     g = torch.Generator().manual_seed(3)
@@ -113,7 +113,7 @@ def test_prefetch_protects_and_counts(lib_built):
 
 def test_clear_counts_and_chunked_copies(lib_built):
     experts, gates = _model(11)
-    eng = _engine(experts, gates, 4, h2d_chunk_bytes=64 * 1024)   # many chunks per expert
+    eng = _engine(experts, gates, 8, h2d_chunk_bytes=64 * 1024)   # many chunks per expert
     ref = _engine(experts, gates, L * E)
     g = torch.Generator().manual_seed(4)
     for l in range(L):
