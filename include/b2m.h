@@ -199,6 +199,20 @@ int b2m_stats_get(b2m_ctx* ctx, b2m_stats* out);
  * counts_host[E]; returns B2M_ESTATE if the last call ran sync-free */
 int b2m_last_counts(b2m_ctx* ctx, int32_t* counts_host);
 
+/* ---- expert parallel (BASELINE config 5): one process per GPU, rank r owns experts [r*E/N, (r+1)*E/N).
+ * The reference has no live collective (README.md:18; dead code modeling_deepseek.py:657-721); these helpers
+ * replace its `.to(device)` token moves (expert_dispatcher.cpp:283-285,403-405) around a fixed-capacity
+ * all-to-all (cap = rows per peer, >= T_local*top_k).  Buffers are caller-owned device memory:
+ *   send_rows/recv_rows/ret_rows/back_rows [nranks][cap][H] model dtype; send_counts [E]; recv_counts [nranks][E].
+ * Call order per layer: b2m_route -> b2m_ep_pack -> (exchange counts+rows) -> b2m_ep_regroup -> b2m_run_experts(T_total)
+ *   -> b2m_ep_ungroup -> (exchange back) -> b2m_ep_unpack -> b2m_combine. */
+int b2m_ep_pack(b2m_ctx* ctx, int nranks, int rank, int cap, int T_local, void* send_rows, int32_t* send_counts,
+                void* stream);
+int b2m_ep_regroup(b2m_ctx* ctx, int nranks, int rank, int cap, int T_total, const void* recv_rows,
+                   const int32_t* recv_counts, void* stream);
+int b2m_ep_ungroup(b2m_ctx* ctx, int nranks, int rank, int cap, void* ret_rows, void* stream);
+int b2m_ep_unpack(b2m_ctx* ctx, int nranks, int rank, int cap, int T_local, const void* back_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

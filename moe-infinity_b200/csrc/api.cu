@@ -131,6 +131,9 @@ struct b2m_ctx {
   std::vector<int> last_active;
 
   int cur_ksplit = 1, cur_nt = 16, cur_T = 0;
+  bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
+  int* d_offsets_src = nullptr;  // [E+1]
+  int* d_dest_of = nullptr;      // [cap_R]
   b2m_stats stats;
 };
 
@@ -512,6 +515,8 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_counts, sizeof(int) * E));
   CKC(cudaMalloc((void**)&c->d_offsets, sizeof(int) * (E + 1)));
   CKC(cudaMemset(c->d_offsets, 0, sizeof(int) * (E + 1)));
+  CKC(cudaMalloc((void**)&c->d_offsets_src, sizeof(int) * (E + 1)));
+  CKC(cudaMalloc((void**)&c->d_dest_of, sizeof(int) * R));
   CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
   CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
   CKC(cudaMalloc((void**)&c->d_logits, sizeof(float) * (size_t)T * E));
@@ -550,7 +555,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -768,7 +773,8 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
     for (int e = 0; e < E; ++e)
       if (c->h_counts[e] > 0) active.push_back(layer * E + e);
   } else {
-    for (int e = 0; e < E; ++e) active.push_back(layer * E + e);
+    for (int e = 0; e < E; ++e)
+      if (!c->ep_mode || c->experts[(size_t)layer * E + e].state != ST_UNREGISTERED) active.push_back(layer * E + e);
   }
   // residency
   for (int id : active) {
@@ -976,6 +982,75 @@ int b2m_last_counts(b2m_ctx* c, int32_t* counts_host) {
   if (!c || !counts_host) return B2M_EINVAL;
   if (!c->last_counts_valid) return fail(c, B2M_ESTATE, "last call ran sync-free; counts were not read back");
   memcpy(counts_host, c->h_counts, sizeof(int) * c->cfg.num_experts);
+  return B2M_OK;
+}
+
+// ------------------------------------------------------------------------------------ expert parallel
+static EpParams ep_base(b2m_ctx* c, int nranks, int rank, int cap) {
+  EpParams p;
+  memset(&p, 0, sizeof p);
+  p.nranks = nranks; p.rank = rank; p.E = c->cfg.num_experts; p.H = c->cfg.hidden; p.cap = cap;
+  p.offsets = c->d_offsets; p.offsets_rw = c->d_offsets; p.offsets_src = c->d_offsets_src;
+  p.xp = c->d_xp; p.y = c->d_y; p.dest_of = c->d_dest_of;
+  return p;
+}
+static int ep_check(b2m_ctx* c, int nranks, int rank, int cap) {
+  if (!c) return B2M_EINVAL;
+  if (nranks < 2 || nranks > 16 || rank < 0 || rank >= nranks || c->cfg.num_experts % nranks || cap < 1)
+    return fail(c, B2M_EINVAL, "bad expert-parallel geometry (nranks=%d rank=%d cap=%d E=%d)", nranks, rank, cap, c->cfg.num_experts);
+  if ((long long)nranks * cap > c->cap_R)
+    return fail(c, B2M_EINVAL, "workspace too small for EP: nranks*cap=%d rows > %d (create the context with max_tokens >= nranks*T_local)", nranks * cap, c->cap_R);
+  return B2M_OK;
+}
+
+int b2m_ep_pack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, void* send_rows, int32_t* send_counts, void* stream) {
+  int r = ep_check(c, nranks, rank, cap);
+  if (r) return r;
+  if (T_local * c->cfg.top_k > cap) return fail(c, B2M_EINVAL, "cap=%d < T_local*top_k=%d", cap, T_local * c->cfg.top_k);
+  EpParams p = ep_base(c, nranks, rank, cap);
+  p.send_rows = send_rows;
+  p.send_counts = send_counts;
+  CK(c, launch_ep_pack(p, T_local * c->cfg.top_k, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  c->ep_mode = true;
+  return B2M_OK;
+}
+
+int b2m_ep_regroup(b2m_ctx* c, int nranks, int rank, int cap, int T_total, const void* recv_rows, const int32_t* recv_counts, void* stream) {
+  int r = ep_check(c, nranks, rank, cap);
+  if (r) return r;
+  if (T_total < 1 || T_total > c->cap_T) return fail(c, B2M_EINVAL, "T_total=%d exceeds workspace capacity %d", T_total, c->cap_T);
+  EpParams p = ep_base(c, nranks, rank, cap);
+  p.recv_rows = recv_rows;
+  p.recv_counts = recv_counts;
+  // plan the local GEMMs for the rows this rank may receive
+  c->cur_T = T_total;
+  c->cur_nt = pick_nt(T_total);
+  c->cur_ksplit = pick_ksplit(c, T_total, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts / nranks, c->cfg.top_k, c->cur_nt);
+  if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)nranks * cap * c->cfg.hidden; }
+  CK(c, launch_ep_regroup(p, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  c->ep_mode = true;
+  return B2M_OK;
+}
+
+int b2m_ep_ungroup(b2m_ctx* c, int nranks, int rank, int cap, void* ret_rows, void* stream) {
+  int r = ep_check(c, nranks, rank, cap);
+  if (r) return r;
+  EpParams p = ep_base(c, nranks, rank, cap);
+  p.ret_rows = ret_rows;
+  CK(c, launch_ep_ungroup(p, c->cfg.dtype, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+int b2m_ep_unpack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, const void* back_rows, void* stream) {
+  int r = ep_check(c, nranks, rank, cap);
+  if (r) return r;
+  EpParams p = ep_base(c, nranks, rank, cap);
+  p.back_rows = back_rows;
+  CK(c, launch_ep_unpack(p, c->cfg.dtype, T_local * c->cfg.top_k, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
   return B2M_OK;
 }
 

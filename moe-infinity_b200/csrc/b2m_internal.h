@@ -93,6 +93,29 @@ struct CombineParams {
 };
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
 
+// ---- expert-parallel dispatch helpers (ep.cu) ----------------------------------------------
+struct EpParams {
+  int nranks, rank, E, H, cap;      // cap = rows per peer in the fixed-capacity exchange buffers
+  const int* offsets;               // in: routing offsets[E+1] (pack) ; out: regrouped offsets (regroup)
+  int* offsets_rw;                  // same buffer, writable (regroup)
+  int* offsets_src;                 // [E+1] source-side copy kept for unpack
+  int* send_counts;                 // [E] this rank's per-expert row counts
+  const int* recv_counts;           // [nranks][E] all ranks' counts
+  void* xp;                         // workspace rows (pack: in, regroup: out)
+  void* send_rows;                  // [nranks][cap][H]
+  const void* recv_rows;            // [nranks][cap][H]
+  void* ret_rows;                   // [nranks][cap][H]
+  const void* back_rows;            // [nranks][cap][H]
+  float* y;                         // fp32 expert outputs
+  int* dest_of;                     // [nranks*cap] workspace row of each received slot (-1: empty)
+  float* y_zero;
+  size_t y_zero_elems;
+};
+cudaError_t launch_ep_pack(const EpParams& p, int max_rows, cudaStream_t st);
+cudaError_t launch_ep_regroup(const EpParams& p, cudaStream_t st);
+cudaError_t launch_ep_ungroup(const EpParams& p, int dtype, cudaStream_t st);
+cudaError_t launch_ep_unpack(const EpParams& p, int dtype, int max_rows, cudaStream_t st);
+
 // fp32 [rows,H] -> model dtype [rows,H] (compat path: per-expert outputs handed back to Python)
 cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st);
 

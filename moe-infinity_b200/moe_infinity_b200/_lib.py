@@ -71,6 +71,10 @@ SYMBOLS = [
     ("b2m_is_resident", _I, [_VP, _I, _I]),
     ("b2m_stats_get", _I, [_VP, C.POINTER(Stats)]),
     ("b2m_last_counts", _I, [_VP, C.POINTER(C.c_int32)]),
+    ("b2m_ep_pack", _I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    ("b2m_ep_regroup", _I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    ("b2m_ep_ungroup", _I, [_VP, _I, _I, _I, _VP, _VP]),
+    ("b2m_ep_unpack", _I, [_VP, _I, _I, _I, _I, _VP, _VP]),
 ]
 
 _lib = None

@@ -1,0 +1,225 @@
+"""Expert-parallel MoE layer over the GPUs of one box (BASELINE config 5): one process per GPU,
+torch.distributed (NCCL over NVLink/NVSwitch) for the exchange, libb2m.so kernels for everything else.
+
+Sharding: rank r owns experts [r*E/N, (r+1)*E/N) of every layer (contiguous blocks, so the expert-sorted
+gathered rows of a rank are already contiguous per destination).  Per layer:
+    route (local tokens) -> ep_pack -> all_gather(counts) + all_to_all(rows, fixed capacity cap = T_local*k per peer)
+    -> ep_regroup -> grouped GEMMs on the received rows -> ep_ungroup -> all_to_all back -> ep_unpack -> combine.
+Nothing in the layer synchronises with the host; capacity is static so no rank ever needs another rank's counts
+on the CPU.  The reference has no live collective (README.md:18) -- it moves rows with `.to(device)`
+inside one process (core/parallel/expert_dispatcher.cpp:283-285,403-405).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def owner_rank(expert: int, num_experts: int, world: int) -> int:
+    return expert // (num_experts // world)
+
+
+def local_experts(rank: int, num_experts: int, world: int):
+    el = num_experts // world
+    return list(range(rank * el, (rank + 1) * el))
+
+
+class _EngineOps:
+    """Device steps of one EP layer, implemented by the CUDA engine."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def _s(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def route(self, layer, x, router_logits=None):
+        return self.eng.route(layer, x, router_logits=router_logits)
+
+    def pack(self, world, rank, cap, T, send_rows, send_counts):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_pack(e._h, world, rank, cap, T, C.c_void_p(send_rows.data_ptr()),
+                                C.c_void_p(send_counts.data_ptr()), self._s()))
+
+    def regroup(self, world, rank, cap, T_total, recv_rows, recv_counts):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_regroup(e._h, world, rank, cap, T_total, C.c_void_p(recv_rows.data_ptr()),
+                                   C.c_void_p(recv_counts.data_ptr()), self._s()))
+
+    def run_experts(self, layer, T_total):
+        self.eng.run_experts(layer, T_total)
+
+    def ungroup(self, world, rank, cap, ret_rows):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_ungroup(e._h, world, rank, cap, C.c_void_p(ret_rows.data_ptr()), self._s()))
+
+    def unpack(self, world, rank, cap, T, back_rows):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_unpack(e._h, world, rank, cap, T, C.c_void_p(back_rows.data_ptr()), self._s()))
+
+    def combine(self, layer, x, out):
+        return self.eng.combine(layer, x, out=out)
+
+
+class EPMoE:
+    """One expert-parallel MoE layer stack.  `ops` is the device backend (the CUDA engine in production; tests inject
+    a CPU stand-in to exercise the exchange schedule under gloo)."""
+
+    def __init__(self, ops, *, num_experts: int, hidden: int, top_k: int, T_local: int, dtype, device,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.ops = ops
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if num_experts % self.world:
+            raise ValueError("num_experts must be divisible by the world size")
+        self.E, self.H, self.k, self.T = num_experts, hidden, top_k, T_local
+        self.cap = T_local * top_k
+        self.T_total = self.world * T_local
+        shape = (self.world, self.cap, hidden)
+        self.send_rows = torch.zeros(shape, dtype=dtype, device=device)
+        self.recv_rows = torch.zeros(shape, dtype=dtype, device=device)
+        self.ret_rows = torch.zeros(shape, dtype=dtype, device=device)
+        self.back_rows = torch.zeros(shape, dtype=dtype, device=device)
+        self.send_counts = torch.zeros(num_experts, dtype=torch.int32, device=device)
+        self.recv_counts = torch.zeros(self.world, num_experts, dtype=torch.int32, device=device)
+
+    def forward(self, layer: int, x: torch.Tensor, out: Optional[torch.Tensor] = None, router_logits=None):
+        T = x.shape[0]
+        if T != self.T:
+            raise ValueError(f"EPMoE was sized for T_local={self.T}, got {T}")
+        w, r, cap = self.world, self.rank, self.cap
+        self.ops.route(layer, x, router_logits)
+        self.ops.pack(w, r, cap, T, self.send_rows, self.send_counts)
+        dist.all_gather_into_tensor(self.recv_counts.view(-1), self.send_counts, group=self.group)
+        dist.all_to_all_single(self.recv_rows, self.send_rows, group=self.group)
+        self.ops.regroup(w, r, cap, self.T_total, self.recv_rows, self.recv_counts)
+        self.ops.run_experts(layer, self.T_total)
+        self.ops.ungroup(w, r, cap, self.ret_rows)
+        dist.all_to_all_single(self.back_rows, self.ret_rows, group=self.group)
+        self.ops.unpack(w, r, cap, T, self.back_rows)
+        return self.ops.combine(layer, x, out)
+
+
+# --------------------------------------------------------------------------------------------- bench (N > 1)
+def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
+    from .engine import MoEEngine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    L, E, H, I, k = (args.layers or cfg["L"]), cfg["E"], cfg["H"], cfg["I"], cfg["k"]
+    if E % world:
+        raise SystemExit(f"--gpus {world} does not divide the {E} experts")
+    T = batch
+    dtype = torch.bfloat16
+    mine = local_experts(rank, E, world)
+    eng = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype,
+                    max_tokens=max(world * T, 16), num_slots=L * len(mine), device=local)
+    torch.manual_seed(1000 + rank)
+    for l in range(L):
+        for e in mine:
+            eng.load_expert(l, e).normal_(0.0, 0.02)
+    g = torch.Generator(device=dev).manual_seed(0)           # gates are replicated: same seed on every rank
+    for l in range(L):
+        eng.set_gate(l, torch.randn(E, H, device=dev, generator=g) * 0.02)
+    x_dev = torch.randn(L, T, H, device=dev).to(dtype)
+    out_dev = torch.empty_like(x_dev)
+    ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev)
+
+    def step():
+        for l in range(L):
+            ep.forward(l, x_dev[l], out=out_dev[l])
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    launches0 = eng.stats()["kernel_launches"]
+    step()
+    launches_per_step = eng.stats()["kernel_launches"] - launches0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        step_ms.append((a, b))
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    total_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    p50 = sorted(a.elapsed_time(b) for a, b in step_ms)[len(step_ms) // 2]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: host buffers, copies inside the timed region
+    x_host = x_dev.cpu().pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    x_in = torch.empty_like(x_dev)
+
+    def step_e2e():
+        x_in.copy_(x_host, non_blocking=True)
+        for l in range(L):
+            ep.forward(l, x_in[l], out=out_dev[l])
+        out_host.copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    wall = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    e2e_ms = float(wall.item()) * 1e3
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ms_per_step = total_ms / args.steps
+        el = len(mine)
+        bytes_rank = L * el * 3 * H * I * 2       # every local expert is hit w.h.p. at T_total*k >= 32 assignments
+        ach = bytes_rank / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": metric, "value": world * batch * args.steps / (total_ms * 1e-3), "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "p50_token_latency_ms": p50, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Mixtral-8x7B MoE dispatch path, expert-parallel over {world} GPUs "
+                                   f"({el} experts/GPU/layer), decode batch {batch} per GPU (global {world*batch}), "
+                                   f"{L} layers, bf16 random-init, all local experts HBM-resident",
+                       "global_batch": world * batch, "layers": L, "parallelism": f"ep{world}",
+                       "exchange": "fixed-capacity all_to_all_single (NCCL) each way + all_gather of counts",
+                       "l2": "inputs larger than L2 (each rank streams %.1f GB of weights per step)" % (bytes_rank / 1e9),
+                       "timed_region": "eager launches, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "peak_source": peak_src, "scope": "whole step, per rank", "traffic": None,
+                         "algorithmic_bytes_per_rank_step": bytes_rank},
+            "cpu_baseline": None,
+            "e2e": {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": x_host.numel() * 2 * world, "d2h_bytes_per_step": out_host.numel() * 2 * world,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps * world), "launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,59 @@
+"""torchrun worker for tests/test_gpu_ep.py: EP over WORLD_SIZE GPUs vs the same layer on one GPU."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "moe-infinity_b200")):
+    sys.path.insert(0, p)
+
+import torch
+import torch.distributed as dist
+
+from moe_infinity_b200 import MoEEngine
+from moe_infinity_b200.ep import EPMoE, _EngineOps, local_experts
+from oracle import moe_oracle as O
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    H, I, E, K, T, L = 256, 512, 8, 2, 12, 2
+    dt = torch.bfloat16
+    experts = [O.make_experts(E, H, I, dt, seed=10 + l, std=0.05) for l in range(L)]
+    g = torch.Generator().manual_seed(3)
+    gates = [(torch.randn(E, H, generator=g) * 0.3).to(dt) for _ in range(L)]
+    full = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=K, dtype=dt, max_tokens=64, device=local)
+    part = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=K, dtype=dt, max_tokens=world * T,
+                     num_slots=L * E // world, device=local)
+    for l in range(L):
+        for e in range(E):
+            full.load_expert(l, e, experts[l][e])
+        for e in local_experts(rank, E, world):
+            part.load_expert(l, e, experts[l][e])
+        full.set_gate(l, gates[l])
+        part.set_gate(l, gates[l])
+    ep = EPMoE(_EngineOps(part), num_experts=E, hidden=H, top_k=K, T_local=T, dtype=dt, device=dev)
+    gx = torch.Generator().manual_seed(50 + rank)
+    bad = 0
+    for it in range(4):
+        for l in range(L):
+            x = torch.randn(T, H, generator=gx).to(dt).cuda()
+            a = full.forward(l, x).clone()
+            b = ep.forward(l, x)
+            torch.cuda.synchronize()
+            if not torch.equal(a, b):
+                bad += 1
+                print(f"rank {rank} it {it} layer {l}: max diff {(a.float()-b.float()).abs().max().item()}", flush=True)
+    t = torch.tensor([bad], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print("EP_WORKER_RESULT", "OK" if int(t.item()) == 0 else f"MISMATCH {int(t.item())}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
