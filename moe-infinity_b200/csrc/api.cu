@@ -762,9 +762,11 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   if (r) return r;
   std::vector<int> active;
   const bool do_residency = (phases & 1) != 0;
+  // expert-parallel contexts hold only this rank's experts, all resident: never the on-demand path
+  const bool on_demand = c->offload && !c->ep_mode;
   if (!do_residency) {
     active = c->last_active;
-  } else if (c->offload) {
+  } else if (on_demand) {
     // on-demand path: read the per-expert counts back (the reference's .cpu() in dispatch_local)
     CK(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
@@ -781,19 +783,20 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
     if (!do_residency) break;
     Expert& x = c->experts[id];
     if (x.state == ST_UNREGISTERED) return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
-    if (c->offload) {
+    if (on_demand) {
       c->stats.dispatches++;
       x.visits += 1;            // incache_visit_count += 1 for every dispatched expert (expert_dispatcher.cpp:264)
       x.total_visits += 1;
     }
     if (x.state == ST_RESIDENT || x.state == ST_LOADING) {
-      if (c->offload) {
+      if (on_demand) {
         c->stats.hits++;
         if (x.prefetched_unused) { c->stats.prefetch_useful++; x.prefetched_unused = false; }
       }
     } else {
       if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
-      if (c->offload) c->stats.misses++;
+      if (c->ep_mode) return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", id / E, id % E);
+      if (on_demand) c->stats.misses++;
       const int slot = acquire_slot(c, active, false);
       if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot: %d experts active, %d slots", (int)active.size(), c->arena.nslots);
       r = issue_copy(c, id, slot, c->fetch_stream, true);
@@ -822,7 +825,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
                           c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
   if (r) return r;
   if (do_residency) c->last_active = active;
-  if (c->offload && (phases & 2)) {
+  if (on_demand && (phases & 2)) {
     int evi;
     cudaEvent_t ev = next_ring_event(c, &evi);
     CK(c, cudaEventRecord(ev, st));
