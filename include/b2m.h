@@ -204,6 +204,9 @@ int b2m_last_counts(b2m_ctx* ctx, int32_t* counts_host);
  * replace its `.to(device)` token moves (expert_dispatcher.cpp:283-285,403-405) around a fixed-capacity
  * all-to-all (cap = rows per peer, >= T_local*top_k).  Buffers are caller-owned device memory:
  *   send_rows/recv_rows/ret_rows/back_rows [nranks][cap][H] model dtype; send_counts [E]; recv_counts [nranks][E].
+ *   Passing NULL for send_counts / recv_counts selects the inline layout: all four row buffers are
+ *   [nranks][cap+1][H] and the extra last row of every peer segment carries counts[E] (int32, needs 4E <= 2H),
+ *   so one all-to-all moves rows and counts together.
  * Call order per layer: b2m_route -> b2m_ep_pack -> (exchange counts+rows) -> b2m_ep_regroup -> b2m_run_experts(T_total)
  *   -> b2m_ep_ungroup -> (exchange back) -> b2m_ep_unpack -> b2m_combine. */
 int b2m_ep_pack(b2m_ctx* ctx, int nranks, int rank, int cap, int T_local, void* send_rows, int32_t* send_counts,

@@ -132,6 +132,7 @@ struct b2m_ctx {
 
   int cur_ksplit = 1, cur_nt = 16, cur_T = 0;
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
+  int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_dest_of = nullptr;      // [cap_R]
   b2m_stats stats;
@@ -394,10 +395,10 @@ void plan_gemm(b2m_ctx* c, int T) {
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt);
 }
 
-int route_launch_count(int T, int router) {
+int route_launch_count(int T, int router, bool fused_gate) {
   if (T == 0) return 0;
   if (T <= 256) return 2;
-  return router == B2M_ROUTER_SWITCH_TOP1 ? 5 : 3;
+  return (router == B2M_ROUTER_SWITCH_TOP1 ? 5 : 3) + (fused_gate ? 1 : 0);
 }
 
 }  // namespace
@@ -702,7 +703,7 @@ int b2m_route(b2m_ctx* c, int layer, const void* x, const void* router_in, int k
   plan_gemm(c, T);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
   CK(c, launch_route(p, st));
-  c->stats.kernel_launches += route_launch_count(T, c->cfg.router);
+  c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0);
   c->last_counts_valid = false;
   return B2M_OK;
 }
@@ -1013,6 +1014,8 @@ int b2m_ep_pack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, void* se
   EpParams p = ep_base(c, nranks, rank, cap);
   p.send_rows = send_rows;
   p.send_counts = send_counts;
+  p.inline_counts = send_counts == nullptr;   // counts ride in the row buffers ([nranks][cap+1][H])
+  c->ep_inline = p.inline_counts;
   CK(c, launch_ep_pack(p, T_local * c->cfg.top_k, (cudaStream_t)stream));
   c->stats.kernel_launches += 1;
   c->ep_mode = true;
@@ -1026,6 +1029,8 @@ int b2m_ep_regroup(b2m_ctx* c, int nranks, int rank, int cap, int T_total, const
   EpParams p = ep_base(c, nranks, rank, cap);
   p.recv_rows = recv_rows;
   p.recv_counts = recv_counts;
+  p.inline_counts = recv_counts == nullptr;
+  c->ep_inline = p.inline_counts;
   // plan the local GEMMs for the rows this rank may receive
   c->cur_T = T_total;
   c->cur_nt = pick_nt(T_total);
@@ -1042,6 +1047,7 @@ int b2m_ep_ungroup(b2m_ctx* c, int nranks, int rank, int cap, void* ret_rows, vo
   if (r) return r;
   EpParams p = ep_base(c, nranks, rank, cap);
   p.ret_rows = ret_rows;
+  p.inline_counts = c->ep_inline;
   CK(c, launch_ep_ungroup(p, c->cfg.dtype, (cudaStream_t)stream));
   c->stats.kernel_launches += 1;
   return B2M_OK;
@@ -1052,6 +1058,7 @@ int b2m_ep_unpack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, const 
   if (r) return r;
   EpParams p = ep_base(c, nranks, rank, cap);
   p.back_rows = back_rows;
+  p.inline_counts = c->ep_inline;
   CK(c, launch_ep_unpack(p, c->cfg.dtype, T_local * c->cfg.top_k, (cudaStream_t)stream));
   c->stats.kernel_launches += 1;
   return B2M_OK;

@@ -96,6 +96,7 @@ cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
 // ---- expert-parallel dispatch helpers (ep.cu) ----------------------------------------------
 struct EpParams {
   int nranks, rank, E, H, cap;      // cap = rows per peer in the fixed-capacity exchange buffers
+  int inline_counts;                // 1: buffers are [nranks][cap+1][H]; the extra last row carries counts[E] (int32)
   const int* offsets;               // in: routing offsets[E+1] (pack) ; out: regrouped offsets (regroup)
   int* offsets_rw;                  // same buffer, writable (regroup)
   int* offsets_src;                 // [E+1] source-side copy kept for unpack

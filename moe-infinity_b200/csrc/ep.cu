@@ -32,9 +32,17 @@ __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
   const int El = p.E / p.nranks;
   if (threadIdx.x <= p.nranks) s_start[threadIdx.x] = p.offsets[threadIdx.x * El];
   __syncthreads();
+  const int stride = p.inline_counts ? p.cap + 1 : p.cap;   // rows per peer segment
   if (blockIdx.x == 0) {
     for (int e = threadIdx.x; e <= p.E; e += EP_THREADS) p.offsets_src[e] = p.offsets[e];
-    for (int e = threadIdx.x; e < p.E; e += EP_THREADS) p.send_counts[e] = p.offsets[e + 1] - p.offsets[e];
+    if (p.send_counts)
+      for (int e = threadIdx.x; e < p.E; e += EP_THREADS) p.send_counts[e] = p.offsets[e + 1] - p.offsets[e];
+    if (p.inline_counts)   // the counts ride in the extra last row of every peer segment: one collective less
+      for (int i = threadIdx.x; i < p.nranks * p.E; i += EP_THREADS) {
+        const int r = i / p.E, e = i - r * p.E;
+        reinterpret_cast<int*>(reinterpret_cast<uint16_t*>(p.send_rows) + ((size_t)r * stride + p.cap) * p.H)[e] =
+            p.offsets[e + 1] - p.offsets[e];
+      }
   }
   const int total = s_start[p.nranks];
   for (int i = blockIdx.x; i < total; i += gridDim.x) {
@@ -43,7 +51,7 @@ __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
     const int pos = i - s_start[r];
     if (pos < p.cap)
       copy_row16(reinterpret_cast<const uint16_t*>(p.xp) + (size_t)i * p.H,
-                 reinterpret_cast<uint16_t*>(p.send_rows) + ((size_t)r * p.cap + pos) * p.H, p.H);
+                 reinterpret_cast<uint16_t*>(p.send_rows) + ((size_t)r * stride + pos) * p.H, p.H);
   }
 }
 
@@ -55,7 +63,14 @@ __global__ void __launch_bounds__(EP_THREADS) ep_regroup_kernel(EpParams p) {
   __shared__ int s_off[EP_MAX_EL + 1];             // first workspace row of local expert le
   __shared__ int s_tot[EP_MAX_RANKS];
   const int N = p.nranks, El = p.E / p.nranks;
-  for (int i = threadIdx.x; i < N * El; i += EP_THREADS) s_cnt[i / El][i % El] = p.recv_counts[(size_t)(i / El) * p.E + p.rank * El + (i % El)];
+  const int stride = p.inline_counts ? p.cap + 1 : p.cap;
+  for (int i = threadIdx.x; i < N * El; i += EP_THREADS) {
+    const int s = i / El, le = i % El;
+    const int* cnt = p.inline_counts
+        ? reinterpret_cast<const int*>(reinterpret_cast<const uint16_t*>(p.recv_rows) + ((size_t)s * stride + p.cap) * p.H)
+        : p.recv_counts + (size_t)s * p.E;
+    s_cnt[s][le] = cnt[p.rank * El + le];
+  }
   __syncthreads();
   if (threadIdx.x < N) {
     int run = 0;
@@ -89,7 +104,7 @@ __global__ void __launch_bounds__(EP_THREADS) ep_regroup_kernel(EpParams p) {
       int le = 0;
       while (le + 1 < El && c >= s_pre[s][le + 1]) ++le;
       dest = s_off[le] + s_src[s][le] + (c - s_pre[s][le]);
-      copy_row16(reinterpret_cast<const uint16_t*>(p.recv_rows) + (size_t)i * p.H,
+      copy_row16(reinterpret_cast<const uint16_t*>(p.recv_rows) + ((size_t)s * stride + c) * p.H,
                  reinterpret_cast<uint16_t*>(p.xp) + (size_t)dest * p.H, p.H);
     }
     if (threadIdx.x == 0) p.dest_of[i] = dest;
@@ -109,7 +124,8 @@ __global__ void __launch_bounds__(EP_THREADS) ep_ungroup_kernel(EpParams p) {
     const int dest = p.dest_of[i];
     if (dest < 0) continue;
     const float* src = p.y + (size_t)dest * p.H;
-    uint16_t* dst = reinterpret_cast<uint16_t*>(p.ret_rows) + (size_t)i * p.H;
+    const int stride = p.inline_counts ? p.cap + 1 : p.cap;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.ret_rows) + ((size_t)(i / p.cap) * stride + (i % p.cap)) * p.H;
     for (int v = threadIdx.x * 8; v < p.H; v += EP_THREADS * 8) {
       const float4 a = *reinterpret_cast<const float4*>(src + v), b = *reinterpret_cast<const float4*>(src + v + 4);
       const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -134,7 +150,8 @@ __global__ void __launch_bounds__(EP_THREADS) ep_unpack_kernel(EpParams p) {
     while (i >= s_start[r + 1]) ++r;
     const int pos = i - s_start[r];
     if (pos >= p.cap) continue;
-    const uint16_t* src = reinterpret_cast<const uint16_t*>(p.back_rows) + ((size_t)r * p.cap + pos) * p.H;
+    const int stride = p.inline_counts ? p.cap + 1 : p.cap;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(p.back_rows) + ((size_t)r * stride + pos) * p.H;
     float* dst = p.y + (size_t)i * p.H;
     for (int v = threadIdx.x * 8; v < p.H; v += EP_THREADS * 8) {
       const uint4 x = *reinterpret_cast<const uint4*>(src + v);
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(EP_THREADS) ep_unpack_kernel(EpParams p) {
 
 static bool ep_ok(const EpParams& p) {
   return p.nranks >= 1 && p.nranks <= EP_MAX_RANKS && p.E % p.nranks == 0 && p.E / p.nranks <= EP_MAX_EL &&
-         p.rank >= 0 && p.rank < p.nranks && p.cap >= 1 && p.H % 8 == 0;
+         p.rank >= 0 && p.rank < p.nranks && p.cap >= 1 && p.H % 8 == 0 && (!p.inline_counts || p.E * 4 <= p.H * 2);
 }
 static int ep_grid(int rows) { return rows < 1 ? 1 : (rows > 148 * 4 ? 148 * 4 : rows); }
 

@@ -104,6 +104,50 @@ __device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[
   __syncwarp();
 }
 
+// Large-T gate: one warp per token, 8 experts per pass (x re-read from L1 for E > 8), 16-byte loads of both operands.
+__global__ void __launch_bounds__(256) gate_logits_kernel(const RouteParams p) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= p.T) return;
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
+  for (int e0 = 0; e0 < p.E; e0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int h = lane * 8; h < p.H; h += 256) {
+      float xf[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + h), p.dtype, xf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (e0 + i < p.E) {
+          float wf[8];
+          if (p.gate_dtype == DT_F32) {
+            const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)(e0 + i) * p.H + h;
+            const float4 a = *reinterpret_cast<const float4*>(w), b = *reinterpret_cast<const float4*>(w + 4);
+            wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = b.x; wf[5] = b.y; wf[6] = b.z; wf[7] = b.w;
+          } else {
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)(e0 + i) * p.H + h),
+                    p.gate_dtype, wf);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float v = warp_sum(acc[i]);
+      if (lane == 0 && e0 + i < p.E) {
+        if (p.router == ROUTER_MIXTRAL)
+          reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e0 + i] =
+              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v) : Half16<DT_F16>::from_f(v);
+        else
+          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v;
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------
 // K1: softmax + top-k (+renorm) for one token (one warp, lane owns experts lane, lane+32, ...)
 // --------------------------------------------------------------------------------------
@@ -429,22 +473,18 @@ __global__ void __launch_bounds__(256) route_scan_kernel(const RouteParams p, in
   }
 }
 
-// one block per group of RT_WARPS chunks; warp w ranks chunk w, then all warps copy that block's rows
+// one block per chunk of 32 tokens: warp 0 ranks the chunk, then all warps copy its rows
 __global__ void __launch_bounds__(RT_THREADS) route_permute_kernel(const RouteParams p) {
-  __shared__ int s_rows[RT_WARPS][CHUNK * MAX_K];
+  __shared__ int s_rows[CHUNK * MAX_K];
   const int warp = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * RT_WARPS + warp;
+  const int chunk = blockIdx.x;
   const int t0 = chunk * CHUNK;
-  if (t0 < p.T) {
+  if (warp == 0 && t0 < p.T) {
     const int* cb = p.chunk_counts + (size_t)chunk * p.E;
-    chunk_rank_warp(p, t0, [&](int e) { return p.offsets[e] + cb[e]; }, s_rows[warp]);
+    chunk_rank_warp(p, t0, [&](int e) { return p.offsets[e] + cb[e]; }, s_rows);
   }
   __syncthreads();
-  for (int w = 0; w < RT_WARPS; ++w) {
-    const int tw = (blockIdx.x * RT_WARPS + w) * CHUNK;
-    if (tw >= p.T) break;
-    copy_rows_block(p, tw, CHUNK * p.k, s_rows[w], 0, RT_WARPS);
-  }
+  if (t0 < p.T) copy_rows_block(p, t0, CHUNK * p.k, s_rows, 0, RT_WARPS);
   // clear the split-K accumulator (grid-stride over the whole grid)
   if (p.y_zero) {
     float4* z = reinterpret_cast<float4*>(p.y_zero);
@@ -591,13 +631,22 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
-  route_topk_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  RouteParams q = p;
+  if (!p.logits) {
+    if (!p.logits_out) return cudaErrorInvalidValue;
+    gate_logits_kernel<<<(p.T + 7) / 8, 256, 0, st>>>(p);
+    q.logits = p.logits_out;
+    q.logits_dtype = p.router == ROUTER_MIXTRAL ? p.dtype : DT_F32;
+    q.logits_are_scores = 0;
+    q.logits_out = nullptr;
+  }
+  route_topk_kernel<<<nblocks, RT_THREADS, 0, st>>>(q);
   if (p.router == ROUTER_SWITCH_TOP1) {
     switch_capacity_kernel<<<p.T / p.seq_len, RT_THREADS, 0, st>>>(p);
     chunk_count_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
   }
   route_scan_kernel<<<1, 256, 0, st>>>(p, nchunks);
-  route_permute_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  route_permute_kernel<<<nchunks, RT_THREADS, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -616,7 +665,7 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
   mask_to_topk_kernel<<<(p.T + RT_THREADS - 1) / RT_THREADS, RT_THREADS, 0, st>>>(p, mask);
   chunk_count_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
   route_scan_kernel<<<1, 256, 0, st>>>(p, nchunks);
-  route_permute_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
+  route_permute_kernel<<<nchunks, RT_THREADS, 0, st>>>(p);
   return cudaGetLastError();
 }
 

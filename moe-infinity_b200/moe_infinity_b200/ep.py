@@ -3,7 +3,7 @@ torch.distributed (NCCL over NVLink/NVSwitch) for the exchange, libb2m.so kernel
 
 Sharding: rank r owns experts [r*E/N, (r+1)*E/N) of every layer (contiguous blocks, so the expert-sorted
 gathered rows of a rank are already contiguous per destination).  Per layer:
-    route (local tokens) -> ep_pack -> all_gather(counts) + all_to_all(rows, fixed capacity cap = T_local*k per peer)
+    route (local tokens) -> ep_pack -> all_to_all(rows + one counts row per peer, fixed capacity cap = T_local*k)
     -> ep_regroup -> grouped GEMMs on the received rows -> ep_ungroup -> all_to_all back -> ep_unpack -> combine.
 Nothing in the layer synchronises with the host; capacity is static so no rank ever needs another rank's counts
 on the CPU.  The reference has no live collective (README.md:18) -- it moves rows with `.to(device)`
@@ -42,15 +42,15 @@ class _EngineOps:
     def route(self, layer, x, router_logits=None):
         return self.eng.route(layer, x, router_logits=router_logits)
 
-    def pack(self, world, rank, cap, T, send_rows, send_counts):
+    def pack(self, world, rank, cap, T, send_rows, send_counts=None):
         e = self.eng
         e._ck(e.lib.b2m_ep_pack(e._h, world, rank, cap, T, C.c_void_p(send_rows.data_ptr()),
-                                C.c_void_p(send_counts.data_ptr()), self._s()))
+                                C.c_void_p(send_counts.data_ptr() if send_counts is not None else 0), self._s()))
 
-    def regroup(self, world, rank, cap, T_total, recv_rows, recv_counts):
+    def regroup(self, world, rank, cap, T_total, recv_rows, recv_counts=None):
         e = self.eng
         e._ck(e.lib.b2m_ep_regroup(e._h, world, rank, cap, T_total, C.c_void_p(recv_rows.data_ptr()),
-                                   C.c_void_p(recv_counts.data_ptr()), self._s()))
+                                   C.c_void_p(recv_counts.data_ptr() if recv_counts is not None else 0), self._s()))
 
     def run_experts(self, layer, T_total):
         self.eng.run_experts(layer, T_total)
@@ -82,13 +82,14 @@ class EPMoE:
         self.E, self.H, self.k, self.T = num_experts, hidden, top_k, T_local
         self.cap = T_local * top_k
         self.T_total = self.world * T_local
-        shape = (self.world, self.cap, hidden)
+        # inline layout: one extra row per peer segment carries counts[E] (int32), so each direction is ONE collective
+        if 4 * num_experts > 2 * hidden:
+            raise ValueError("inline counts need 4*E <= 2*H")
+        shape = (self.world, self.cap + 1, hidden)
         self.send_rows = torch.zeros(shape, dtype=dtype, device=device)
         self.recv_rows = torch.zeros(shape, dtype=dtype, device=device)
         self.ret_rows = torch.zeros(shape, dtype=dtype, device=device)
         self.back_rows = torch.zeros(shape, dtype=dtype, device=device)
-        self.send_counts = torch.zeros(num_experts, dtype=torch.int32, device=device)
-        self.recv_counts = torch.zeros(self.world, num_experts, dtype=torch.int32, device=device)
 
     def forward(self, layer: int, x: torch.Tensor, out: Optional[torch.Tensor] = None, router_logits=None):
         T = x.shape[0]
@@ -96,10 +97,9 @@ class EPMoE:
             raise ValueError(f"EPMoE was sized for T_local={self.T}, got {T}")
         w, r, cap = self.world, self.rank, self.cap
         self.ops.route(layer, x, router_logits)
-        self.ops.pack(w, r, cap, T, self.send_rows, self.send_counts)
-        dist.all_gather_into_tensor(self.recv_counts.view(-1), self.send_counts, group=self.group)
+        self.ops.pack(w, r, cap, T, self.send_rows)
         dist.all_to_all_single(self.recv_rows, self.send_rows, group=self.group)
-        self.ops.regroup(w, r, cap, self.T_total, self.recv_rows, self.recv_counts)
+        self.ops.regroup(w, r, cap, self.T_total, self.recv_rows)
         self.ops.run_experts(layer, self.T_total)
         self.ops.ungroup(w, r, cap, self.ret_rows)
         dist.all_to_all_single(self.back_rows, self.ret_rows, group=self.group)
@@ -145,6 +145,30 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     launches0 = eng.stats()["kernel_launches"]
     step()
     launches_per_step = eng.stats()["kernel_launches"] - launches0
+    # one CUDA graph per 32-layer step (NCCL all-to-alls are captured too); fall back to eager launches
+    eager_step = step
+    timed = "eager launches"
+    if not os.environ.get("B2M_EP_NO_GRAPH"):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            s_cap = torch.cuda.Stream()
+            s_cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_cap):
+                eager_step()
+            torch.cuda.current_stream().wait_stream(s_cap)
+            torch.cuda.synchronize()
+            dist.barrier()
+            with torch.cuda.graph(graph):
+                eager_step()
+            torch.cuda.synchronize()
+            step = graph.replay
+            timed = "CUDA graph replay of the step (kernels + NCCL all-to-all)"
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        except Exception as ex:  # pragma: no cover
+            step = eager_step
+            timed = f"eager launches (graph capture failed: {type(ex).__name__})"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -207,9 +231,9 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                                    f"({el} experts/GPU/layer), decode batch {batch} per GPU (global {world*batch}), "
                                    f"{L} layers, bf16 random-init, all local experts HBM-resident",
                        "global_batch": world * batch, "layers": L, "parallelism": f"ep{world}",
-                       "exchange": "fixed-capacity all_to_all_single (NCCL) each way + all_gather of counts",
+                       "exchange": "one fixed-capacity all_to_all_single (NCCL) each way; counts ride in the row buffer",
                        "l2": "inputs larger than L2 (each rank streams %.1f GB of weights per step)" % (bytes_rank / 1e9),
-                       "timed_region": "eager launches, max over ranks"},
+                       "timed_region": timed + ", max over ranks"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "peak_source": peak_src, "scope": "whole step, per rank", "traffic": None,
                          "algorithmic_bytes_per_rank_step": bytes_rank},

@@ -38,13 +38,14 @@ class CpuOps:
         self.perm_token = toks
         self.offsets = torch.cat([torch.zeros(1, dtype=torch.long), self.counts.long().cumsum(0)])
 
-    def pack(self, world, rank, cap, T_, send_rows, send_counts):
-        send_counts.copy_(self.counts)
+    def pack(self, world, rank, cap, T_, send_rows, send_counts=None):
         for r in range(world):
+            send_rows[r, cap].view(torch.int32)[:E] = self.counts      # inline counts row (csrc/ep.cu)
             a, b = int(self.offsets[r * self.el]), int(self.offsets[(r + 1) * self.el])
             send_rows[r, : b - a] = self.xp[a:b]
 
-    def regroup(self, world, rank, cap, T_total, recv_rows, recv_counts):
+    def regroup(self, world, rank, cap, T_total, recv_rows, recv_counts=None):
+        recv_counts = torch.stack([recv_rows[s, cap].view(torch.int32)[:E] for s in range(world)])
         self.groups = []          # per local expert: list of (source, slot) in source-major order
         for le in range(self.el):
             e = rank * self.el + le
