@@ -216,6 +216,20 @@ int b2m_ep_regroup(b2m_ctx* ctx, int nranks, int rank, int cap, int T_total, con
 int b2m_ep_ungroup(b2m_ctx* ctx, int nranks, int rank, int cap, void* ret_rows, void* stream);
 int b2m_ep_unpack(b2m_ctx* ctx, int nranks, int rank, int cap, int T_local, const void* back_rows, void* stream);
 
+/* Peer-to-peer variant of the same exchange: no collective library call inside the layer.  Each rank allocates its
+ * receive/return areas + flag words (b2m_ep_p2p_init returns a 64-byte CUDA IPC handle), the host side exchanges the
+ * handles once (any transport) and maps the peers with b2m_ep_p2p_open.  Per layer:
+ *   b2m_route -> b2m_ep_p2p_dispatch (stores rows + counts straight into the owners' buffers over NVLink, then
+ *   publishes an epoch flag with st.release.sys) -> b2m_ep_p2p_regroup (ld.acquire.sys wait, regroup) ->
+ *   b2m_run_experts(T_total) -> b2m_ep_p2p_return (outputs stored into the source ranks' buffers + flag) ->
+ *   b2m_ep_p2p_collect (wait, unpack) -> b2m_combine.  Every rank must issue the same sequence of calls. */
+int b2m_ep_p2p_init(b2m_ctx* ctx, int nranks, int rank, int cap, void* ipc_handle_out64);
+int b2m_ep_p2p_open(b2m_ctx* ctx, int peer, const void* ipc_handle64);
+int b2m_ep_p2p_dispatch(b2m_ctx* ctx, int T_local, void* stream);
+int b2m_ep_p2p_regroup(b2m_ctx* ctx, int T_total, void* stream);
+int b2m_ep_p2p_return(b2m_ctx* ctx, void* stream);
+int b2m_ep_p2p_collect(b2m_ctx* ctx, int T_local, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

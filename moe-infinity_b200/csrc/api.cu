@@ -133,6 +133,14 @@ struct b2m_ctx {
   int cur_ksplit = 1, cur_nt = 16, cur_T = 0;
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
+  // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
+  struct P2P {
+    int nranks = 0, rank = 0, cap = 0;
+    uint8_t* base = nullptr;            // own allocation: [recv area][back area][flags]
+    size_t area_bytes = 0;
+    uint8_t* peer_base[16] = {nullptr};
+    int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters
+  } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_dest_of = nullptr;      // [cap_R]
   b2m_stats stats;
@@ -558,6 +566,10 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
                   c->d_chunk_counts, c->d_offsets_src, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
+  for (int r = 0; r < c->p2p.nranks; ++r)
+    if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
+  if (c->p2p.base) cudaFree(c->p2p.base);
+  if (c->p2p.local_ctr) cudaFree(c->p2p.local_ctr);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
@@ -1059,6 +1071,120 @@ int b2m_ep_unpack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, const 
   EpParams p = ep_base(c, nranks, rank, cap);
   p.back_rows = back_rows;
   p.inline_counts = c->ep_inline;
+  CK(c, launch_ep_unpack(p, c->cfg.dtype, T_local * c->cfg.top_k, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+// ---- peer-to-peer exchange: rows go straight into the peers' buffers over NVLink, no collective call ----
+static size_t p2p_area_bytes(const b2m_ctx* c, int nranks, int cap) {
+  return (size_t)nranks * (cap + 1) * c->cfg.hidden * 2;
+}
+static EpParams ep_p2p_params(b2m_ctx* c) {
+  const b2m_ctx::P2P& q = c->p2p;
+  EpParams p = ep_base(c, q.nranks, q.rank, q.cap);
+  p.inline_counts = 1;
+  p.p2p = 1;
+  for (int r = 0; r < q.nranks; ++r) {
+    p.peer_recv[r] = q.peer_base[r];
+    p.peer_back[r] = q.peer_base[r] + q.area_bytes;
+    p.peer_recv_flag[r] = reinterpret_cast<int*>(q.peer_base[r] + 2 * q.area_bytes);
+    p.peer_back_flag[r] = p.peer_recv_flag[r] + 16;
+  }
+  p.local_recv_flag = reinterpret_cast<int*>(q.base + 2 * q.area_bytes);
+  p.local_back_flag = p.local_recv_flag + 16;
+  p.recv_rows = q.base;
+  p.back_rows = q.base + q.area_bytes;
+  p.epoch = q.local_ctr;
+  p.done_ctr = q.local_ctr + 2;
+  return p;
+}
+
+int b2m_ep_p2p_init(b2m_ctx* c, int nranks, int rank, int cap, void* ipc_handle_out64) {
+  int r = ep_check(c, nranks, rank, cap);
+  if (r) return r;
+  if (!ipc_handle_out64) return fail(c, B2M_EINVAL, "null handle buffer");
+  if (c->p2p.base) return fail(c, B2M_ESTATE, "peer-to-peer exchange already initialised");
+  if (4 * c->cfg.num_experts > 2 * c->cfg.hidden) return fail(c, B2M_EINVAL, "inline counts need 4*E <= 2*H");
+  b2m_ctx::P2P& q = c->p2p;
+  q.nranks = nranks; q.rank = rank; q.cap = cap;
+  q.area_bytes = p2p_area_bytes(c, nranks, cap);
+  const size_t total = 2 * q.area_bytes + 32 * sizeof(int);
+  CK(c, cudaMalloc((void**)&q.base, total));
+  CK(c, cudaMemset(q.base, 0, total));
+  CK(c, cudaMalloc((void**)&q.local_ctr, 4 * sizeof(int)));
+  CK(c, cudaMemset(q.local_ctr, 0, 4 * sizeof(int)));
+  CK(c, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(c, cudaIpcGetMemHandle(&h, q.base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(ipc_handle_out64, &h, 64);
+  q.peer_base[rank] = q.base;
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_open(b2m_ctx* c, int peer, const void* ipc_handle64) {
+  if (!c || !ipc_handle64) return B2M_EINVAL;
+  b2m_ctx::P2P& q = c->p2p;
+  if (!q.base) return fail(c, B2M_ESTATE, "call b2m_ep_p2p_init first");
+  if (peer < 0 || peer >= q.nranks) return fail(c, B2M_EINVAL, "peer %d out of range", peer);
+  if (peer == q.rank) return B2M_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, 64);
+  void* ptr = nullptr;
+  CK(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  q.peer_base[peer] = reinterpret_cast<uint8_t*>(ptr);
+  return B2M_OK;
+}
+
+static int p2p_ready(b2m_ctx* c) {
+  if (!c) return B2M_EINVAL;
+  if (!c->p2p.base) return fail(c, B2M_ESTATE, "peer-to-peer exchange not initialised");
+  for (int r = 0; r < c->p2p.nranks; ++r)
+    if (!c->p2p.peer_base[r]) return fail(c, B2M_ESTATE, "peer %d buffer not opened (b2m_ep_p2p_open)", r);
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_dispatch(b2m_ctx* c, int T_local, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  if (T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "cap=%d < T_local*top_k", c->p2p.cap);
+  EpParams p = ep_p2p_params(c);
+  CK(c, launch_ep_pack(p, T_local * c->cfg.top_k, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  c->ep_mode = true;
+  c->ep_inline = 1;
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  if (T_total < 1 || T_total > c->cap_T) return fail(c, B2M_EINVAL, "T_total=%d exceeds workspace capacity %d", T_total, c->cap_T);
+  EpParams p = ep_p2p_params(c);
+  c->cur_T = T_total;
+  c->cur_nt = pick_nt(T_total);
+  c->cur_ksplit = pick_ksplit(c, T_total, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts / c->p2p.nranks, c->cfg.top_k, c->cur_nt);
+  if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)c->p2p.nranks * c->p2p.cap * c->cfg.hidden; }
+  CK(c, launch_ep_regroup(p, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  c->ep_mode = true;
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_return(b2m_ctx* c, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  EpParams p = ep_p2p_params(c);
+  CK(c, launch_ep_ungroup(p, c->cfg.dtype, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_collect(b2m_ctx* c, int T_local, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  EpParams p = ep_p2p_params(c);
   CK(c, launch_ep_unpack(p, c->cfg.dtype, T_local * c->cfg.top_k, (cudaStream_t)stream));
   c->stats.kernel_launches += 1;
   return B2M_OK;

@@ -111,6 +111,17 @@ struct EpParams {
   int* dest_of;                     // [nranks*cap] workspace row of each received slot (-1: empty)
   float* y_zero;
   size_t y_zero_elems;
+  // ---- peer-to-peer mode (p2p = 1): rows are stored straight into the peers' buffers over NVLink and completion is
+  // signalled with release/acquire flags in peer memory; no collective library call in the layer.
+  int p2p;
+  void* peer_recv[16];        // peer r's receive area  [nranks][cap+1][H]   (peer-mapped via CUDA IPC)
+  void* peer_back[16];        // peer r's return area   [nranks][cap+1][H]
+  int* peer_recv_flag[16];    // peer r's recv_flag[nranks]
+  int* peer_back_flag[16];    // peer r's back_flag[nranks]
+  int* local_recv_flag;       // this rank's recv_flag[nranks]
+  int* local_back_flag;
+  int* epoch;                 // local: [0] dispatches issued, [1] returns issued
+  int* done_ctr;              // local: [0] CTAs finished in dispatch kernel, [1] in return kernel
 };
 cudaError_t launch_ep_pack(const EpParams& p, int max_rows, cudaStream_t st);
 cudaError_t launch_ep_regroup(const EpParams& p, cudaStream_t st);

@@ -26,6 +26,42 @@ __device__ __forceinline__ void copy_row16(const uint16_t* src, uint16_t* dst, i
   for (int v = threadIdx.x; v < H / 8; v += EP_THREADS) d[v] = s[v];
 }
 
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Every CTA calls this after its last store to peer memory; the last CTA to arrive publishes epoch to all peers.
+__device__ void p2p_signal(const EpParams& p, int which /*0 dispatch, 1 return*/) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.done_ctr + which, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) {
+    p.done_ctr[which] = 0;
+    const int e = p.epoch[which] + 1;
+    p.epoch[which] = e;
+    __threadfence_system();
+    for (int r = 0; r < p.nranks; ++r) st_release_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
+  }
+}
+// Wait until every source rank's flag reached this rank's own epoch (all ranks issue the same number of exchanges).
+__device__ void p2p_wait(const EpParams& p, int which) {
+  if (threadIdx.x < p.nranks) {
+    const int want = p.epoch[which];
+    const int* f = (which ? p.local_back_flag : p.local_recv_flag) + threadIdx.x;
+    while (ld_acquire_sys(f) < want) __nanosleep(64);
+  }
+  __syncthreads();
+}
+
 // grid: one CTA per permuted row (grid-stride); CTA 0 also publishes counts and the source-side offsets copy
 __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
   __shared__ int s_start[EP_MAX_RANKS + 1];
@@ -40,8 +76,9 @@ __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
     if (p.inline_counts)   // the counts ride in the extra last row of every peer segment: one collective less
       for (int i = threadIdx.x; i < p.nranks * p.E; i += EP_THREADS) {
         const int r = i / p.E, e = i - r * p.E;
-        reinterpret_cast<int*>(reinterpret_cast<uint16_t*>(p.send_rows) + ((size_t)r * stride + p.cap) * p.H)[e] =
-            p.offsets[e + 1] - p.offsets[e];
+        uint16_t* seg = p.p2p ? reinterpret_cast<uint16_t*>(p.peer_recv[r]) + (size_t)p.rank * stride * p.H
+                              : reinterpret_cast<uint16_t*>(p.send_rows) + (size_t)r * stride * p.H;
+        reinterpret_cast<int*>(seg + (size_t)p.cap * p.H)[e] = p.offsets[e + 1] - p.offsets[e];
       }
   }
   const int total = s_start[p.nranks];
@@ -49,10 +86,13 @@ __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
     int r = 0;
     while (i >= s_start[r + 1]) ++r;
     const int pos = i - s_start[r];
-    if (pos < p.cap)
-      copy_row16(reinterpret_cast<const uint16_t*>(p.xp) + (size_t)i * p.H,
-                 reinterpret_cast<uint16_t*>(p.send_rows) + ((size_t)r * stride + pos) * p.H, p.H);
+    if (pos < p.cap) {
+      uint16_t* seg = p.p2p ? reinterpret_cast<uint16_t*>(p.peer_recv[r]) + (size_t)p.rank * stride * p.H
+                            : reinterpret_cast<uint16_t*>(p.send_rows) + (size_t)r * stride * p.H;
+      copy_row16(reinterpret_cast<const uint16_t*>(p.xp) + (size_t)i * p.H, seg + (size_t)pos * p.H, p.H);
+    }
   }
+  if (p.p2p) p2p_signal(p, 0);
 }
 
 // grid-stride over (source rank s, slot c); every CTA rebuilds the small prefix tables in shared memory
@@ -64,6 +104,7 @@ __global__ void __launch_bounds__(EP_THREADS) ep_regroup_kernel(EpParams p) {
   __shared__ int s_tot[EP_MAX_RANKS];
   const int N = p.nranks, El = p.E / p.nranks;
   const int stride = p.inline_counts ? p.cap + 1 : p.cap;
+  if (p.p2p) p2p_wait(p, 0);
   for (int i = threadIdx.x; i < N * El; i += EP_THREADS) {
     const int s = i / El, le = i % El;
     const int* cnt = p.inline_counts
@@ -125,7 +166,9 @@ __global__ void __launch_bounds__(EP_THREADS) ep_ungroup_kernel(EpParams p) {
     if (dest < 0) continue;
     const float* src = p.y + (size_t)dest * p.H;
     const int stride = p.inline_counts ? p.cap + 1 : p.cap;
-    uint16_t* dst = reinterpret_cast<uint16_t*>(p.ret_rows) + ((size_t)(i / p.cap) * stride + (i % p.cap)) * p.H;
+    const int src_rank = i / p.cap, c = i % p.cap;
+    uint16_t* dst = p.p2p ? reinterpret_cast<uint16_t*>(p.peer_back[src_rank]) + ((size_t)p.rank * stride + c) * p.H
+                          : reinterpret_cast<uint16_t*>(p.ret_rows) + ((size_t)src_rank * stride + c) * p.H;
     for (int v = threadIdx.x * 8; v < p.H; v += EP_THREADS * 8) {
       const float4 a = *reinterpret_cast<const float4*>(src + v), b = *reinterpret_cast<const float4*>(src + v + 4);
       const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -136,12 +179,14 @@ __global__ void __launch_bounds__(EP_THREADS) ep_ungroup_kernel(EpParams p) {
       *reinterpret_cast<uint4*>(dst + v) = o;
     }
   }
+  if (p.p2p) p2p_signal(p, 1);
 }
 
 template <int DT>
 __global__ void __launch_bounds__(EP_THREADS) ep_unpack_kernel(EpParams p) {
   __shared__ int s_start[EP_MAX_RANKS + 1];
   const int El = p.E / p.nranks;
+  if (p.p2p) p2p_wait(p, 1);
   if (threadIdx.x <= p.nranks) s_start[threadIdx.x] = p.offsets_src[threadIdx.x * El];
   __syncthreads();
   const int total = s_start[p.nranks];

@@ -75,6 +75,12 @@ SYMBOLS = [
     ("b2m_ep_regroup", _I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     ("b2m_ep_ungroup", _I, [_VP, _I, _I, _I, _VP, _VP]),
     ("b2m_ep_unpack", _I, [_VP, _I, _I, _I, _I, _VP, _VP]),
+    ("b2m_ep_p2p_init", _I, [_VP, _I, _I, _I, _VP]),
+    ("b2m_ep_p2p_open", _I, [_VP, _I, _VP]),
+    ("b2m_ep_p2p_dispatch", _I, [_VP, _I, _VP]),
+    ("b2m_ep_p2p_regroup", _I, [_VP, _I, _VP]),
+    ("b2m_ep_p2p_return", _I, [_VP, _VP]),
+    ("b2m_ep_p2p_collect", _I, [_VP, _I, _VP]),
 ]
 
 _lib = None

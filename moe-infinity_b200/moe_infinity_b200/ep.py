@@ -66,14 +66,45 @@ class _EngineOps:
     def combine(self, layer, x, out):
         return self.eng.combine(layer, x, out=out)
 
+    # ---- peer-to-peer exchange (no collective call inside the layer)
+    def p2p_setup(self, world, rank, cap, group):
+        """Allocate this rank's exchange areas, swap CUDA IPC handles with the peers (once), map them."""
+        e = self.eng
+        h = (C.c_ubyte * 64)()
+        e._ck(e.lib.b2m_ep_p2p_init(e._h, world, rank, cap, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h), group=group)
+        for r, hb in enumerate(handles):
+            buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+            e._ck(e.lib.b2m_ep_p2p_open(e._h, r, buf))
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def p2p_dispatch(self, T):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_p2p_dispatch(e._h, T, self._s()))
+
+    def p2p_regroup(self, T_total):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_p2p_regroup(e._h, T_total, self._s()))
+
+    def p2p_return(self):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_p2p_return(e._h, self._s()))
+
+    def p2p_collect(self, T):
+        e = self.eng
+        e._ck(e.lib.b2m_ep_p2p_collect(e._h, T, self._s()))
+
 
 class EPMoE:
     """One expert-parallel MoE layer stack.  `ops` is the device backend (the CUDA engine in production; tests inject
     a CPU stand-in to exercise the exchange schedule under gloo)."""
 
     def __init__(self, ops, *, num_experts: int, hidden: int, top_k: int, T_local: int, dtype, device,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, p2p: bool = False):
         self.ops = ops
+        self.p2p = p2p
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -85,6 +116,10 @@ class EPMoE:
         # inline layout: one extra row per peer segment carries counts[E] (int32), so each direction is ONE collective
         if 4 * num_experts > 2 * hidden:
             raise ValueError("inline counts need 4*E <= 2*H")
+        if p2p:
+            # rows are stored directly into the owners' buffers by the dispatch kernel (NVLink stores + flags)
+            self.ops.p2p_setup(self.world, self.rank, self.cap, group)
+            return
         shape = (self.world, self.cap + 1, hidden)
         self.send_rows = torch.zeros(shape, dtype=dtype, device=device)
         self.recv_rows = torch.zeros(shape, dtype=dtype, device=device)
@@ -97,6 +132,13 @@ class EPMoE:
             raise ValueError(f"EPMoE was sized for T_local={self.T}, got {T}")
         w, r, cap = self.world, self.rank, self.cap
         self.ops.route(layer, x, router_logits)
+        if self.p2p:
+            self.ops.p2p_dispatch(T)
+            self.ops.p2p_regroup(self.T_total)
+            self.ops.run_experts(layer, self.T_total)
+            self.ops.p2p_return()
+            self.ops.p2p_collect(T)
+            return self.ops.combine(layer, x, out)
         self.ops.pack(w, r, cap, T, self.send_rows)
         dist.all_to_all_single(self.recv_rows, self.send_rows, group=self.group)
         self.ops.regroup(w, r, cap, self.T_total, self.recv_rows)
@@ -133,7 +175,8 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
         eng.set_gate(l, torch.randn(E, H, device=dev, generator=g) * 0.02)
     x_dev = torch.randn(L, T, H, device=dev).to(dtype)
     out_dev = torch.empty_like(x_dev)
-    ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev)
+    use_p2p = os.environ.get("B2M_EP_EXCHANGE", "p2p") == "p2p"
+    ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev, p2p=use_p2p)
 
     def step():
         for l in range(L):
@@ -231,7 +274,9 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                                    f"({el} experts/GPU/layer), decode batch {batch} per GPU (global {world*batch}), "
                                    f"{L} layers, bf16 random-init, all local experts HBM-resident",
                        "global_batch": world * batch, "layers": L, "parallelism": f"ep{world}",
-                       "exchange": "one fixed-capacity all_to_all_single (NCCL) each way; counts ride in the row buffer",
+                       "exchange": ("fused peer-to-peer: dispatch/return kernels store rows into the owners' buffers over NVLink, "
+                                    "st.release.sys/ld.acquire.sys epoch flags, no collective call") if use_p2p else
+                                   "one fixed-capacity all_to_all_single (NCCL) each way; counts ride in the row buffer",
                        "l2": "inputs larger than L2 (each rank streams %.1f GB of weights per step)" % (bytes_rank / 1e9),
                        "timed_region": timed + ", max over ranks"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -245,5 +290,14 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    # teardown: a captured graph holds NCCL work; destroying the process group under it can hang, so drop the graph,
+    # drain, and leave without running communicator destructors
+    step = eager_step
+    graph = None
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)

@@ -35,17 +35,26 @@ def main():
         full.set_gate(l, gates[l])
         part.set_gate(l, gates[l])
     ep = EPMoE(_EngineOps(part), num_experts=E, hidden=H, top_k=K, T_local=T, dtype=dt, device=dev)
+    part2 = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=K, dtype=dt, max_tokens=world * T,
+                      num_slots=L * E // world, device=local)
+    for l in range(L):
+        for e in local_experts(rank, E, world):
+            part2.load_expert(l, e, experts[l][e])
+        part2.set_gate(l, gates[l])
+    ep2 = EPMoE(_EngineOps(part2), num_experts=E, hidden=H, top_k=K, T_local=T, dtype=dt, device=dev, p2p=True)
     gx = torch.Generator().manual_seed(50 + rank)
     bad = 0
-    for it in range(4):
+    for it in range(6):
         for l in range(L):
             x = torch.randn(T, H, generator=gx).to(dt).cuda()
             a = full.forward(l, x).clone()
-            b = ep.forward(l, x)
+            b = ep.forward(l, x).clone()          # NCCL all-to-all exchange
+            c = ep2.forward(l, x)                 # fused peer-to-peer exchange
             torch.cuda.synchronize()
-            if not torch.equal(a, b):
+            if not torch.equal(a, b) or not torch.equal(a, c):
                 bad += 1
-                print(f"rank {rank} it {it} layer {l}: max diff {(a.float()-b.float()).abs().max().item()}", flush=True)
+                print(f"rank {rank} it {it} layer {l}: nccl diff {(a.float()-b.float()).abs().max().item()} "
+                      f"p2p diff {(a.float()-c.float()).abs().max().item()}", flush=True)
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
     if rank == 0:
