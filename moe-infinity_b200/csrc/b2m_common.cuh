@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace b2m {
 
@@ -28,6 +29,12 @@ template <> struct Half16<DT_F16> {
 };
 // round-trip through the 16-bit type ("round to model dtype", value kept as fp32)
 template <int DT> __device__ __forceinline__ float round_dt(float f) { return Half16<DT>::to_f(Half16<DT>::from_f(f)); }
+
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor drains;
+// it must call pdl_wait() before its first global-memory access (read OR write).  pdl_launch() lets the successor
+// begin launching as early as possible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -148,6 +155,31 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int dtype, int M, int N) {
   uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
+// ---- host: launch helper with the PDL attribute (B2M_PDL=0 disables) ----------------------------------
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2M_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace b2m

@@ -66,6 +66,8 @@ __device__ void p2p_wait(const EpParams& p, int which) {
 __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {
   __shared__ int s_start[EP_MAX_RANKS + 1];
   const int El = p.E / p.nranks;
+  pdl_launch();
+  pdl_wait();
   if (threadIdx.x <= p.nranks) s_start[threadIdx.x] = p.offsets[threadIdx.x * El];
   __syncthreads();
   const int stride = p.inline_counts ? p.cap + 1 : p.cap;   // rows per peer segment
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(EP_THREADS) ep_regroup_kernel(EpParams p) {
   __shared__ int s_tot[EP_MAX_RANKS];
   const int N = p.nranks, El = p.E / p.nranks;
   const int stride = p.inline_counts ? p.cap + 1 : p.cap;
+  pdl_launch();
+  pdl_wait();
   if (p.p2p) p2p_wait(p, 0);
   for (int i = threadIdx.x; i < N * El; i += EP_THREADS) {
     const int s = i / El, le = i % El;
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(EP_THREADS) ep_regroup_kernel(EpParams p) {
 template <int DT>
 __global__ void __launch_bounds__(EP_THREADS) ep_ungroup_kernel(EpParams p) {
   const int slots = p.nranks * p.cap;
+  pdl_launch();
+  pdl_wait();
   for (int i = blockIdx.x; i < slots; i += gridDim.x) {
     const int dest = p.dest_of[i];
     if (dest < 0) continue;
@@ -186,6 +192,8 @@ template <int DT>
 __global__ void __launch_bounds__(EP_THREADS) ep_unpack_kernel(EpParams p) {
   __shared__ int s_start[EP_MAX_RANKS + 1];
   const int El = p.E / p.nranks;
+  pdl_launch();
+  pdl_wait();
   if (p.p2p) p2p_wait(p, 1);
   if (threadIdx.x <= p.nranks) s_start[threadIdx.x] = p.offsets_src[threadIdx.x * El];
   __syncthreads();
@@ -218,27 +226,23 @@ static int ep_grid(int rows) { return rows < 1 ? 1 : (rows > 148 * 4 ? 148 * 4 :
 
 cudaError_t launch_ep_pack(const EpParams& p, int max_rows, cudaStream_t st) {
   if (!ep_ok(p)) return cudaErrorInvalidValue;
-  ep_pack_kernel<<<ep_grid(max_rows), EP_THREADS, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(ep_pack_kernel, dim3(ep_grid(max_rows)), dim3(EP_THREADS), 0, st, p);
 }
 cudaError_t launch_ep_regroup(const EpParams& p, cudaStream_t st) {
   if (!ep_ok(p)) return cudaErrorInvalidValue;
-  ep_regroup_kernel<<<ep_grid(p.nranks * p.cap), EP_THREADS, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(ep_regroup_kernel, dim3(ep_grid(p.nranks * p.cap)), dim3(EP_THREADS), 0, st, p);
 }
 cudaError_t launch_ep_ungroup(const EpParams& p, int dtype, cudaStream_t st) {
   if (!ep_ok(p)) return cudaErrorInvalidValue;
-  if (dtype == DT_BF16) ep_ungroup_kernel<DT_BF16><<<ep_grid(p.nranks * p.cap), EP_THREADS, 0, st>>>(p);
-  else if (dtype == DT_F16) ep_ungroup_kernel<DT_F16><<<ep_grid(p.nranks * p.cap), EP_THREADS, 0, st>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (dtype == DT_BF16) return launch_pdl(ep_ungroup_kernel<DT_BF16>, dim3(ep_grid(p.nranks * p.cap)), dim3(EP_THREADS), 0, st, p);
+  if (dtype == DT_F16) return launch_pdl(ep_ungroup_kernel<DT_F16>, dim3(ep_grid(p.nranks * p.cap)), dim3(EP_THREADS), 0, st, p);
+  return cudaErrorInvalidValue;
 }
 cudaError_t launch_ep_unpack(const EpParams& p, int dtype, int max_rows, cudaStream_t st) {
   if (!ep_ok(p)) return cudaErrorInvalidValue;
-  if (dtype == DT_BF16) ep_unpack_kernel<DT_BF16><<<ep_grid(max_rows), EP_THREADS, 0, st>>>(p);
-  else if (dtype == DT_F16) ep_unpack_kernel<DT_F16><<<ep_grid(max_rows), EP_THREADS, 0, st>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (dtype == DT_BF16) return launch_pdl(ep_unpack_kernel<DT_BF16>, dim3(ep_grid(max_rows)), dim3(EP_THREADS), 0, st, p);
+  if (dtype == DT_F16) return launch_pdl(ep_unpack_kernel<DT_F16>, dim3(ep_grid(max_rows)), dim3(EP_THREADS), 0, st, p);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace b2m

@@ -111,12 +111,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
 
   // ---- one-time setup -------------------------------------------------------------
-  if (p.single_n >= 0) {
-    if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
-  } else {
-    for (int i = threadIdx.x; i <= E; i += GEMM_THREADS) offs[i] = p.offsets[i];
-    for (int i = threadIdx.x; i < E; i += GEMM_THREADS) slots[i] = p.slot_of[i];
-  }
+  pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     if (DUAL) tma_prefetch_desc(&tmA1);
@@ -136,6 +131,13 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (warp == 2) {
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish();
+  }
+  pdl_wait();   // everything above is on-chip; from here on we touch memory the previous kernel produced
+  if (p.single_n >= 0) {
+    if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
+  } else {
+    for (int i = threadIdx.x; i <= E; i += GEMM_THREADS) offs[i] = p.offsets[i];
+    for (int i = threadIdx.x; i < E; i += GEMM_THREADS) slots[i] = p.slot_of[i];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -347,8 +349,7 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, st, a0, a1, b, p);
 }
 
 template <int DT>

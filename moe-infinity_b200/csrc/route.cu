@@ -507,6 +507,8 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   __shared__ float s_scr[MAX_PL * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x;
+  pdl_launch();
+  pdl_wait();
   bool scores_in = false;
   if (p.logits) {
     for (int e = threadIdx.x; e < p.E; e += RT_THREADS) s_logits[e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
@@ -541,6 +543,8 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
   const int npairs = p.T * p.k;
+  pdl_launch();
+  pdl_wait();
   for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx[i] = p.topk_idx[i];
   __syncthreads();
   if (p.router == ROUTER_SWITCH_TOP1) {
@@ -625,9 +629,9 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   if (!route_args_ok(p)) return cudaErrorInvalidValue;
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
-    gate_topk_small_kernel<<<p.T, RT_THREADS, 0, st>>>(p);
-    permute_small_kernel<<<small_permute_grid(p), RT_THREADS, 0, st>>>(p);
-    return cudaGetLastError();
+    cudaError_t e = launch_pdl(gate_topk_small_kernel, dim3(p.T), dim3(RT_THREADS), 0, st, p);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(permute_small_kernel, dim3(small_permute_grid(p)), dim3(RT_THREADS), 0, st, p);
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
@@ -657,8 +661,7 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
     mask_to_topk_kernel<<<(p.T + RT_THREADS - 1) / RT_THREADS, RT_THREADS, 0, st>>>(p, mask);
     RouteParams q = p;
     q.router = ROUTER_MIXTRAL;   // routing decisions already taken: no capacity pass
-    permute_small_kernel<<<small_permute_grid(q), RT_THREADS, 0, st>>>(q);
-    return cudaGetLastError();
+    return launch_pdl(permute_small_kernel, dim3(small_permute_grid(q)), dim3(RT_THREADS), 0, st, q);
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
@@ -681,6 +684,8 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   const int t = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int k = p.k;
+  pdl_launch();
+  pdl_wait();
   // each warp loads the token's routing list into lanes 0..k-1 and sorts it by expert id via shuffles
   int my_e = 0x7fffffff, my_row = -1;
   float my_w = 0.f;
@@ -774,10 +779,9 @@ cudaError_t launch_combine(const CombineParams& p, cudaStream_t st) {
   if (p.k > MAX_K || p.H % 8 != 0) return cudaErrorInvalidValue;
   int gy = (p.H + CB_THREADS * 8 - 1) / (CB_THREADS * 8);
   dim3 grid(p.T, gy);
-  if (p.dtype == DT_BF16) combine_kernel<DT_BF16><<<grid, CB_THREADS, 0, st>>>(p);
-  else if (p.dtype == DT_F16) combine_kernel<DT_F16><<<grid, CB_THREADS, 0, st>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (p.dtype == DT_BF16) return launch_pdl(combine_kernel<DT_BF16>, grid, dim3(CB_THREADS), 0, st, p);
+  if (p.dtype == DT_F16) return launch_pdl(combine_kernel<DT_F16>, grid, dim3(CB_THREADS), 0, st, p);
+  return cudaErrorInvalidValue;
 }
 
 template <int DT>
