@@ -229,6 +229,12 @@ int b2m_ep_p2p_dispatch(b2m_ctx* ctx, int T_local, void* stream);
 int b2m_ep_p2p_regroup(b2m_ctx* ctx, int T_total, void* stream);
 int b2m_ep_p2p_return(b2m_ctx* ctx, void* stream);
 int b2m_ep_p2p_collect(b2m_ctx* ctx, int T_local, void* stream);
+/* fused variants (T_local <= 256): b2m_ep_p2p_route = b2m_route + b2m_ep_p2p_dispatch in the same two kernels (the
+ * permute kernel stores each gathered row straight into its owner's buffer); b2m_ep_p2p_combine = b2m_ep_p2p_collect +
+ * b2m_combine in one kernel (the combine kernel reads the returned rows in place). */
+int b2m_ep_p2p_route(b2m_ctx* ctx, int layer, const void* x, const void* router_in, int router_in_kind,
+                     int router_in_dtype, int T_local, void* stream);
+int b2m_ep_p2p_combine(b2m_ctx* ctx, int layer, const void* x, int T_local, void* out, void* stream);
 
 #ifdef __cplusplus
 }

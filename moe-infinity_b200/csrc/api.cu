@@ -693,8 +693,17 @@ int b2m_ws_ptr(b2m_ctx* c, int which, void** p) {
 }
 
 // ------------------------------------------------------------------------------------
+static EpParams ep_p2p_params(b2m_ctx* c);
+static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T,
+                      int seq_len, void* stream, bool ep_dispatch);
+
 int b2m_route(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T, int seq_len,
               void* stream) {
+  return route_impl(c, layer, x, router_in, kind, in_dtype, T, seq_len, stream, false);
+}
+
+static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T,
+                      int seq_len, void* stream, bool ep_dispatch) {
   int r = check_layer(c, layer);
   if (r) return r;
   if (T < 0 || T > c->cap_T) return fail(c, B2M_EINVAL, "T=%d exceeds workspace capacity %d", T, c->cap_T);
@@ -714,6 +723,12 @@ int b2m_route(b2m_ctx* c, int layer, const void* x, const void* router_in, int k
     return fail(c, B2M_EINVAL, "T=%d is not a multiple of seq_len=%d", T, p.seq_len);
   plan_gemm(c, T);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
+  if (ep_dispatch) {
+    if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
+    p.ep_dispatch = 1;
+    p.ep = ep_p2p_params(c);
+    p.y_zero = nullptr;        // the regroup kernel clears the accumulator for the rows this rank will compute
+  }
   CK(c, launch_route(p, st));
   c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0);
   c->last_counts_valid = false;
@@ -864,7 +879,13 @@ static int run_shared(b2m_ctx* c, int layer, const void* x, int T, cudaStream_t 
                              c->d_hmid_s, c->d_y_s, nt, ks, st);
 }
 
+static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream, bool ep_collect);
+
 int b2m_combine(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream) {
+  return combine_impl(c, layer, x, T, out, stream, false);
+}
+
+static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream, bool ep_collect) {
   int r = check_layer(c, layer);
   if (r) return r;
   if (T == 0) return B2M_OK;
@@ -884,6 +905,10 @@ int b2m_combine(b2m_ctx* c, int layer, const void* x, int T, void* out, void* st
     r = run_shared(c, layer, x, T, st);
     if (r) return r;
     p.y_shared = c->d_y_s;
+  }
+  if (ep_collect) {
+    p.ep_collect = 1;
+    p.ep = ep_p2p_params(c);
   }
   CK(c, launch_combine(p, st));
   c->stats.kernel_launches += 1;
@@ -1155,6 +1180,24 @@ int b2m_ep_p2p_dispatch(b2m_ctx* c, int T_local, void* stream) {
   c->ep_mode = true;
   c->ep_inline = 1;
   return B2M_OK;
+}
+
+int b2m_ep_p2p_route(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T_local,
+                     void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  if (T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "cap=%d < T_local*top_k", c->p2p.cap);
+  r = route_impl(c, layer, x, router_in, kind, in_dtype, T_local, 0, stream, true);
+  if (r) return r;
+  c->ep_mode = true;
+  c->ep_inline = 1;
+  return B2M_OK;
+}
+
+int b2m_ep_p2p_combine(b2m_ctx* c, int layer, const void* x, int T_local, void* out, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  return combine_impl(c, layer, x, T_local, out, stream, true);
 }
 
 int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {

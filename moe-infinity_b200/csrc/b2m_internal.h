@@ -47,52 +47,6 @@ cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_e
                                      const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st);
 int gemm_tc_smem_bytes(int nt, bool dual);
 
-// ---- routing / permutation / combine (route.cu) -----------------------------------------
-struct RouteParams {
-  // inputs
-  const void* x;             // [T,H] model dtype
-  const void* gate_w;        // [E,H] router weight (model dtype for Mixtral, any of bf16/f16/f32 otherwise) or null
-  const void* logits;        // optional precomputed router logits/scores [T,E]
-  int logits_dtype;          // DT_* of `logits`
-  int logits_are_scores;     // 1: `logits` already holds fp32 softmax scores (DeepSeek parity tests)
-  int gate_dtype;            // DT_* of gate_w
-  int T, H, E, k;
-  int dtype;                 // model dtype
-  int router;                // ROUTER_*
-  int n_group, topk_group, norm_topk_prob;
-  float routed_scaling_factor;
-  int seq_len, expert_capacity;   // Switch only
-  // outputs (workspace)
-  float* scores;             // [T,E] fp32 softmax probabilities (optional, may be null)
-  void* logits_out;          // [T,E] router logits in their natural dtype (optional)
-  int* topk_idx;             // [T,k]
-  float* topk_w;             // [T,k]
-  int* row_of;               // [T,k] permuted row of (t,j); -1 if dropped
-  int* perm_token;           // [T*k] source token of each permuted row
-  int* counts;               // [E]
-  int* offsets;              // [E+1]
-  int* chunk_counts;         // [ceil(T/32), E]
-  void* xp;                  // [T*k, H] gathered activations
-  float* y_zero;             // optional fp32 buffer to clear (split-K accumulator), y_zero_elems floats
-  size_t y_zero_elems;
-};
-cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
-// routing from a caller-supplied dense mask (reference compat: ExpertDispatcher::SetInputs + per-expert gather,
-// core/parallel/expert_dispatcher.h:66-70, expert_dispatcher.cpp:274-285)
-cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask /*[T,E]*/, cudaStream_t st);
-
-struct CombineParams {
-  const float* y;          // [rows, H] fp32 expert outputs (permuted row order)
-  const float* y_shared;   // [T, H] fp32 shared-expert output or null
-  const void* x;           // [T,H] (Switch pass-through) or null
-  const int* topk_idx;     // [T,k]
-  const float* topk_w;     // [T,k]
-  const int* row_of;       // [T,k]
-  void* out;               // [T,H] model dtype
-  int T, H, k, dtype, mode;
-};
-cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
-
 // ---- expert-parallel dispatch helpers (ep.cu) ----------------------------------------------
 struct EpParams {
   int nranks, rank, E, H, cap;      // cap = rows per peer in the fixed-capacity exchange buffers
@@ -127,6 +81,56 @@ cudaError_t launch_ep_pack(const EpParams& p, int max_rows, cudaStream_t st);
 cudaError_t launch_ep_regroup(const EpParams& p, cudaStream_t st);
 cudaError_t launch_ep_ungroup(const EpParams& p, int dtype, cudaStream_t st);
 cudaError_t launch_ep_unpack(const EpParams& p, int dtype, int max_rows, cudaStream_t st);
+
+// ---- routing / permutation / combine (route.cu) -----------------------------------------
+struct RouteParams {
+  // inputs
+  const void* x;             // [T,H] model dtype
+  const void* gate_w;        // [E,H] router weight (model dtype for Mixtral, any of bf16/f16/f32 otherwise) or null
+  const void* logits;        // optional precomputed router logits/scores [T,E]
+  int logits_dtype;          // DT_* of `logits`
+  int logits_are_scores;     // 1: `logits` already holds fp32 softmax scores (DeepSeek parity tests)
+  int gate_dtype;            // DT_* of gate_w
+  int T, H, E, k;
+  int dtype;                 // model dtype
+  int router;                // ROUTER_*
+  int n_group, topk_group, norm_topk_prob;
+  float routed_scaling_factor;
+  int seq_len, expert_capacity;   // Switch only
+  // outputs (workspace)
+  float* scores;             // [T,E] fp32 softmax probabilities (optional, may be null)
+  void* logits_out;          // [T,E] router logits in their natural dtype (optional)
+  int* topk_idx;             // [T,k]
+  float* topk_w;             // [T,k]
+  int* row_of;               // [T,k] permuted row of (t,j); -1 if dropped
+  int* perm_token;           // [T*k] source token of each permuted row
+  int* counts;               // [E]
+  int* offsets;              // [E+1]
+  int* chunk_counts;         // [ceil(T/32), E]
+  void* xp;                  // [T*k, H] gathered activations
+  float* y_zero;             // optional fp32 buffer to clear (split-K accumulator), y_zero_elems floats
+  size_t y_zero_elems;
+  int ep_dispatch;           // 1 (T <= 256 only): gathered rows go straight to the owning ranks' buffers (ep)
+  EpParams ep;
+};
+cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
+// routing from a caller-supplied dense mask (reference compat: ExpertDispatcher::SetInputs + per-expert gather,
+// core/parallel/expert_dispatcher.h:66-70, expert_dispatcher.cpp:274-285)
+cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask /*[T,E]*/, cudaStream_t st);
+
+struct CombineParams {
+  const float* y;          // [rows, H] fp32 expert outputs (permuted row order)
+  const float* y_shared;   // [T, H] fp32 shared-expert output or null
+  const void* x;           // [T,H] (Switch pass-through) or null
+  const int* topk_idx;     // [T,k]
+  const float* topk_w;     // [T,k]
+  const int* row_of;       // [T,k]
+  void* out;               // [T,H] model dtype
+  int T, H, k, dtype, mode;
+  int ep_collect;          // 1: expert outputs are read from the peer-written return area (model dtype rows)
+  EpParams ep;
+};
+cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
 
 // fp32 [rows,H] -> model dtype [rows,H] (compat path: per-expert outputs handed back to Python)
 cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st);

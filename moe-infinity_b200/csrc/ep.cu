@@ -13,6 +13,7 @@
 //   unpack   : back[r][i] rows -> fp32 Y at the source rank's permuted row positions, ready for the combine kernel
 #include "b2m_common.cuh"
 #include "b2m_internal.h"
+#include "ep_device.cuh"
 
 namespace b2m {
 
@@ -26,41 +27,6 @@ __device__ __forceinline__ void copy_row16(const uint16_t* src, uint16_t* dst, i
   for (int v = threadIdx.x; v < H / 8; v += EP_THREADS) d[v] = s[v];
 }
 
-
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Every CTA calls this after its last store to peer memory; the last CTA to arrive publishes epoch to all peers.
-__device__ void p2p_signal(const EpParams& p, int which /*0 dispatch, 1 return*/) {
-  __shared__ int s_last;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(p.done_ctr + which, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x == 0) {
-    p.done_ctr[which] = 0;
-    const int e = p.epoch[which] + 1;
-    p.epoch[which] = e;
-    __threadfence_system();
-    for (int r = 0; r < p.nranks; ++r) st_release_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
-  }
-}
-// Wait until every source rank's flag reached this rank's own epoch (all ranks issue the same number of exchanges).
-__device__ void p2p_wait(const EpParams& p, int which) {
-  if (threadIdx.x < p.nranks) {
-    const int want = p.epoch[which];
-    const int* f = (which ? p.local_back_flag : p.local_recv_flag) + threadIdx.x;
-    while (ld_acquire_sys(f) < want) __nanosleep(64);
-  }
-  __syncthreads();
-}
 
 // grid: one CTA per permuted row (grid-stride); CTA 0 also publishes counts and the source-side offsets copy
 __global__ void __launch_bounds__(EP_THREADS) ep_pack_kernel(EpParams p) {

@@ -11,6 +11,7 @@
 // activation rows, written with 16-byte vector stores.
 #include "b2m_common.cuh"
 #include "b2m_internal.h"
+#include "ep_device.cuh"
 
 namespace b2m {
 
@@ -588,6 +589,14 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   if (blockIdx.x == 0 && threadIdx.x <= p.E) {
     p.offsets[threadIdx.x] = s_off[threadIdx.x];
     if (threadIdx.x < p.E) p.counts[threadIdx.x] = s_tot[threadIdx.x];
+    if (p.ep_dispatch) p.ep.offsets_src[threadIdx.x] = s_off[threadIdx.x];
+  }
+  if (p.ep_dispatch && blockIdx.x == 0) {
+    // counts ride in the extra last row of every peer segment
+    for (int i = threadIdx.x; i < p.ep.nranks * p.E; i += RT_THREADS) {
+      const int r = i / p.E, e = i - r * p.E;
+      reinterpret_cast<int*>(ep_send_row(p.ep, r, p.ep.cap))[e] = s_tot[e];
+    }
   }
   if (warp < nchunks) {
     const int* cb = s_cnt[warp];
@@ -602,9 +611,19 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
     if (row < 0) continue;
     const int t = i / p.k;
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+    uint4* dst;
+    if (p.ep_dispatch) {
+      // expert-parallel: the row goes to the rank that owns its expert (peer memory over NVLink, or the send buffer)
+      const int El = p.E / p.ep.nranks;
+      const int e = s_idx[i];
+      const int r = e / El;
+      dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, r, row - s_off[r * El]));
+    } else {
+      dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+    }
     for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
   }
+  if (p.ep_dispatch && p.ep.p2p) p2p_signal(p.ep, 0);
   if (p.y_zero) {
     float4* z = reinterpret_cast<float4*>(p.y_zero);
     const size_t n4 = p.y_zero_elems / 4;
@@ -702,15 +721,29 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   }
   int rows[MAX_K];
   float ws[MAX_K];
+  const uint16_t* src16[MAX_K];
+  if (p.ep_collect) {
+    if (p.ep.p2p) p2p_wait(p.ep, 1);     // return rows of every owner rank have landed
+    if (lane < k && my_row >= 0) {
+      // permuted row -> (owner rank, position in that rank's segment of this rank's return area)
+      const int El = p.ep.E / p.ep.nranks;
+      const int r = my_e / El;
+      const int stride = p.ep.inline_counts ? p.ep.cap + 1 : p.ep.cap;
+      my_row = r * stride + (my_row - p.ep.offsets_src[r * El]);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < MAX_K; ++r) {
     rows[r] = -1;
     ws[r] = 0.f;
+    src16[r] = nullptr;
     if (r < k) {
       const uint32_t who = __ballot_sync(0xffffffffu, lane < k && rank == r);
       const int src = __ffs(who) - 1;
       rows[r] = __shfl_sync(0xffffffffu, my_row, src);
       ws[r] = __shfl_sync(0xffffffffu, my_w, src);
+      if (p.ep_collect && rows[r] >= 0)
+        src16[r] = reinterpret_cast<const uint16_t*>(p.ep.back_rows) + (size_t)rows[r] * p.H;
     }
   }
   const int H = p.H;
@@ -722,9 +755,17 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
 #pragma unroll
     for (int r = 0; r < MAX_K; ++r) {
       if (r < k && rows[r] >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)rows[r] * H + h);
-        const float4 a = src[0], b = src[1];
-        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float y[8];
+        if (p.ep_collect) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src16[r] + h);
+          const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = Half16<DT>::to_f(vs[i]);
+        } else {
+          const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)rows[r] * H + h);
+          const float4 a = src[0], b = src[1];
+          y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+        }
         const float w = ws[r];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -81,6 +81,8 @@ SYMBOLS = [
     ("b2m_ep_p2p_regroup", _I, [_VP, _I, _VP]),
     ("b2m_ep_p2p_return", _I, [_VP, _VP]),
     ("b2m_ep_p2p_collect", _I, [_VP, _I, _VP]),
+    ("b2m_ep_p2p_route", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
+    ("b2m_ep_p2p_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
 ]
 
 _lib = None

@@ -80,6 +80,25 @@ class _EngineOps:
         torch.cuda.synchronize()
         dist.barrier(group=group)
 
+    def p2p_route(self, layer, x, router_logits=None):
+        """route + dispatch fused (<= 256 tokens): gathered rows are stored straight into the owners' buffers."""
+        e = self.eng
+        x2 = e._check_x(x)
+        rin, kind, rdt = e._router_args(router_logits, None)
+        e._ck(e.lib.b2m_ep_p2p_route(e._h, layer, C.c_void_p(x2.data_ptr()),
+                                     C.c_void_p(rin.data_ptr() if rin is not None else 0), kind, rdt, x2.shape[0],
+                                     self._s()))
+
+    def p2p_combine(self, layer, x, out):
+        """collect + combine fused: the combine kernel reads the returned rows in place."""
+        e = self.eng
+        x2 = e._check_x(x)
+        if out is None:
+            out = torch.empty_like(x2)
+        e._ck(e.lib.b2m_ep_p2p_combine(e._h, layer, C.c_void_p(x2.data_ptr()), x2.shape[0],
+                                       C.c_void_p(out.data_ptr()), self._s()))
+        return out
+
     def p2p_dispatch(self, T):
         e = self.eng
         e._ck(e.lib.b2m_ep_p2p_dispatch(e._h, T, self._s()))
@@ -102,9 +121,10 @@ class EPMoE:
     a CPU stand-in to exercise the exchange schedule under gloo)."""
 
     def __init__(self, ops, *, num_experts: int, hidden: int, top_k: int, T_local: int, dtype, device,
-                 group: Optional[dist.ProcessGroup] = None, p2p: bool = False):
+                 group: Optional[dist.ProcessGroup] = None, p2p: bool = False, fused: bool = True):
         self.ops = ops
         self.p2p = p2p
+        self.fused = fused
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -131,6 +151,12 @@ class EPMoE:
         if T != self.T:
             raise ValueError(f"EPMoE was sized for T_local={self.T}, got {T}")
         w, r, cap = self.world, self.rank, self.cap
+        if self.p2p and T <= 256 and self.fused:
+            self.ops.p2p_route(layer, x, router_logits)          # gate/top-k + permute-and-dispatch (2 kernels)
+            self.ops.p2p_regroup(self.T_total)
+            self.ops.run_experts(layer, self.T_total)
+            self.ops.p2p_return()
+            return self.ops.p2p_combine(layer, x, out)            # collect-and-combine (1 kernel)
         self.ops.route(layer, x, router_logits)
         if self.p2p:
             self.ops.p2p_dispatch(T)

@@ -41,7 +41,8 @@ def main():
         for e in local_experts(rank, E, world):
             part2.load_expert(l, e, experts[l][e])
         part2.set_gate(l, gates[l])
-    ep2 = EPMoE(_EngineOps(part2), num_experts=E, hidden=H, top_k=K, T_local=T, dtype=dt, device=dev, p2p=True)
+    ep2 = EPMoE(_EngineOps(part2), num_experts=E, hidden=H, top_k=K, T_local=T, dtype=dt, device=dev, p2p=True,
+                fused=(os.environ.get("B2M_EP_FUSED", "1") == "1"))
     gx = torch.Generator().manual_seed(50 + rank)
     bad = 0
     for it in range(6):
