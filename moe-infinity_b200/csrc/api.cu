@@ -806,42 +806,9 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
     for (int e = 0; e < E; ++e)
       if (!c->ep_mode || c->experts[(size_t)layer * E + e].state != ST_UNREGISTERED) active.push_back(layer * E + e);
   }
-  // residency
-  for (int id : active) {
-    if (!do_residency) break;
-    Expert& x = c->experts[id];
-    if (x.state == ST_UNREGISTERED) return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
-    if (on_demand) {
-      c->stats.dispatches++;
-      x.visits += 1;            // incache_visit_count += 1 for every dispatched expert (expert_dispatcher.cpp:264)
-      x.total_visits += 1;
-    }
-    if (x.state == ST_RESIDENT || x.state == ST_LOADING) {
-      if (on_demand) {
-        c->stats.hits++;
-        if (x.prefetched_unused) { c->stats.prefetch_useful++; x.prefetched_unused = false; }
-      }
-    } else {
-      if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
-      if (c->ep_mode) return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", id / E, id % E);
-      if (on_demand) c->stats.misses++;
-      const int slot = acquire_slot(c, active, false);
-      if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot: %d experts active, %d slots", (int)active.size(), c->arena.nslots);
-      r = issue_copy(c, id, slot, c->fetch_stream, true);
-      if (r) return r;
-    }
-  }
-  for (int id : active) {
-    Expert& x = c->experts[id];
-    if (x.ready_pending) {
-      CK(c, cudaStreamWaitEvent(st, x.ready, 0));
-      x.ready_pending = false;
-    }
-    if (x.state == ST_LOADING) x.state = ST_RESIDENT;   // every later use is stream-ordered after the wait above
-  }
-  r = upload_row_if_dirty(c, layer, st);
-  if (r) return r;
-
+  // ---- residency + launch, in waves.  Normally one wave holds every activated expert.  When the HBM budget is
+  // smaller than one layer's active set (reference: experts run one at a time, a single slot suffices) the set is
+  // split: a wave is staged, its GEMMs are launched against a slot row that names only that wave, then the next.
   GemmParams base;
   memset(&base, 0, sizeof base);
   base.offsets = c->d_offsets;
@@ -849,16 +816,81 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   base.E = E;
   base.single_n = -1;
   const int ni = nt_index(c->cur_nt);
-  r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid, c->d_hmid,
-                          c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
-  if (r) return r;
-  if (do_residency) c->last_active = active;
-  if (on_demand && (phases & 2)) {
-    int evi;
-    cudaEvent_t ev = next_ring_event(c, &evi);
-    CK(c, cudaEventRecord(ev, st));
-    for (int id : active) c->slots[c->experts[id].slot].last_use_ev = evi;
+  if (!do_residency) {
+    r = upload_row_if_dirty(c, layer, st);
+    if (r) return r;
+    return launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid,
+                               c->d_hmid, c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
   }
+  for (int id : active)
+    if (c->experts[id].state == ST_UNREGISTERED)
+      return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
+  std::vector<int> remaining = active, wave;
+  int waves = 0;
+  while (!remaining.empty()) {
+    wave.clear();
+    for (int id : remaining) {
+      Expert& x = c->experts[id];
+      const bool resident = x.state == ST_RESIDENT || x.state == ST_LOADING;
+      if (!resident) {
+        if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
+        if (c->ep_mode) return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", id / E, id % E);
+        const int slot = acquire_slot(c, remaining, false);   // never evict an expert this layer still has to run
+        if (slot < 0) continue;                               // no room in this wave: stays in `remaining`
+        if (on_demand) c->stats.misses++;
+        r = issue_copy(c, id, slot, c->fetch_stream, true);
+        if (r) return r;
+      } else if (on_demand) {
+        c->stats.hits++;
+        if (x.prefetched_unused) { c->stats.prefetch_useful++; x.prefetched_unused = false; }
+      }
+      if (on_demand) {
+        c->stats.dispatches++;
+        x.visits += 1;            // incache_visit_count += 1 for every dispatched expert (expert_dispatcher.cpp:264)
+        x.total_visits += 1;
+      }
+      wave.push_back(id);
+    }
+    if (wave.empty())
+      return fail(c, B2M_ENOMEM, "no evictable HBM slot: %d experts active, %d slots", (int)active.size(), c->arena.nslots);
+    for (int id : wave) {
+      Expert& x = c->experts[id];
+      if (x.ready_pending) {
+        CK(c, cudaStreamWaitEvent(st, x.ready, 0));
+        x.ready_pending = false;
+      }
+      if (x.state == ST_LOADING) x.state = ST_RESIDENT;   // every later use is stream-ordered after the wait above
+    }
+    const bool whole = wave.size() == active.size();
+    if (!whole && phases != 3) return fail(c, B2M_ESTATE, "phase-split launches need the whole active set resident");
+    if (whole) {
+      r = upload_row_if_dirty(c, layer, st);
+      if (r) return r;
+    } else {
+      // partial wave: the device row names only this wave's experts (others -1 => their tiles are skipped)
+      if (waves > 0 && waves % (STAGE_RING - 1) == 0) CK(c, cudaStreamSynchronize(st));   // staging ring would wrap
+      int* stage = c->h_stage + (size_t)c->stage_pos * E;
+      c->stage_pos = (c->stage_pos + 1) % STAGE_RING;
+      for (int e = 0; e < E; ++e) stage[e] = -1;
+      for (int id : wave) stage[id % E] = c->experts[id].slot;
+      CK(c, cudaMemcpyAsync(c->d_slot_of + (size_t)layer * E, stage, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+      c->row_dirty[layer] = 1;   // the true mapping is re-uploaded by the next whole-wave call
+    }
+    r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid,
+                            c->d_hmid, c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
+    if (r) return r;
+    if (on_demand) {
+      int evi;
+      cudaEvent_t ev = next_ring_event(c, &evi);
+      CK(c, cudaEventRecord(ev, st));
+      for (int id : wave) c->slots[c->experts[id].slot].last_use_ev = evi;
+    }
+    ++waves;
+    remaining.erase(std::remove_if(remaining.begin(), remaining.end(),
+                                   [&](int id) { return std::find(wave.begin(), wave.end(), id) != wave.end(); }),
+                    remaining.end());
+  }
+  c->last_active = wave;   // experts of the last wave are still being read by kernels in flight
   return B2M_OK;
 }
 

@@ -68,26 +68,37 @@ class CacheOracle:
         return True
 
     def dispatch(self, layer: int, experts: Iterable[int]) -> List[Tuple[int, bool]]:
-        """One MoE layer call with the given activated experts (ascending).  Returns [(expert, hit)]."""
-        active = [self._id(layer, e) for e in sorted(experts)]
+        """One MoE layer call with the given activated experts.  Returns [(expert, hit)] sorted by expert.
+        If the active set does not fit next to itself it is processed in waves (csrc/api.cu b2m_run_experts_ex):
+        a wave takes every still-to-run expert that is resident or can get a slot without evicting another
+        still-to-run expert; finished waves become evictable."""
+        active = [self._id(layer, e) for e in sorted(set(experts))]
         out = []
-        for i in active:
-            self.stats["dispatches"] += 1
-            self.visits[i] += 1
-            if self.resident[i]:
-                self.stats["hits"] += 1
-                if self.prefetched_unused[i]:
-                    self.stats["prefetch_useful"] += 1
-                    self.prefetched_unused[i] = False
-                out.append((i % self.E, True))
-            else:
-                self.stats["misses"] += 1
-                if not self._acquire(active, False):
-                    raise RuntimeError("no evictable slot")
-                self.resident[i] = True
-                out.append((i % self.E, False))
-        self.last_active = active
-        return out
+        remaining = list(active)
+        wave: List[int] = []
+        while remaining:
+            wave = []
+            for i in remaining:
+                if self.resident[i]:
+                    self.stats["hits"] += 1
+                    if self.prefetched_unused[i]:
+                        self.stats["prefetch_useful"] += 1
+                        self.prefetched_unused[i] = False
+                    out.append((i % self.E, True))
+                else:
+                    if not self._acquire(remaining, False):
+                        continue
+                    self.stats["misses"] += 1
+                    self.resident[i] = True
+                    out.append((i % self.E, False))
+                self.stats["dispatches"] += 1
+                self.visits[i] += 1
+                wave.append(i)
+            if not wave:
+                raise RuntimeError("no evictable slot")
+            remaining = [i for i in remaining if i not in wave]
+        self.last_active = wave
+        return sorted(out)
 
     def replace_cache_candidates(self, pairs: Iterable[Tuple[int, int]]):
         self.protected = {self._id(l, e) for l, e in pairs}

@@ -123,13 +123,38 @@ def test_clear_counts_and_chunked_copies(lib_built):
     assert eng.stats()["misses"] > 0
 
 
-def test_too_few_slots_is_an_error_not_an_abort(lib_built):
+def test_fewer_slots_than_active_experts_runs_in_waves(lib_built):
+    """The reference runs experts one at a time and works with a single slot; here the active set is split into
+    waves.  Results and cache statistics must match the all-resident engine / the policy oracle."""
+    experts, gates = _model(13)
+    ref = _engine(experts, gates, L * E)
+    g = torch.Generator().manual_seed(8)
+    for nslots in (1, 2, 3):
+        eng = _engine(experts, gates, nslots)
+        orc = CacheOracle(L, E, nslots)
+        for step in range(3):
+            for l in range(L):
+                x = torch.randn(6, H, generator=g).to(DT).cuda()
+                a = eng.forward(l, x)
+                b = ref.forward(l, x)
+                torch.cuda.synchronize()
+                assert torch.equal(a, b), (nslots, step, l)
+                counts = eng.last_counts()
+                orc.dispatch(l, [e for e in range(E) if counts[e] > 0])
+        s = eng.stats()
+        for k in ("dispatches", "hits", "misses", "evictions"):
+            assert s[k] == orc.stats[k], (nslots, k, s[k], orc.stats[k])
+
+
+def test_no_evictable_slot_is_an_error_not_an_abort(lib_built):
     from moe_infinity_b200 import B2MError
     experts, gates = _model(13)
-    eng = _engine(experts, gates, 1)
+    eng = _engine(experts, gates, 2)
+    eng.make_resident(1, 0, pin=True)       # both slots pinned by another layer's experts
+    eng.make_resident(1, 1, pin=True)
     x = torch.randn(6, H).to(DT).cuda()
     with pytest.raises(B2MError) as ei:
-        eng.forward(0, x)                 # top-2 needs >= 2 experts resident at once
+        eng.forward(0, x)
     assert "slot" in str(ei.value)
 
 

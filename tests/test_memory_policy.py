@@ -151,11 +151,16 @@ def test_cache_oracle_lfu_eviction_and_tie_order():
     assert c.stats["misses"] == 4 and c.stats["hits"] == 1
 
 
-def test_cache_oracle_never_evicts_current_dispatch():
+def test_cache_oracle_waves_when_active_set_exceeds_slots():
     c = CacheOracle(1, 4, 2)
     c.dispatch(0, [0, 1])
+    # 3 active experts, 2 slots: wave 1 = {1 (hit)} + nothing else fits without evicting a still-to-run expert...
+    res = c.dispatch(0, [1, 2, 3])
+    assert res == [(1, True), (2, False), (3, False)]
+    assert c.stats["evictions"] == 2 and sum(c.resident) == 2
+    c0 = CacheOracle(1, 4, 0)
     with pytest.raises(RuntimeError):
-        c.dispatch(0, [1, 2, 3])       # needs 3 slots at once, only 2 exist
+        c0.dispatch(0, [0])
 
 
 def test_cache_oracle_prefetch_respects_protection():
