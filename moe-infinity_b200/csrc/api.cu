@@ -754,6 +754,7 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
 static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, const CUtensorMap& tm_b_up,
                                const CUtensorMap& tm_b_down, const void* b_up, int ldb_up, const void* b_down,
                                void* hmid, float* y, int nt, int ksplit, cudaStream_t st, int phases = 3) {
+  const bool T_hint_large = c->cur_T > 128;   // several token tiles per expert are likely: tensor-bound regime
   const b2m_config& f = c->cfg;
   const ExpertShape& s = a.shape;
   GemmParams up = base;
@@ -771,7 +772,13 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
   } else {
     if (phases & 1) CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
-    if (phases & 2) CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+    if (phases & 2) {
+      // prefill-sized token tiles: pair two m-tiles of the down matrix on one token tile (dual_m) -> 1.33x the
+      // FLOP per operand byte; decode keeps single tiles (finer split-K balance, HBM bound anyway)
+      const bool pair = nt == 128 && s.H >= 256 && T_hint_large;
+      dn.dual_m = pair ? 1 : 0;
+      CK(c, launch_grouped_gemm_tc(f.dtype, nt, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+    }
   }
   c->stats.kernel_launches += ((phases & 1) ? 1 : 0) + ((phases & 2) ? 1 : 0);
   return B2M_OK;

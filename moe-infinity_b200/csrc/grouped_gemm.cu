@@ -53,7 +53,7 @@ struct TileWalker {
   const int* tile_start;  // smem [E+1]
   const int* offs;        // smem [E+1]
   const int* slots;       // smem [E]
-  int E, NTv, ksplit, kblocks, e_cur;
+  int E, NTv, ksplit, kblocks, e_cur, m_step;
   __device__ __forceinline__ bool get(int tile, TileInfo& t) {
     if (tile >= tile_start[E]) return false;
     while (tile >= tile_start[e_cur + 1]) ++e_cur;
@@ -69,7 +69,7 @@ struct TileWalker {
     const int kb_per = (kblocks + ksplit - 1) / ksplit;
     t.e = e;
     t.slot = slots[e];
-    t.m0 = m * BLOCK_M;
+    t.m0 = m * m_step;
     t.row0 = offs[e] + n * NTv;
     t.ncols = min(NTv, n_e - n * NTv);
     t.kb_begin = s * kb_per;
@@ -108,7 +108,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int lane = threadIdx.x & 31;
   const int E = p.E;
   const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // dual_m: the two A tiles are rows [m0, m0+128) and [m0+128, m0+256) of the SAME matrix sharing one token tile
+  // (doubles the arithmetic intensity of the down projection at prefill; the kernel is L2->SM operand-bandwidth bound)
+  const int m_step = (DUAL && p.dual_m) ? 2 * BLOCK_M : BLOCK_M;
+  const int m_tiles = (p.M + m_step - 1) / m_step;
 
   // ---- one-time setup -------------------------------------------------------------
   pdl_launch();
@@ -154,7 +157,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0};
+  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0, m_step};
   TileInfo t;
 
   if (warp == 0) {
@@ -169,9 +172,11 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           uint8_t* sA1 = sA0 + A_TILE_BYTES;
           uint8_t* sB = sA0 + (DUAL ? 2 : 1) * A_TILE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          // weights are streamed exactly once per (tile): evict-first; tokens are re-read by every m-tile: keep
-          tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, CACHE_EVICT_FIRST);
-          if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0, t.slot, CACHE_EVICT_FIRST);
+          // decode: weights are streamed exactly once -> evict-first.  Several n-tiles per expert (prefill): the same
+          // weight tile is re-read by every n-tile -> keep it in L2.  Tokens are re-read by every m-tile: keep.
+          const uint64_t wh = (offs[t.e + 1] - offs[t.e] <= NT) ? CACHE_EVICT_FIRST : CACHE_EVICT_NORMAL;
+          tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, wh);
+          if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0 + (p.dual_m ? BLOCK_M : 0), t.slot, wh);
           tma_load_2d(&tmB, &full_bar[stage], sB, kb * BLOCK_K, t.row0, CACHE_EVICT_LAST);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -235,10 +240,16 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (row_ok && c0 + j < t.ncols) {
+            if (c0 + j < t.ncols) {
               float* dst = out + (size_t)(t.row0 + c0 + j) * p.ld_out + m;
-              const float v = __uint_as_float(vg[j]);
-              if (p.ksplit > 1) atomicAdd(dst, v); else *dst = v;
+              if (row_ok) {
+                const float v = __uint_as_float(vg[j]);
+                if (p.ksplit > 1) atomicAdd(dst, v); else *dst = v;
+              }
+              if (DUAL && m + BLOCK_M < p.M) {   // dual_m: second accumulator = rows m0+128..m0+255
+                const float v = __uint_as_float(vu[j]);
+                if (p.ksplit > 1) atomicAdd(dst + BLOCK_M, v); else dst[BLOCK_M] = v;
+              }
             }
           }
         } else {
