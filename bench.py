@@ -10,16 +10,18 @@ experts HBM resident (90.2 GB).  A "step" = one pass of the hot path (router gat
 grouped gate/up GEMM with fused SwiGLU + grouped down GEMM + weighted combine) over the 32 layers for one batch
 of synthetic hidden states (the attention between MoE blocks is outside the path).
   value : whole-job tokens/s with inputs resident in HBM, the 32-layer step replayed as one CUDA graph.
-  e2e   : same metric through the public Python API (MoEEngine.forward per layer) with HOST buffers: the step's
-          inputs are copied from pinned host memory and its outputs copied back inside the timed region.
+  e2e   : same metric through the public Python API with HOST buffers (DecodeSession.step()): the step's inputs
+          are copied from pinned host memory and its outputs copied back inside the timed region; the per-layer
+          eager API (MoEEngine.forward x 32) is reported next to it.
   roofline : dominant kernel = grouped gate/up GEMM (K3, 2/3 of the weight bytes), timed with CUDA events on
           its launch stream; algorithmic bytes counted from the actual routing of the timed inputs.
   cpu_baseline : the oracle port (oracle/moe_oracle.py, the reference's per-expert ATen loop) on the host cores
           for a bounded sample (one full-size layer, repeated) -- also used as a full-size parity check.
 --impl reference times that oracle port only (kind "port": the reference's own native engine needs libtorch +
 a GPU and its Python package does not import in this image).
-N>1: expert parallel over N ranks (expert e -> rank e % N), weak scaling (batch 8 per rank), fixed-capacity
-all-to-all token dispatch over NCCL (moe_infinity_b200.ep).
+N>1: expert parallel over N ranks (rank r owns experts [r*E/N, (r+1)*E/N)), weak scaling (batch 8 per rank),
+fused peer-to-peer token dispatch over NVLink (B2M_EP_EXCHANGE=nccl selects the NCCL all-to-all baseline);
+see moe_infinity_b200/ep.py.
 """
 from __future__ import annotations
 
@@ -300,33 +302,47 @@ def run_ours(args):
                 "step": {"algorithmic_bytes": bytes_step, "achieved": bytes_step / (ms_per_step * 1e-3) / 1e9,
                          "frac": bytes_step / (ms_per_step * 1e-3) / 1e9 / peak}}
 
-    # ---- e2e: public API per layer, HOST buffers, copies inside the timed region
-    x_host = x_dev.cpu().pin_memory()
-    out_host = torch.empty_like(x_host).pin_memory()
+    # ---- e2e: public API with HOST buffers -- DecodeSession.step(): pinned host -> device copy of the step's inputs,
+    # all 32 layers, device -> pinned host copy of the outputs, one stream synchronise; all inside the timed region
+    from moe_infinity_b200 import DecodeSession
+    sess = DecodeSession(eng, T).capture()
+    sess.x_host.copy_(x_dev.cpu())
+    for _ in range(max(3, args.warmup // 2)):
+        sess.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sess.step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    # same thing without the graph: MoEEngine.forward called layer by layer from Python
+    x_host, out_host = sess.x_host, sess.out_host
     x_in = torch.empty_like(x_dev)
 
-    def step_e2e():
+    def step_eager():
         x_in.copy_(x_host, non_blocking=True)
         for l in range(L):
             eng.forward(l, x_in[l], out=out_dev[l])
         out_host.copy_(out_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for _ in range(max(3, args.warmup // 2)):
-        step_e2e()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        step_eager()
     torch.cuda.synchronize()
-    e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+        step_eager()
+    eager_ms = (time.perf_counter() - t0) * 1e3
     e2e = {"value": BATCH * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s",
            "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2,
-           "ms_per_step": e2e_ms / args.steps, "api": "MoEEngine.forward per layer (ctypes -> b2m_moe_forward)"}
+           "ms_per_step": e2e_ms / args.steps,
+           "api": "DecodeSession.step(): graph of H2D copy + 32 x b2m_moe_forward + D2H copy, host synchronised",
+           "eager_per_layer_api": {"value": BATCH * args.steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / args.steps,
+                                   "api": "MoEEngine.forward per layer (ctypes -> b2m_moe_forward)"}}
 
     # ---- cpu baseline on a bounded sample + full-size parity of layer 0
     cpu = None

@@ -9,11 +9,14 @@ from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, EXPERT_DEEPSEEK, EXPERT_MIX
                    EXPERT_SWITCH_GATED, NUMERICS_FP32, NUMERICS_REFERENCE, ROUTER_DEEPSEEK_GREEDY,
                    ROUTER_DEEPSEEK_GROUP, ROUTER_MIXTRAL, ROUTER_SWITCH_TOP1, B2MError)
 
-__all__ = ["MoEEngine", "B2MError"]
+__all__ = ["MoEEngine", "DecodeSession", "B2MError"]
 
 
 def __getattr__(name):
     if name == "MoEEngine":
         from .engine import MoEEngine
         return MoEEngine
+    if name == "DecodeSession":
+        from .engine import DecodeSession
+        return DecodeSession
     raise AttributeError(name)

@@ -275,3 +275,52 @@ class MoEEngine:
         arr = (C.c_int32 * self.E)()
         self._ck(self.lib.b2m_last_counts(self._h, arr))
         return list(arr)
+
+
+class DecodeSession:
+    """One decode step (all MoE layers of the model for a fixed batch) as a replayable CUDA graph with HOST I/O.
+
+    The step's inputs live in pinned host memory (`x_host[L,T,H]`, written by the caller), the outputs come back in
+    pinned host memory (`out_host[L,T,H]`); the graph contains the H2D copy, every layer's kernels and the D2H copy.
+    Only valid when every expert is HBM resident (the on-demand path synchronises with the host and cannot be
+    captured) -- which is exactly the regime where per-layer Python/launch overhead would otherwise matter."""
+
+    def __init__(self, engine: MoEEngine, T: int, layers: Optional[Sequence[int]] = None):
+        self.eng = engine
+        self.layers = list(range(engine.L)) if layers is None else list(layers)
+        n = len(self.layers)
+        self.x_host = torch.zeros(n, T, engine.H, dtype=engine.dtype).pin_memory()
+        self.out_host = torch.zeros(n, T, engine.H, dtype=engine.dtype).pin_memory()
+        self._x = torch.zeros(n, T, engine.H, dtype=engine.dtype, device=engine.device)
+        self._out = torch.zeros_like(self._x)
+        self._graph = None
+
+    def _run(self):
+        self._x.copy_(self.x_host, non_blocking=True)
+        for i, l in enumerate(self.layers):
+            self.eng.forward(l, self._x[i], out=self._out[i])
+        self.out_host.copy_(self._out, non_blocking=True)
+
+    def capture(self):
+        side = torch.cuda.Stream(device=self.eng.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run()          # warm-up outside capture: kernel attributes, slot table upload
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run()
+        self._graph = g
+        return self
+
+    def step(self, sync: bool = True) -> torch.Tensor:
+        """Replay the captured step on the current stream; returns the pinned output buffer."""
+        if self._graph is None:
+            self._run()
+        else:
+            self._graph.replay()
+        if sync:
+            torch.cuda.current_stream().synchronize()
+        return self.out_host
