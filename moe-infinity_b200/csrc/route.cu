@@ -105,45 +105,58 @@ __device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[
   __syncwarp();
 }
 
-// Large-T gate: one warp per token, 8 experts per pass (x re-read from L1 for E > 8), 16-byte loads of both operands.
+// One warp, one token, experts [e0, e0+8): x is loaded once per 8-element chunk and reused for all 8 rows
+// (16-byte loads of both operands).  out[i] (i < 8) valid in every lane.
+__device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int e0, float (&out)[8]) {
+  const int lane = threadIdx.x & 31;
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+  for (int h = lane * 8; h < p.H; h += 256) {
+    float xf[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + h), p.dtype, xf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (e0 + i < p.E) {
+        float wf[8];
+        if (p.gate_dtype == DT_F32) {
+          const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)(e0 + i) * p.H + h;
+          const float4 a = *reinterpret_cast<const float4*>(w), b = *reinterpret_cast<const float4*>(w + 4);
+          wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = b.x; wf[5] = b.y; wf[6] = b.z; wf[7] = b.w;
+        } else {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)(e0 + i) * p.H + h),
+                  p.gate_dtype, wf);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float v = warp_sum(acc[i]);
+    out[i] = (p.router == ROUTER_MIXTRAL) ? round_to(v, p.dtype) : v;
+  }
+}
+
+// Large-T gate: one warp per token, 8 experts per pass.
 __global__ void __launch_bounds__(256) gate_logits_kernel(const RouteParams p) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= p.T) return;
-  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
   for (int e0 = 0; e0 < p.E; e0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int h = lane * 8; h < p.H; h += 256) {
-      float xf[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + h), p.dtype, xf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (e0 + i < p.E) {
-          float wf[8];
-          if (p.gate_dtype == DT_F32) {
-            const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)(e0 + i) * p.H + h;
-            const float4 a = *reinterpret_cast<const float4*>(w), b = *reinterpret_cast<const float4*>(w + 4);
-            wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = b.x; wf[5] = b.y; wf[6] = b.z; wf[7] = b.w;
-          } else {
-            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)(e0 + i) * p.H + h),
-                    p.gate_dtype, wf);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
-        }
-      }
-    }
+    float v[8];
+    gate_dot8_warp(p, t, e0, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float v = warp_sum(acc[i]);
       if (lane == 0 && e0 + i < p.E) {
         if (p.router == ROUTER_MIXTRAL)
           reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e0 + i] =
-              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v) : Half16<DT_F16>::from_f(v);
+              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v[i]) : Half16<DT_F16>::from_f(v[i]);
         else
-          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v;
+          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v[i];
       }
     }
   }
@@ -515,9 +528,20 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
     for (int e = threadIdx.x; e < p.E; e += RT_THREADS) s_logits[e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
     scores_in = p.logits_are_scores != 0;
   } else {
-    for (int e = warp; e < p.E; e += RT_WARPS) {
-      const float v = gate_dot_warp(p, t, e);
-      if (lane == 0) s_logits[e] = v;
+    if (p.E >= 8 * RT_WARPS) {
+      // many experts (DeepSeek): every warp takes 8 experts per pass and reads the token row once per pass
+      for (int e0 = warp * 8; e0 < p.E; e0 += 8 * RT_WARPS) {
+        float v[8];
+        gate_dot8_warp(p, t, e0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (lane == 0 && e0 + i < p.E) s_logits[e0 + i] = v[i];
+      }
+    } else {
+      for (int e = warp; e < p.E; e += RT_WARPS) {
+        const float v = gate_dot_warp(p, t, e);
+        if (lane == 0) s_logits[e] = v;
+      }
     }
   }
   __syncthreads();
