@@ -120,9 +120,8 @@ struct b2m_ctx {
 
   // streams / events
   cudaStream_t fetch_stream = nullptr, prefetch_stream = nullptr;
-  cudaEvent_t ev_ring[EVENT_RING];
+  cudaEvent_t ev_ring[EVENT_RING] = {nullptr};
   int ev_pos = 0;
-  cudaEvent_t ev_route = nullptr;
 
   // prefetch scheduler
   std::unordered_set<int> protected_set;
@@ -164,8 +163,6 @@ int fail(b2m_ctx* c, int code, const char* fmt, ...) {
     if (_e != cudaSuccess)                                                                            \
       return fail((c), B2M_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
-
-int elem_size(int dtype) { return (dtype == B2M_DTYPE_F32) ? 4 : 2; }
 
 bool make_shape(int expert_type, int H, int I, ExpertShape* s) {
   const size_t m = (size_t)H * I * 2;
@@ -550,7 +547,6 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaStreamCreateWithPriority(&c->fetch_stream, cudaStreamNonBlocking, hi));
   CKC(cudaStreamCreateWithPriority(&c->prefetch_stream, cudaStreamNonBlocking, lo));
   for (int i = 0; i < EVENT_RING; ++i) CKC(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
-  CKC(cudaEventCreateWithFlags(&c->ev_route, cudaEventDisableTiming));
   c->stats.slots = (uint64_t)nslots;
   c->stats.slot_bytes = shape.bytes;
 #undef CKC
@@ -575,10 +571,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
   if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
   if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
-  if (c->ev_route) {
-    for (int i = 0; i < EVENT_RING; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
-    cudaEventDestroy(c->ev_route);
-  }
+  for (int i = 0; i < EVENT_RING; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
   delete c;
   return B2M_OK;
 }

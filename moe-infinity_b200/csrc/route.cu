@@ -96,15 +96,6 @@ __device__ float gate_dot_warp(const RouteParams& p, int t, int e) {
   acc = warp_sum(acc);
   return (p.router == ROUTER_MIXTRAL) ? round_to(acc, p.dtype) : acc;
 }
-__device__ void gate_token_warp(const RouteParams& p, int t, float* s_logits /*[E] smem, this warp*/) {
-  const int lane = threadIdx.x & 31;
-  for (int e = 0; e < p.E; ++e) {
-    const float v = gate_dot_warp(p, t, e);
-    if (lane == 0) s_logits[e] = v;
-  }
-  __syncwarp();
-}
-
 // One warp, one token, experts [e0, e0+8): x is loaded once per 8-element chunk and reused for all 8 rows
 // (16-byte loads of both operands).  out[i] (i < 8) valid in every lane.
 __device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int e0, float (&out)[8]) {
@@ -371,14 +362,10 @@ __global__ void __launch_bounds__(RT_THREADS) route_topk_kernel(const RouteParam
   for (int i = warp; i < TOK_PER_BLOCK; i += RT_WARPS) {
     const int t = tb + i;
     if (t >= p.T) break;
-    bool scores_in = false;
-    if (p.logits) {
-      for (int e = lane; e < p.E; e += 32) s_logits[warp][e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
-      scores_in = p.logits_are_scores != 0;
-      __syncwarp();
-    } else {
-      gate_token_warp(p, t, s_logits[warp]);
-    }
+    // large-T path: logits/scores always come from memory (caller-supplied, or written by gate_logits_kernel)
+    for (int e = lane; e < p.E; e += 32) s_logits[warp][e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
+    const bool scores_in = p.logits_are_scores != 0;
+    __syncwarp();
     if (p.logits_out && !scores_in) {
       for (int e = lane; e < p.E; e += 32) {
         const float lv = s_logits[warp][e];

@@ -111,6 +111,45 @@ def deepseek(T, iters=20):
             "algorithmic_bytes": bytes_step, "hbm_gbs": bytes_step / ms / 1e6, "tflops": flops / ms / 1e9}
 
 
+def torch_gpu_reference(layers=4, T=8, iters=20):
+    """R-torch-gpu: what plain HF-style PyTorch gives on the same B200 for the same path --
+    softmax/topk + per-expert index/matmul loop + index_add, ATen/cuBLAS kernels, eager launches.  Written out here
+    (not the oracle): this is a measurement of the library path the reference itself calls on the GPU
+    (core/parallel/expert_module.cpp:171-175 via torch::matmul), without its offload engine."""
+    import torch.nn.functional as F
+    H, I, E, k = 4096, 14336, 8, 2
+    dev = "cuda"
+    w = [[(torch.randn(I, H, device=dev) * 0.02).bfloat16(), (torch.randn(H, I, device=dev) * 0.02).bfloat16(),
+          (torch.randn(I, H, device=dev) * 0.02).bfloat16()] for _ in range(E * layers)]
+    gates = [(torch.randn(E, H, device=dev) * 0.02).bfloat16() for _ in range(layers)]
+    x = torch.randn(layers, T, H, device=dev).bfloat16()
+
+    def step():
+        outs = []
+        for l in range(layers):
+            h = x[l]
+            logits = F.linear(h, gates[l])
+            p = F.softmax(logits, dim=1, dtype=torch.float)
+            pw, sel = torch.topk(p, k, dim=-1)
+            pw = (pw / pw.sum(-1, keepdim=True)).to(h.dtype)
+            final = torch.zeros_like(h)
+            mask = F.one_hot(sel, num_classes=E).permute(2, 1, 0)
+            for e in range(E):
+                idx, top = torch.where(mask[e])
+                if top.numel() == 0:
+                    continue
+                w1, w2, w3 = w[l * E + e]
+                cur = h[top]
+                y = F.linear(F.silu(F.linear(cur, w1)) * F.linear(cur, w3), w2)
+                final.index_add_(0, top, y * pw[top, idx, None])
+            outs.append(final)
+        return outs
+    ms = ev_time(step, iters, warm=3)
+    return {"layers": layers, "T": T, "ms_per_layer": ms / layers, "ms_per_step_32_layers": ms / layers * 32,
+            "tokens_per_s_32_layers": T / (ms / layers * 32) * 1e3,
+            "note": "eager PyTorch (cuBLAS + ATen), torch.where forces a host sync per expert like the reference"}
+
+
 class C_void:
     def __init__(self):
         import ctypes
@@ -196,7 +235,7 @@ def offload(layers=8, steps=24, prefetch=True, resident_frac=127 / 256, skew=1.0
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="h2d,prefill,deepseek,offload")
+    ap.add_argument("--what", default="h2d,torchgpu,prefill,deepseek,offload")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     a = ap.parse_args()
     res = {}
@@ -204,6 +243,9 @@ if __name__ == "__main__":
     if "h2d" in what:
         res["h2d_pinned_gbs"] = h2d_bw()
         print("h2d", res["h2d_pinned_gbs"], flush=True)
+    if "torchgpu" in what:
+        res["torch_gpu_reference_mixtral_decode"] = torch_gpu_reference()
+        print(res["torch_gpu_reference_mixtral_decode"], flush=True)
     if "prefill" in what:
         res["mixtral_prefill_T16384_one_layer"] = prefill()
         print(res["mixtral_prefill_T16384_one_layer"], flush=True)
