@@ -97,10 +97,18 @@ __device__ float gate_dot_warp(const RouteParams& p, int t, int e) {
   return (p.router == ROUTER_MIXTRAL) ? round_to(acc, p.dtype) : acc;
 }
 // One warp, one token, experts [e0, e0+8): x is loaded once per 8-element chunk and reused for all 8 rows
-// (16-byte loads of both operands).  out[i] (i < 8) valid in every lane.
-__device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int e0, float (&out)[8]) {
+// (16-byte loads of both operands).  out[i] (i < 8) valid in every lane.  No predicates inside the loop (expert
+// indices beyond E are clamped to a valid row and their results ignored) so that all 17 loads of an iteration
+// are in flight together -- with per-expert `if`s the compiler serialised them: 64 dependent DRAM round trips.
+template <bool WF32>
+__device__ __forceinline__ void gate_dot8_impl(const RouteParams& p, int t, int e0, float (&out)[8]) {
   const int lane = threadIdx.x & 31;
   const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
+  const size_t wsz = WF32 ? 4 : 2;
+  const char* wrow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    wrow[i] = reinterpret_cast<const char*>(p.gate_w) + (size_t)min(e0 + i, p.E - 1) * p.H * wsz;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -108,28 +116,32 @@ __device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int 
   for (int h = lane * 8; h < p.H; h += 256) {
     float xf[8];
     unpack8(*reinterpret_cast<const uint4*>(x + h), p.dtype, xf);
+    float wf[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (e0 + i < p.E) {
-        float wf[8];
-        if (p.gate_dtype == DT_F32) {
-          const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)(e0 + i) * p.H + h;
-          const float4 a = *reinterpret_cast<const float4*>(w), b = *reinterpret_cast<const float4*>(w + 4);
-          wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = b.x; wf[5] = b.y; wf[6] = b.z; wf[7] = b.w;
-        } else {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)(e0 + i) * p.H + h),
-                  p.gate_dtype, wf);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
+      if (WF32) {
+        const float4 a = *reinterpret_cast<const float4*>(wrow[i] + (size_t)h * 4);
+        const float4 b = *reinterpret_cast<const float4*>(wrow[i] + (size_t)h * 4 + 16);
+        wf[i][0] = a.x; wf[i][1] = a.y; wf[i][2] = a.z; wf[i][3] = a.w;
+        wf[i][4] = b.x; wf[i][5] = b.y; wf[i][6] = b.z; wf[i][7] = b.w;
+      } else {
+        unpack8(*reinterpret_cast<const uint4*>(wrow[i] + (size_t)h * 2), p.gate_dtype, wf[i]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[i][j], acc[i]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float v = warp_sum(acc[i]);
     out[i] = (p.router == ROUTER_MIXTRAL) ? round_to(v, p.dtype) : v;
   }
+}
+__device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int e0, float (&out)[8]) {
+  if (p.gate_dtype == DT_F32) gate_dot8_impl<true>(p, t, e0, out);
+  else gate_dot8_impl<false>(p, t, e0, out);
 }
 
 // Large-T gate: one warp per token, 8 experts per pass.
@@ -591,10 +603,30 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
     s_tot[e] = run;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int e = 0; e < p.E; ++e) { s_off[e] = acc; acc += s_tot[e]; }
-    s_off[p.E] = acc;
+  if (warp == 0) {
+    // exclusive scan of the per-expert totals by one warp (E <= 256: 8 per lane)
+    int v[MAX_PL], run = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane * MAX_PL + i;
+      v[i] = e < p.E ? s_tot[e] : 0;
+      run += v[i];
+    }
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    int base = incl - run;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane * MAX_PL + i;
+      if (e < p.E) s_off[e] = base;
+      base += v[i];
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) s_off[p.E] = total;
   }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x <= p.E) {
@@ -763,20 +795,31 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     bool any = false;
+    // issue the loads of all k expert rows up front (invalid rows read row 0 and are ignored): k independent
+    // requests in flight instead of k dependent round trips
+    float yk[MAX_K][8];
+#pragma unroll
+    for (int r = 0; r < MAX_K; ++r) {
+      if (r < k) {
+        const bool ok = rows[r] >= 0;
+        if (p.ep_collect) {
+          const uint16_t* sp = ok ? src16[r] : reinterpret_cast<const uint16_t*>(p.ep.back_rows);
+          const uint4 v = *reinterpret_cast<const uint4*>(sp + h);
+          const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) yk[r][i] = Half16<DT>::to_f(vs[i]);
+        } else {
+          const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)(ok ? rows[r] : 0) * H + h);
+          const float4 a = src[0], b = src[1];
+          yk[r][0] = a.x; yk[r][1] = a.y; yk[r][2] = a.z; yk[r][3] = a.w;
+          yk[r][4] = b.x; yk[r][5] = b.y; yk[r][6] = b.z; yk[r][7] = b.w;
+        }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < MAX_K; ++r) {
       if (r < k && rows[r] >= 0) {
-        float y[8];
-        if (p.ep_collect) {
-          const uint4 v = *reinterpret_cast<const uint4*>(src16[r] + h);
-          const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = Half16<DT>::to_f(vs[i]);
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)rows[r] * H + h);
-          const float4 a = src[0], b = src[1];
-          y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
-        }
+        const float (&y)[8] = yk[r];
         const float w = ws[r];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
