@@ -795,49 +795,55 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     bool any = false;
-    // issue the loads of all k expert rows up front (invalid rows read row 0 and are ignored): k independent
-    // requests in flight instead of k dependent round trips
-    float yk[MAX_K][8];
+    // expert rows are fetched four at a time (invalid rows read row 0 and are ignored): up to 4 independent requests
+    // in flight instead of one dependent round trip per expert, at 32 registers
 #pragma unroll
-    for (int r = 0; r < MAX_K; ++r) {
-      if (r < k) {
-        const bool ok = rows[r] >= 0;
-        if (p.ep_collect) {
-          const uint16_t* sp = ok ? src16[r] : reinterpret_cast<const uint16_t*>(p.ep.back_rows);
-          const uint4 v = *reinterpret_cast<const uint4*>(sp + h);
-          const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);
+    for (int r0 = 0; r0 < MAX_K; r0 += 4) {
+      if (r0 >= k) break;
+      float yk[4][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yk[r][i] = Half16<DT>::to_f(vs[i]);
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)(ok ? rows[r] : 0) * H + h);
-          const float4 a = src[0], b = src[1];
-          yk[r][0] = a.x; yk[r][1] = a.y; yk[r][2] = a.z; yk[r][3] = a.w;
-          yk[r][4] = b.x; yk[r][5] = b.y; yk[r][6] = b.z; yk[r][7] = b.w;
-        }
-      }
-    }
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q;
+        if (r < k) {
+          const bool ok = rows[r] >= 0;
+          if (p.ep_collect) {
+            const uint16_t* sp = ok ? src16[r] : reinterpret_cast<const uint16_t*>(p.ep.back_rows);
+            const uint4 v = *reinterpret_cast<const uint4*>(sp + h);
+            const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);
 #pragma unroll
-    for (int r = 0; r < MAX_K; ++r) {
-      if (r < k && rows[r] >= 0) {
-        const float (&y)[8] = yk[r];
-        const float w = ws[r];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (p.mode == COMBINE_FP32) {
-            acc[i] = fmaf(y[i], w, acc[i]);
-          } else if (p.mode == COMBINE_MIXTRAL) {
-            // out (model dtype) * weight (model dtype) -> rounded; final += -> rounded  (mixtral.py:98-101)
-            const float prod = round_dt<DT>(__fmul_rn(round_dt<DT>(y[i]), w));
-            acc[i] = any ? round_dt<DT>(__fadd_rn(acc[i], prod)) : prod;
-          } else if (p.mode == COMBINE_DEEPSEEK) {
-            // out (model dtype) * weight (fp32) -> fp32; final(model dtype) += fp32 -> rounded (deepseek.py:125-128)
-            const float prod = __fmul_rn(round_dt<DT>(y[i]), w);
-            acc[i] = round_dt<DT>(__fadd_rn(acc[i], prod));
-          } else {  // COMBINE_SWITCH: next_states[idx] = out (switch_transformers.py:99-101)
-            acc[i] = round_dt<DT>(y[i]);
+            for (int i = 0; i < 8; ++i) yk[q][i] = Half16<DT>::to_f(vs[i]);
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(p.y + (size_t)(ok ? rows[r] : 0) * H + h);
+            const float4 a = src[0], b = src[1];
+            yk[q][0] = a.x; yk[q][1] = a.y; yk[q][2] = a.z; yk[q][3] = a.w;
+            yk[q][4] = b.x; yk[q][5] = b.y; yk[q][6] = b.z; yk[q][7] = b.w;
           }
         }
-        any = true;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q;
+        if (r < k && rows[r] >= 0) {
+          const float (&y)[8] = yk[q];
+          const float w = ws[r];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.mode == COMBINE_FP32) {
+              acc[i] = fmaf(y[i], w, acc[i]);
+            } else if (p.mode == COMBINE_MIXTRAL) {
+              // out (model dtype) * weight (model dtype) -> rounded; final += -> rounded  (mixtral.py:98-101)
+              const float prod = round_dt<DT>(__fmul_rn(round_dt<DT>(y[i]), w));
+              acc[i] = any ? round_dt<DT>(__fadd_rn(acc[i], prod)) : prod;
+            } else if (p.mode == COMBINE_DEEPSEEK) {
+              // out (model dtype) * weight (fp32) -> fp32; final(model dtype) += fp32 -> rounded (deepseek.py:125-128)
+              const float prod = __fmul_rn(round_dt<DT>(y[i]), w);
+              acc[i] = round_dt<DT>(__fadd_rn(acc[i], prod));
+            } else {  // COMBINE_SWITCH: next_states[idx] = out (switch_transformers.py:99-101)
+              acc[i] = round_dt<DT>(y[i]);
+            }
+          }
+          any = true;
+        }
       }
     }
     if (p.mode == COMBINE_SWITCH) {
