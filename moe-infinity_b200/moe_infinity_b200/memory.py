@@ -165,3 +165,47 @@ class ExpertPrefetcher:
 
     def fetch_experts_lock_cache(self, layer_id: int, expert_list: Sequence[int]):  # :36-40
         self.archer_engine.replace_cache_candidates([(layer_id, j) for j in expert_list])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# P6: the paper's "sparsity-aware" cache priority (moe_infinity/memory/expert_priority_score.py:84-172).  The
+# reference never instantiates ExpertCache (runtime/model_offload.py:83 is commented out), so this is a policy
+# *specification*; it is restated here, vectorised, for users who want to feed the C-ABI scheduler with it
+# (e.g. as `prefetch_hint` scores or to choose `replace_cache_candidates`).
+# --------------------------------------------------------------------------------------------------------------
+def priority_score_matrix(expert_freq: Dict[Tuple[int, int], float], decoder_matrix: np.ndarray, current_layer: int,
+                          total_layer: int) -> np.ndarray:
+    """score[l, e] = topo_decay(l | current_layer) * normalised activations of the running sequence * normalised
+    visit frequency, each term + 1e-6 (expert_priority_score.py:93-172).  `expert_freq` maps (expert, layer) -> visits.
+    Returns the [L, E] matrix (the reference converts entries > 0 into a list of ExpertCacheEntry)."""
+    L_, E_ = decoder_matrix.shape
+    ne = total_layer // 2                                        # :92 num_encoder_layers
+    freq = np.zeros((L_, E_), dtype=np.float64)
+    for (e, l), v in expert_freq.items():                        # :96-98
+        freq[l, e] = v
+    if freq[ne:].sum() == 0:                                     # :100-104
+        freq[ne:] = 1
+    if freq[:ne].sum() == 0:
+        freq[:ne] = 1
+    freq = freq / freq.sum() + 1e-6                              # :106
+    i = np.arange(L_, dtype=np.float64)
+    first = -1.0 / ne * i + 1 if ne else np.ones(L_)             # decay_from_first(x, L)  :8
+    last = 1.0 / (ne + 1) * (i - ne)                             # decay_from_last(x - ne, L)  :9
+    topo = np.empty(L_, dtype=np.float64)
+    enc = i < ne
+    if current_layer < ne:                                       # :115-126
+        topo[enc] = np.where(i[enc] > current_layer, first[enc], 1.0)
+        topo[~enc] = last[~enc]
+    else:                                                        # :127-138
+        topo[enc] = first[enc]
+        topo[~enc] = np.where(i[~enc] > current_layer, last[~enc], 1.0)
+    topo = np.repeat(topo[:, None], E_, axis=1)
+    topo = topo / topo.sum() + 1e-6                              # :139
+    dec = decoder_matrix.astype(np.float64).copy()               # :161-171
+    if dec.sum() == 0:
+        dec = np.ones_like(dec)
+    rows = dec.sum(axis=1, keepdims=True)
+    dec = np.where(rows == 0, 1.0, dec)
+    dec = dec / dec.sum(axis=1, keepdims=True)
+    dec = dec / dec.sum() + 1e-6
+    return topo * dec * freq                                     # :172

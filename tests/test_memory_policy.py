@@ -140,6 +140,28 @@ def test_tracer_finish_entry_and_counts():
     assert tr.trace_collection[0].sum() == 6 and tr.collection_access[0] == 1
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("current_layer", [0, 2, 3, 5])
+def test_priority_score_matches_literal_reference(current_layer):
+    import importlib
+    import ref_loader
+    ref_loader.load()
+    ps = importlib.import_module("moe_infinity.memory.expert_priority_score")
+    ent = importlib.import_module("moe_infinity.memory.expert_entry")
+    L, E = 6, 4
+    rng = np.random.default_rng(current_layer)
+    dec = rng.integers(0, 4, size=(L, E)).astype(np.float64)
+    dec[1] = 0                                           # an all-zero layer row
+    freq = {(int(e), int(l)): float(rng.integers(0, 5)) for l in range(L) for e in range(E) if rng.random() < 0.6}
+    entry = ent.ExpertTraceEntry("s", dec.copy(), 0, 0)
+    ref_list = ps.priority_score(freq, set(), set(), entry, current_layer, L)
+    ref_m = np.zeros((L, E))
+    for ce in ref_list:
+        ref_m[ce.layer_idx, ce.expert_idx] = ce.r
+    ours = M.priority_score_matrix(freq, dec, current_layer, L)
+    np.testing.assert_allclose(ours, ref_m, rtol=1e-12, atol=0)
+
+
 # ---------------------------------------------------------------- cache policy oracle: the stated rules
 def test_cache_oracle_lfu_eviction_and_tie_order():
     c = CacheOracle(num_layers=2, num_experts=4, num_slots=3)
