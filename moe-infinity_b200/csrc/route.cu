@@ -629,10 +629,12 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
     if (lane == 0) s_off[p.E] = total;
   }
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x <= p.E) {
-    p.offsets[threadIdx.x] = s_off[threadIdx.x];
-    if (threadIdx.x < p.E) p.counts[threadIdx.x] = s_tot[threadIdx.x];
-    if (p.ep_dispatch) p.ep.offsets_src[threadIdx.x] = s_off[threadIdx.x];
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e <= p.E; e += RT_THREADS) {   // E may equal the block size: stride loop, not tid <= E
+      p.offsets[e] = s_off[e];
+      if (e < p.E) p.counts[e] = s_tot[e];
+      if (p.ep_dispatch) p.ep.offsets_src[e] = s_off[e];
+    }
   }
   if (p.ep_dispatch && blockIdx.x == 0) {
     // counts ride in the extra last row of every peer segment
