@@ -202,7 +202,20 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     x_dev = torch.randn(L, T, H, device=dev).to(dtype)
     out_dev = torch.empty_like(x_dev)
     use_p2p = os.environ.get("B2M_EP_EXCHANGE", "p2p") == "p2p"
-    ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev, p2p=use_p2p)
+    ep = None
+    if use_p2p:
+        # CUDA IPC mapping of the peers' buffers can be unavailable (container/driver policy): agree on a fallback
+        ok = torch.ones(1, device=dev)
+        try:
+            ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev, p2p=True)
+        except Exception as ex:  # pragma: no cover
+            print(f"[rank {rank}] peer-to-peer exchange unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            use_p2p, ep = False, None
+    if ep is None:
+        ep = EPMoE(_EngineOps(eng), num_experts=E, hidden=H, top_k=k, T_local=T, dtype=dtype, device=dev, p2p=False)
 
     def step():
         for l in range(L):
