@@ -234,50 +234,46 @@ __device__ void route_token_warp(const RouteParams& p, int t, const float* s_in 
     }
     __syncwarp();
   }
-  // --- top-k, ties -> lowest expert index
+  // --- top-k, ties -> lowest expert index.  The k selection rounds are a real loop (winners parked in shared
+  // scratch) rather than 8x8 unrolled code: the kernel is launch/latency bound and instruction-cache cold every launch.
   uint32_t taken = 0;
-  float sel_v[MAX_K];
-  int sel_i[MAX_K];
-#pragma unroll
-  for (int j = 0; j < MAX_K; ++j) {
-    if (j < p.k) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < MAX_PL; ++i) {
-        const int e = lane + 32 * i;
-        if (e < E && !((taken >> i) & 1u) && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = e; }
-      }
-      warp_argmax(bv, bi);
-      sel_v[j] = bv;
-      sel_i[j] = bi;
-      if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
-    }
-  }
-  // --- weights
   float denom = 0.f;
+  __syncwarp();
+#pragma unroll 1
+  for (int j = 0; j < p.k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
 #pragma unroll
-  for (int j = 0; j < MAX_K; ++j)
-    if (j < p.k) denom = __fadd_rn(denom, sel_v[j]);
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < MAX_K; ++j) {
-      if (j < p.k) {
-        float w;
-        if (p.router == ROUTER_MIXTRAL) {
-          w = round_to(__fdiv_rn(sel_v[j], denom), p.dtype);                       // mixtral.py:52-54
-        } else if (p.router == ROUTER_SWITCH_TOP1) {
-          w = sel_v[j];
-        } else if (p.k > 1 && p.norm_topk_prob) {
-          w = __fdiv_rn(sel_v[j], __fadd_rn(denom, 1e-20f));                        // modeling_deepseek.py:508-510
-        } else {
-          w = __fmul_rn(sel_v[j], p.routed_scaling_factor);                        // :512
-        }
-        out_idx[j] = sel_i[j];
-        out_w[j] = w;
-      }
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane + 32 * i;
+      if (e < E && !((taken >> i) & 1u) && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = e; }
+    }
+    warp_argmax(bv, bi);
+    if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
+    denom = __fadd_rn(denom, bv);
+    if (lane == 0) {
+      s_scr[j] = bv;
+      s_scr[MAX_K + j] = __int_as_float(bi);
     }
   }
+  __syncwarp();
+  // --- weights
+  if (lane < p.k) {
+    const float sv = s_scr[lane];
+    float w;
+    if (p.router == ROUTER_MIXTRAL) {
+      w = round_to(__fdiv_rn(sv, denom), p.dtype);                       // mixtral.py:52-54
+    } else if (p.router == ROUTER_SWITCH_TOP1) {
+      w = sv;
+    } else if (p.k > 1 && p.norm_topk_prob) {
+      w = __fdiv_rn(sv, __fadd_rn(denom, 1e-20f));                        // modeling_deepseek.py:508-510
+    } else {
+      w = __fmul_rn(sv, p.routed_scaling_factor);                        // :512
+    }
+    out_idx[lane] = __float_as_int(s_scr[MAX_K + lane]);
+    out_w[lane] = w;
+  }
+  __syncwarp();
 }
 
 // lane == token: does this lane's token route to expert e ?
