@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -52,6 +53,7 @@ struct Arena {
   bool owned = false;
   ExpertShape shape;
   CUtensorMap tm_gate, tm_up, tm_down;
+  CUtensorMap tm_gate_h, tm_up_h, tm_down_h;   // 64-row boxes for the 2-CTA multicast kernels (each CTA fetches half a tile)
 };
 
 enum ExpertState : int { ST_UNREGISTERED = 0, ST_HOST = 1, ST_LOADING = 2, ST_RESIDENT = 3 };
@@ -201,21 +203,27 @@ int encode_map(b2m_ctx* c, CUtensorMap* tm, int dtype, void* base, int rank, con
   return B2M_OK;
 }
 
+int build_arena_maps_box(b2m_ctx* c, Arena* a, uint32_t box_rows, CUtensorMap* g, CUtensorMap* u, CUtensorMap* d);
 int build_arena_maps(b2m_ctx* c, Arena* a) {
+  int r = build_arena_maps_box(c, a, 128, &a->tm_gate, &a->tm_up, &a->tm_down);
+  if (r) return r;
+  return build_arena_maps_box(c, a, 64, &a->tm_gate_h, &a->tm_up_h, &a->tm_down_h);
+}
+int build_arena_maps_box(b2m_ctx* c, Arena* a, uint32_t box_rows, CUtensorMap* tg, CUtensorMap* tu, CUtensorMap* td) {
   const ExpertShape& s = a->shape;
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box[3] = {64, box_rows, 1};
   {
     const uint64_t dims[3] = {(uint64_t)s.H, (uint64_t)s.I, (uint64_t)a->nslots};
     const uint64_t str[2] = {(uint64_t)s.H * 2, (uint64_t)a->slot_bytes};
-    int r = encode_map(c, &a->tm_gate, c->cfg.dtype, a->base + s.off_gate, 3, dims, str, box);
+    int r = encode_map(c, tg, c->cfg.dtype, a->base + s.off_gate, 3, dims, str, box);
     if (r) return r;
-    r = encode_map(c, &a->tm_up, c->cfg.dtype, a->base + s.off_up, 3, dims, str, box);
+    r = encode_map(c, tu, c->cfg.dtype, a->base + s.off_up, 3, dims, str, box);
     if (r) return r;
   }
   {
     const uint64_t dims[3] = {(uint64_t)s.I, (uint64_t)s.H, (uint64_t)a->nslots};
     const uint64_t str[2] = {(uint64_t)s.I * 2, (uint64_t)a->slot_bytes};
-    int r = encode_map(c, &a->tm_down, c->cfg.dtype, a->base + s.off_down, 3, dims, str, box);
+    int r = encode_map(c, td, c->cfg.dtype, a->base + s.off_down, 3, dims, str, box);
     if (r) return r;
   }
   return B2M_OK;
@@ -764,13 +772,20 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     if (phases & 2)
       CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
   } else {
-    if (phases & 1) CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
+    // tensor-bound regime (several 128-token tiles per expert): 2-CTA clusters multicast the weight tiles (B2M_MC2=0 off)
+    static const bool mc2_on = !(getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '0');
+    const bool mc2 = mc2_on && nt == 128 && T_hint_large;
+    if (phases & 1) {
+      if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
+      else CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
+    }
     if (phases & 2) {
       // prefill-sized token tiles: pair two m-tiles of the down matrix on one token tile (dual_m) -> 1.33x the
       // FLOP per operand byte; decode keeps single tiles (finer split-K balance, HBM bound anyway)
       const bool pair = nt == 128 && s.H >= 256 && T_hint_large;
       dn.dual_m = pair ? 1 : 0;
-      CK(c, launch_grouped_gemm_tc(f.dtype, nt, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+      if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
+      else CK(c, launch_grouped_gemm_tc(f.dtype, nt, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
     }
   }
   c->stats.kernel_launches += ((phases & 1) ? 1 : 0) + ((phases & 2) ? 1 : 0);

@@ -44,6 +44,8 @@ struct GemmParams {
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
                                    const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& a0h, const CUtensorMap& a1h,
+                                       const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st);
 cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_elems, size_t offA0, size_t offA1,
                                      const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st);
 int gemm_tc_smem_bytes(int nt, bool dual);

@@ -54,24 +54,25 @@ struct TileWalker {
   const int* offs;        // smem [E+1]
   const int* slots;       // smem [E]
   int E, NTv, ksplit, kblocks, e_cur, m_step;
+  int mc, rank;   // multicast cluster size (1|2) and this CTA's rank: the CTAs of a cluster take adjacent token tiles
   __device__ __forceinline__ bool get(int tile, TileInfo& t) {
     if (tile >= tile_start[E]) return false;
     while (tile >= tile_start[e_cur + 1]) ++e_cur;
     const int e = e_cur;
     const int n_e = offs[e + 1] - offs[e];
-    const int n_tiles = (n_e + NTv - 1) / NTv;
+    const int n_tiles = ((n_e + NTv - 1) / NTv + mc - 1) / mc;   // token-tile groups (one per cluster)
     int local = tile - tile_start[e];
     const int per_m = n_tiles * ksplit;
     const int m = local / per_m;
     local -= m * per_m;
-    const int n = local / ksplit;
-    const int s = local - n * ksplit;
+    const int n = (local / ksplit) * mc + rank;
+    const int s = local % ksplit;
     const int kb_per = (kblocks + ksplit - 1) / ksplit;
     t.e = e;
     t.slot = slots[e];
     t.m0 = m * m_step;
     t.row0 = offs[e] + n * NTv;
-    t.ncols = min(NTv, n_e - n * NTv);
+    t.ncols = max(0, min(NTv, n_e - n * NTv));   // 0: ghost tile of an odd group (loads + MMA still run in lock step)
     t.kb_begin = s * kb_per;
     t.kb_end = min(kblocks, t.kb_begin + kb_per);
     return true;
@@ -85,7 +86,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-template <int NT, bool DUAL, int DT>
+template <int NT, bool DUAL, int DT, int MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -123,7 +124,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);   // with multicast operands a stage is free when every CTA of the cluster consumed it
     }
     for (int a = 0; a < Cfg::ACC_STAGES; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -148,7 +149,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     for (int e = 0; e < E; ++e) {
       tile_start[e] = acc;
       const int n_e = offs[e + 1] - offs[e];
-      if (n_e > 0 && slots[e] >= 0) acc += m_tiles * ((n_e + NT - 1) / NT) * p.ksplit;
+      if (n_e > 0 && slots[e] >= 0) acc += m_tiles * (((n_e + NT - 1) / NT + MC - 1) / MC) * p.ksplit;
     }
     tile_start[E] = acc;
   }
@@ -156,16 +157,19 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
+  if (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast targets them
 
-  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0, m_step};
+  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0, m_step, MC, crank};
   TileInfo t;
+  const int tile0 = blockIdx.x / MC, tile_stride = gridDim.x / MC;   // tiles are dealt to clusters
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+      for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA0 = stage_base + stage * Cfg::STAGE_BYTES;
@@ -175,8 +179,20 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           // decode: weights are streamed exactly once -> evict-first.  Several n-tiles per expert (prefill): the same
           // weight tile is re-read by every n-tile -> keep it in L2.  Tokens are re-read by every m-tile: keep.
           const uint64_t wh = (offs[t.e + 1] - offs[t.e] <= NT) ? CACHE_EVICT_FIRST : CACHE_EVICT_NORMAL;
-          tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, wh);
-          if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0 + (p.dual_m ? BLOCK_M : 0), t.slot, wh);
+          if (MC == 1) {
+            tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, wh);
+            if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0 + (p.dual_m ? BLOCK_M : 0), t.slot, wh);
+          } else {
+            // 2-CTA multicast: the cluster's CTAs work on the same weight tiles and adjacent token tiles; each CTA fetches
+            // HALF of every weight tile (64 rows; tmA* carry 64-row boxes) and multicasts it into both CTAs' stages, so
+            // a CTA pulls 16+16 KB instead of 32+16 KB per k-block from L2 (the kernel is L2->SM operand-bandwidth bound)
+            const int half = crank * (BLOCK_M / 2);          // rows this CTA fetches
+            const int hoff = crank * (A_TILE_BYTES / 2);     // where they sit inside the 128-row stage tile
+            tma_load_3d_mc(&tmA0, &full_bar[stage], sA0 + hoff, kb * BLOCK_K, t.m0 + half, t.slot, (uint16_t)0x3, wh);
+            if (DUAL)
+              tma_load_3d_mc(&tmA1, &full_bar[stage], sA1 + hoff, kb * BLOCK_K,
+                             t.m0 + (p.dual_m ? BLOCK_M : 0) + half, t.slot, (uint16_t)0x3, wh);
+          }
           tma_load_2d(&tmB, &full_bar[stage], sB, kb * BLOCK_K, t.row0, CACHE_EVICT_LAST);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -189,7 +205,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+    for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * Cfg::ACC_COLS;
@@ -210,7 +226,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             tc_mma_f16(d0, da0 + koff, db + koff, idesc, accum);
             if (DUAL) tc_mma_f16(d0 + NT, da1 + koff, db + koff, idesc, accum);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (MC == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          else tc_commit_mc(&empty_bar[stage], (uint16_t)0x3);   // ... in both CTAs: the peer multicasts into it too
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -225,7 +242,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     const int r = q * 32 + lane;         // weight row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; walker.get(tile, t); tile += gridDim.x) {
+    for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
@@ -287,6 +304,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   // ---- teardown ---------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast / commit into its shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -349,18 +367,19 @@ __global__ void grouped_gemm_simt_kernel(const uint16_t* __restrict__ arena, siz
 // --------------------------------------------------------------------------------------
 // host launchers
 // --------------------------------------------------------------------------------------
-template <int NT, bool DUAL, int DT>
+template <int NT, bool DUAL, int DT, int MC = 1>
 static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
                              int grid, cudaStream_t st) {
   using Cfg = GemmCfg<NT, DUAL>;
-  auto kern = grouped_gemm_tc_kernel<NT, DUAL, DT>;
+  auto kern = grouped_gemm_tc_kernel<NT, DUAL, DT, MC>;
   static bool attr_done = false;   // per-instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  return launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, st, a0, a1, b, p);
+  if (MC > 1) grid -= grid % MC;
+  return launch_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, a0, a1, b, p);
 }
 
 template <int DT>
@@ -378,6 +397,17 @@ static cudaError_t dispatch_nt(int nt, bool dual, const CUtensorMap& a0, const C
       return cudaErrorInvalidValue;
   }
 #undef B2M_CASE
+}
+
+// 2-CTA multicast variant (prefill: NT = 128, several token tiles per expert); a0/a1 must be the 64-row-box maps
+cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& a0h, const CUtensorMap& a1h,
+                                       const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st) {
+  if (p.E > MAX_E) return cudaErrorInvalidValue;
+  if (dtype == DT_BF16)
+    return dual ? launch_tc<128, true, DT_BF16, 2>(a0h, a1h, b, p, grid, st) : launch_tc<128, false, DT_BF16, 2>(a0h, a1h, b, p, grid, st);
+  if (dtype == DT_F16)
+    return dual ? launch_tc<128, true, DT_F16, 2>(a0h, a1h, b, p, grid, st) : launch_tc<128, false, DT_F16, 2>(a0h, a1h, b, p, grid, st);
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
