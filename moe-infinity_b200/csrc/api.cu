@@ -33,7 +33,7 @@ using namespace b2m;
 
 namespace {
 
-constexpr int NT_LIST[4] = {16, 32, 64, 128};
+constexpr int NT_LIST[5] = {16, 32, 64, 128, 256};
 constexpr int EVENT_RING = 64;
 constexpr int STAGE_RING = 8;
 
@@ -118,7 +118,7 @@ struct b2m_ctx {
   float* d_y_s = nullptr;
   int* h_counts = nullptr;  // pinned [E+1]
   bool last_counts_valid = false;
-  CUtensorMap tm_xp[4], tm_hmid[4], tm_hmid_s[4];
+  CUtensorMap tm_xp[5], tm_hmid[5], tm_hmid_s[5];
 
   // streams / events
   cudaStream_t fetch_stream = nullptr, prefetch_stream = nullptr;
@@ -236,12 +236,19 @@ int build_act_map(b2m_ctx* c, CUtensorMap* tm, void* base, int K, int rows, int 
   return encode_map(c, tm, c->cfg.dtype, base, 2, dims, str, box);
 }
 
-int nt_index(int nt) { return nt == 16 ? 0 : nt == 32 ? 1 : nt == 64 ? 2 : 3; }
+int nt_index(int nt) { return nt == 16 ? 0 : nt == 32 ? 1 : nt == 64 ? 2 : nt == 128 ? 3 : 4; }
 
 int pick_nt(int T) {
   for (int i = 0; i < 4; ++i)
     if (T <= NT_LIST[i]) return NT_LIST[i];
   return 128;
+}
+// tensor-bound regime: 256-token tiles when the average expert sees at least two of them (B2M_NT256=0 disables)
+int pick_nt_model(const b2m_config& f, int T) {
+  static const bool on = !(getenv("B2M_NT256") && getenv("B2M_NT256")[0] == '0');
+  const long long avg = (long long)T * f.top_k / f.num_experts;
+  if (on && avg >= 512 && f.hidden >= 256) return 256;
+  return pick_nt(T);
 }
 
 // split-K for the down projection: enough tiles for ~6 waves, every split non-empty and >= 4 k-blocks
@@ -404,7 +411,7 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
 
 void plan_gemm(b2m_ctx* c, int T) {
   c->cur_T = T;
-  c->cur_nt = pick_nt(T);
+  c->cur_nt = pick_nt_model(c->cfg, T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt);
 }
 
@@ -544,7 +551,7 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
     CKC(cudaMemset(c->d_hmid_s, 0, (size_t)T * cfg->shared_inter * 2));
     CKC(cudaMalloc((void**)&c->d_y_s, (size_t)T * H * sizeof(float)));
   }
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     r = build_act_map(c, &c->tm_xp[i], c->d_xp, H, (int)R, NT_LIST[i]);
     if (!r) r = build_act_map(c, &c->tm_hmid[i], c->d_hmid, I, (int)R, NT_LIST[i]);
     if (!r && cfg->shared_inter > 0) r = build_act_map(c, &c->tm_hmid_s[i], c->d_hmid_s, cfg->shared_inter, T, NT_LIST[i]);
@@ -773,7 +780,9 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
   } else {
     // tensor-bound regime (several 128-token tiles per expert): 2-CTA clusters multicast the weight tiles (B2M_MC2=0 off)
-    static const bool mc2_on = !(getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '0');
+    // measured: no gain on B200 (L2 already de-duplicates the two CTAs' requests; the SM ingest port is the limit), so
+    // the variant is opt-in: B2M_MC2=1
+    static const bool mc2_on = getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '1';
     const bool mc2 = mc2_on && nt == 128 && T_hint_large;
     if (phases & 1) {
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
@@ -782,7 +791,7 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     if (phases & 2) {
       // prefill-sized token tiles: pair two m-tiles of the down matrix on one token tile (dual_m) -> 1.33x the
       // FLOP per operand byte; decode keeps single tiles (finer split-K balance, HBM bound anyway)
-      const bool pair = nt == 128 && s.H >= 256 && T_hint_large;
+      const bool pair = nt >= 128 && s.H >= 256 && T_hint_large;
       dn.dual_m = pair ? 1 : 0;
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));

@@ -34,7 +34,12 @@ struct GemmCfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
   static constexpr int ACC_COLS = (DUAL ? 2 : 1) * NT;
-  static constexpr int ACC_STAGES = 2;
+  // NT=256 with two accumulators fills the 512 TMEM columns with ONE stage (no MMA/epilogue overlap); it is used in the
+  // tensor-bound regime because it halves the weight bytes an SM has to ingest per FLOP (the SM ingest port, ~64 B/clk,
+  // is what limited the 128-token tiles to ~65 % tensor-pipe activity).  Eight epilogue warps shorten the bubble.
+  static constexpr int ACC_STAGES = (ACC_COLS * 2 <= 512) ? 2 : 1;
+  static constexpr int EPI_WARPS = (NT >= 256) ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
@@ -87,7 +92,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 }
 
 template <int NT, bool DUAL, int DT, int MC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<NT, DUAL>::THREADS), 1)
 grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<NT, DUAL>;
@@ -128,7 +133,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
     for (int a = 0; a < Cfg::ACC_STAGES; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -140,8 +145,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
   } else {
-    for (int i = threadIdx.x; i <= E; i += GEMM_THREADS) offs[i] = p.offsets[i];
-    for (int i = threadIdx.x; i < E; i += GEMM_THREADS) slots[i] = p.slot_of[i];
+    for (int i = threadIdx.x; i <= E; i += Cfg::THREADS) offs[i] = p.offsets[i];
+    for (int i = threadIdx.x; i < E; i += Cfg::THREADS) slots[i] = p.slot_of[i];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -239,6 +244,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int cgrp = (warp - 4) >> 2;    // with 8 epilogue warps two warps share a quadrant and alternate 16-column chunks
     const int r = q * 32 + lane;         // weight row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -248,7 +254,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
       const int m = t.m0 + r;
       const bool row_ok = m < p.M;
-      for (int c0 = 0; c0 < t.ncols; c0 += 16) {   // warp-uniform trip count
+      for (int c0 = cgrp * 16; c0 < t.ncols; c0 += 16 * (Cfg::EPI_WARPS / 4)) {   // warp-uniform trip count
         uint32_t vg[16], vu[16];
         tmem_ld_x16(taddr + c0, vg);
         if (DUAL) tmem_ld_x16(taddr + NT + c0, vu);
@@ -379,7 +385,7 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr_done = true;
   }
   if (MC > 1) grid -= grid % MC;
-  return launch_cluster(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, a0, a1, b, p);
+  return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, a0, a1, b, p);
 }
 
 template <int DT>
@@ -393,6 +399,7 @@ static cudaError_t dispatch_nt(int nt, bool dual, const CUtensorMap& a0, const C
     B2M_CASE(32)
     B2M_CASE(64)
     B2M_CASE(128)
+    B2M_CASE(256)
     default:
       return cudaErrorInvalidValue;
   }
@@ -438,6 +445,7 @@ int gemm_tc_smem_bytes(int nt, bool dual) {
     case 32: return dual ? GemmCfg<32, true>::SMEM_BYTES : GemmCfg<32, false>::SMEM_BYTES;
     case 64: return dual ? GemmCfg<64, true>::SMEM_BYTES : GemmCfg<64, false>::SMEM_BYTES;
     case 128: return dual ? GemmCfg<128, true>::SMEM_BYTES : GemmCfg<128, false>::SMEM_BYTES;
+    case 256: return dual ? GemmCfg<256, true>::SMEM_BYTES : GemmCfg<256, false>::SMEM_BYTES;
   }
   return -1;
 }
