@@ -131,7 +131,7 @@ struct b2m_ctx {
   std::vector<int> inflight;
   std::vector<int> last_active;
 
-  int cur_ksplit = 1, cur_nt = 16, cur_T = 0;
+  int cur_ksplit = 1, cur_nt = 16, cur_nt_dn = 16, cur_T = 0;   // token-tile widths of the up (K3) and down (K4) GEMMs
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
@@ -243,7 +243,10 @@ int pick_nt(int T) {
     if (T <= NT_LIST[i]) return NT_LIST[i];
   return 128;
 }
-// tensor-bound regime: 256-token tiles when the average expert sees at least two of them (B2M_NT256=0 disables)
+// tensor-bound regime, DOWN projection only: 256-token tiles when the average expert sees at least two of them
+// (B2M_NT256=0 disables).  Measured (profiles/r01f_prefill.txt): down 3.40 -> 2.65 ms (1.45 PFLOP/s); the gate/up GEMM
+// gets SLOWER with 256-token tiles (7.2 -> 8.1 ms) because its two 256-column accumulators leave no second TMEM stage and
+// the SwiGLU epilogue then serialises with the MMAs, so it keeps 128-token double-buffered tiles.
 int pick_nt_model(const b2m_config& f, int T) {
   static const bool on = !(getenv("B2M_NT256") && getenv("B2M_NT256")[0] == '0');
   const long long avg = (long long)T * f.top_k / f.num_experts;
@@ -411,8 +414,9 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
 
 void plan_gemm(b2m_ctx* c, int T) {
   c->cur_T = T;
-  c->cur_nt = pick_nt_model(c->cfg, T);
-  c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt);
+  c->cur_nt = pick_nt(T);
+  c->cur_nt_dn = pick_nt_model(c->cfg, T);
+  c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
 }
 
 int route_launch_count(int T, int router, bool fused_gate) {
@@ -761,7 +765,7 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
 
 static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, const CUtensorMap& tm_b_up,
                                const CUtensorMap& tm_b_down, const void* b_up, int ldb_up, const void* b_down,
-                               void* hmid, float* y, int nt, int ksplit, cudaStream_t st, int phases = 3) {
+                               void* hmid, float* y, int nt, int nt_dn, int ksplit, cudaStream_t st, int phases = 3) {
   const bool T_hint_large = c->cur_T > 128;   // several token tiles per expert are likely: tensor-bound regime
   const b2m_config& f = c->cfg;
   const ExpertShape& s = a.shape;
@@ -791,10 +795,10 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     if (phases & 2) {
       // prefill-sized token tiles: pair two m-tiles of the down matrix on one token tile (dual_m) -> 1.33x the
       // FLOP per operand byte; decode keeps single tiles (finer split-K balance, HBM bound anyway)
-      const bool pair = nt >= 128 && s.H >= 256 && T_hint_large;
+      const bool pair = nt_dn >= 128 && s.H >= 256 && T_hint_large;
       dn.dual_m = pair ? 1 : 0;
-      if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
-      else CK(c, launch_grouped_gemm_tc(f.dtype, nt, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+      if (mc2 && nt_dn == 128) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
+      else CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
     }
   }
   c->stats.kernel_launches += ((phases & 1) ? 1 : 0) + ((phases & 2) ? 1 : 0);
@@ -839,12 +843,12 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   base.slot_of = c->d_slot_of + (size_t)layer * E;
   base.E = E;
   base.single_n = -1;
-  const int ni = nt_index(c->cur_nt);
+  const int ni = nt_index(c->cur_nt), nd = nt_index(c->cur_nt_dn);
   if (!do_residency) {
     r = upload_row_if_dirty(c, layer, st);
     if (r) return r;
-    return launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid,
-                               c->d_hmid, c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
+    return launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[nd], c->d_xp, c->cfg.hidden, c->d_hmid,
+                               c->d_hmid, c->d_y, c->cur_nt, c->cur_nt_dn, c->cur_ksplit, st, phases);
   }
   for (int id : active)
     if (c->experts[id].state == ST_UNREGISTERED)
@@ -900,8 +904,8 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
       CK(c, cudaMemcpyAsync(c->d_slot_of + (size_t)layer * E, stage, sizeof(int) * E, cudaMemcpyHostToDevice, st));
       c->row_dirty[layer] = 1;   // the true mapping is re-uploaded by the next whole-wave call
     }
-    r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[ni], c->d_xp, c->cfg.hidden, c->d_hmid,
-                            c->d_hmid, c->d_y, c->cur_nt, c->cur_ksplit, st, phases);
+    r = launch_expert_gemms(c, c->arena, base, c->tm_xp[ni], c->tm_hmid[nd], c->d_xp, c->cfg.hidden, c->d_hmid,
+                            c->d_hmid, c->d_y, c->cur_nt, c->cur_nt_dn, c->cur_ksplit, st, phases);
     if (r) return r;
     if (on_demand) {
       int evi;
@@ -932,7 +936,7 @@ static int run_shared(b2m_ctx* c, int layer, const void* x, int T, cudaStream_t 
   base.single_n = T;
   base.single_slot = layer;
   return launch_expert_gemms(c, c->shared_arena, base, tm_x, c->tm_hmid_s[nt_index(nt)], x, c->cfg.hidden, c->d_hmid_s,
-                             c->d_hmid_s, c->d_y_s, nt, ks, st);
+                             c->d_hmid_s, c->d_y_s, nt, nt, ks, st);
 }
 
 static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream, bool ep_collect);
@@ -1126,7 +1130,7 @@ int b2m_ep_regroup(b2m_ctx* c, int nranks, int rank, int cap, int T_total, const
   c->ep_inline = p.inline_counts;
   // plan the local GEMMs for the rows this rank may receive
   c->cur_T = T_total;
-  c->cur_nt = pick_nt(T_total);
+  c->cur_nt = c->cur_nt_dn = pick_nt(T_total);
   c->cur_ksplit = pick_ksplit(c, T_total, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts / nranks, c->cfg.top_k, c->cur_nt);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)nranks * cap * c->cfg.hidden; }
   CK(c, launch_ep_regroup(p, (cudaStream_t)stream));
@@ -1262,7 +1266,7 @@ int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {
   if (T_total < 1 || T_total > c->cap_T) return fail(c, B2M_EINVAL, "T_total=%d exceeds workspace capacity %d", T_total, c->cap_T);
   EpParams p = ep_p2p_params(c);
   c->cur_T = T_total;
-  c->cur_nt = pick_nt(T_total);
+  c->cur_nt = c->cur_nt_dn = pick_nt(T_total);
   c->cur_ksplit = pick_ksplit(c, T_total, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts / c->p2p.nranks, c->cfg.top_k, c->cur_nt);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)c->p2p.nranks * c->p2p.cap * c->cfg.hidden; }
   CK(c, launch_ep_regroup(p, (cudaStream_t)stream));
