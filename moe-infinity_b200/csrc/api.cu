@@ -414,8 +414,10 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
 
 void plan_gemm(b2m_ctx* c, int T) {
   c->cur_T = T;
-  c->cur_nt = pick_nt(T);
   c->cur_nt_dn = pick_nt_model(c->cfg, T);
+  // B2M_NT256_UP=1: 256-token tiles for the gate/up GEMM too (experiment; needs the MUFU epilogue to pay off)
+  static const bool up256 = getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '1';
+  c->cur_nt = (up256 && c->cur_nt_dn == 256) ? 256 : pick_nt(T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
 }
 
