@@ -244,9 +244,9 @@ int pick_nt(int T) {
   return 128;
 }
 // tensor-bound regime, DOWN projection only: 256-token tiles when the average expert sees at least two of them
-// (B2M_NT256=0 disables).  Measured (profiles/r01f_prefill.txt): down 3.40 -> 2.65 ms (1.45 PFLOP/s); the gate/up GEMM
-// gets SLOWER with 256-token tiles (7.2 -> 8.1 ms) because its two 256-column accumulators leave no second TMEM stage and
-// the SwiGLU epilogue then serialises with the MMAs, so it keeps 128-token double-buffered tiles.
+// (B2M_NT256=0 disables).  Measured (profiles/r01f_prefill.txt): down 3.40 -> 2.65 ms (1.45 PFLOP/s, tensor pipe 92 %).
+// The gate/up GEMM's two 256-column accumulators leave no second TMEM stage, so its SwiGLU epilogue serialises with the
+// MMAs: with the precise expf/div epilogue it got slower (7.2 -> 8.1 ms), with the MUFU epilogue faster (-> 6.6 ms).
 int pick_nt_model(const b2m_config& f, int T) {
   static const bool on = !(getenv("B2M_NT256") && getenv("B2M_NT256")[0] == '0');
   const long long avg = (long long)T * f.top_k / f.num_experts;
@@ -415,8 +415,9 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
 void plan_gemm(b2m_ctx* c, int T) {
   c->cur_T = T;
   c->cur_nt_dn = pick_nt_model(c->cfg, T);
-  // B2M_NT256_UP=1: 256-token tiles for the gate/up GEMM too (experiment; needs the MUFU epilogue to pay off)
-  static const bool up256 = getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '1';
+  // gate/up GEMM: 256-token tiles too (single TMEM stage, MUFU SiLU epilogue): 7.37 -> 6.61 ms at T=16384
+  // (profiles/r01f_prefill.txt); B2M_NT256_UP=0 keeps the 128-token double-buffered tiles
+  static const bool up256 = !(getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '0');
   c->cur_nt = (up256 && c->cur_nt_dn == 256) ? 256 : pick_nt(T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
 }
