@@ -26,6 +26,9 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int GEMM_THREADS = 256;
 constexpr int MAX_E = 256;
 constexpr int SMEM_BUDGET = 216 * 1024;
+#ifndef B2M_EPI_WARPS_256
+#define B2M_EPI_WARPS_256 16   // epilogue warps of the 256-token-tile instantiations (4 per TMEM lane quadrant; measured 8: 6.6 ms, 16: 5.5-6.0 ms, 24: same)
+#endif
 
 template <int NT, bool DUAL>
 struct GemmCfg {
@@ -38,7 +41,7 @@ struct GemmCfg {
   // tensor-bound regime because it halves the weight bytes an SM has to ingest per FLOP (the SM ingest port, ~64 B/clk,
   // is what limited the 128-token tiles to ~65 % tensor-pipe activity).  Eight epilogue warps shorten the bubble.
   static constexpr int ACC_STAGES = (ACC_COLS * 2 <= 512) ? 2 : 1;
-  static constexpr int EPI_WARPS = (NT >= 256) ? 8 : 4;
+  static constexpr int EPI_WARPS = (NT >= 256) ? B2M_EPI_WARPS_256 : 4;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
