@@ -144,22 +144,56 @@ __device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int 
   else gate_dot8_impl<false>(p, t, e0, out);
 }
 
-// Large-T gate: one warp per token, 8 experts per pass.
+// Large-T gate (prefill): one warp per token, 8 experts per pass.  The token row is the HBM stream: eight 16-byte loads
+// of x are issued back to back per lane (MLP), the gate rows (E*H elements, cache resident) are read as they are used.
 __global__ void __launch_bounds__(256) gate_logits_kernel(const RouteParams p) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= p.T) return;
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
+  const bool wf32 = p.gate_dtype == DT_F32;
   for (int e0 = 0; e0 < p.E; e0 += 8) {
-    float v[8];
-    gate_dot8_warp(p, t, e0, v);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int hb = lane * 8; hb < p.H; hb += 256 * 8) {
+      uint4 xv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int h = hb + q * 256;
+        xv[q] = h < p.H ? *reinterpret_cast<const uint4*>(x + h) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int h = hb + q * 256;
+        if (h >= p.H) break;
+        float xf[8];
+        unpack8(xv[q], p.dtype, xf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const size_t row = (size_t)min(e0 + i, p.E - 1) * p.H + h;
+          float wf[8];
+          if (wf32) {
+            const float* w = reinterpret_cast<const float*>(p.gate_w) + row;
+            const float4 a = *reinterpret_cast<const float4*>(w), c = *reinterpret_cast<const float4*>(w + 4);
+            wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = c.x; wf[5] = c.y; wf[6] = c.z; wf[7] = c.w;
+          } else {
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + row), p.gate_dtype, wf);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      float v = warp_sum(acc[i]);
       if (lane == 0 && e0 + i < p.E) {
         if (p.router == ROUTER_MIXTRAL)
           reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e0 + i] =
-              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v[i]) : Half16<DT_F16>::from_f(v[i]);
+              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v) : Half16<DT_F16>::from_f(v);
         else
-          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v[i];
+          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v;
       }
     }
   }
@@ -366,8 +400,8 @@ __global__ void __launch_bounds__(RT_THREADS) route_topk_kernel(const RouteParam
   __shared__ float s_logits[RT_WARPS][MAX_PL * 32];
   __shared__ float s_scr[RT_WARPS][MAX_PL * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tb = blockIdx.x * TOK_PER_BLOCK;
-  for (int i = warp; i < TOK_PER_BLOCK; i += RT_WARPS) {
+  const int tb = blockIdx.x * CHUNK;   // one 32-token ranking chunk per block: T/32 blocks keep every SM busy
+  for (int i = warp; i < CHUNK; i += RT_WARPS) {
     const int t = tb + i;
     if (t >= p.T) break;
     // large-T path: logits/scores always come from memory (caller-supplied, or written by gate_logits_kernel)
@@ -393,9 +427,7 @@ __global__ void __launch_bounds__(RT_THREADS) route_topk_kernel(const RouteParam
   __threadfence_block();
   __syncthreads();
   // per-chunk counts
-  const int chunk = blockIdx.x * RT_WARPS + warp;
-  const int t0 = chunk * CHUNK;
-  if (t0 < p.T) chunk_count_warp(p.topk_idx, t0, p.T, p.k, p.E, p.chunk_counts + (size_t)chunk * p.E);
+  if (warp == 0 && tb < p.T) chunk_count_warp(p.topk_idx, tb, p.T, p.k, p.E, p.chunk_counts + (size_t)blockIdx.x * p.E);
 }
 
 // Switch capacity (cumsum priority <= capacity, per batch row), then per-chunk counts.  One block per batch row.
@@ -704,7 +736,7 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
     q.logits_are_scores = 0;
     q.logits_out = nullptr;
   }
-  route_topk_kernel<<<nblocks, RT_THREADS, 0, st>>>(q);
+  route_topk_kernel<<<nchunks, RT_THREADS, 0, st>>>(q);
   if (p.router == ROUTER_SWITCH_TOP1) {
     switch_capacity_kernel<<<p.T / p.seq_len, RT_THREADS, 0, st>>>(p);
     chunk_count_kernel<<<nblocks, RT_THREADS, 0, st>>>(p);
