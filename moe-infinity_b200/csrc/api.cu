@@ -122,6 +122,9 @@ struct b2m_ctx {
 
   // streams / events
   cudaStream_t fetch_stream = nullptr, prefetch_stream = nullptr;
+  cudaStream_t shared_stream = nullptr;          // DeepSeek shared experts run here, concurrently with the routing kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool shared_in_flight = false;                 // b2m_moe_forward already launched this call's shared-expert GEMMs
   cudaEvent_t ev_ring[EVENT_RING] = {nullptr};
   int ev_pos = 0;
 
@@ -569,6 +572,9 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaStreamCreateWithPriority(&c->fetch_stream, cudaStreamNonBlocking, hi));
   CKC(cudaStreamCreateWithPriority(&c->prefetch_stream, cudaStreamNonBlocking, lo));
   for (int i = 0; i < EVENT_RING; ++i) CKC(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+  CKC(cudaStreamCreateWithFlags(&c->shared_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->stats.slots = (uint64_t)nslots;
   c->stats.slot_bytes = shape.bytes;
 #undef CKC
@@ -593,6 +599,9 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
   if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
   if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
+  if (c->shared_stream) cudaStreamDestroy(c->shared_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (int i = 0; i < EVENT_RING; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
   delete c;
   return B2M_OK;
@@ -768,8 +777,10 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
 
 static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, const CUtensorMap& tm_b_up,
                                const CUtensorMap& tm_b_down, const void* b_up, int ldb_up, const void* b_down,
-                               void* hmid, float* y, int nt, int nt_dn, int ksplit, cudaStream_t st, int phases = 3) {
-  const bool T_hint_large = c->cur_T > 128;   // several token tiles per expert are likely: tensor-bound regime
+                               void* hmid, float* y, int nt, int nt_dn, int ksplit, cudaStream_t st, int phases = 3,
+                               int T_hint = -1) {
+  // several token tiles per expert are likely: tensor-bound regime
+  const bool T_hint_large = (T_hint >= 0 ? T_hint : c->cur_T) > 128;
   const b2m_config& f = c->cfg;
   const ExpertShape& s = a.shape;
   GemmParams up = base;
@@ -939,7 +950,7 @@ static int run_shared(b2m_ctx* c, int layer, const void* x, int T, cudaStream_t 
   base.single_n = T;
   base.single_slot = layer;
   return launch_expert_gemms(c, c->shared_arena, base, tm_x, c->tm_hmid_s[nt_index(nt)], x, c->cfg.hidden, c->d_hmid_s,
-                             c->d_hmid_s, c->d_y_s, nt, nt, ks, st);
+                             c->d_hmid_s, c->d_y_s, nt, nt, ks, st, 3, T);
 }
 
 static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream, bool ep_collect);
@@ -965,8 +976,14 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   else if (f.numerics == B2M_NUMERICS_FP32) p.mode = COMBINE_FP32;
   else p.mode = f.router == B2M_ROUTER_MIXTRAL ? COMBINE_MIXTRAL : COMBINE_DEEPSEEK;
   if (f.shared_inter > 0) {
-    r = run_shared(c, layer, x, T, st);
-    if (r) return r;
+    if (c->shared_in_flight) {
+      // launched by b2m_moe_forward on the side stream at the start of the call: join it
+      CK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+      c->shared_in_flight = false;
+    } else {
+      r = run_shared(c, layer, x, T, st);
+      if (r) return r;
+    }
     p.y_shared = c->d_y_s;
   }
   if (ep_collect) {
@@ -980,10 +997,25 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
 
 int b2m_moe_forward(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T,
                     int seq_len, void* out, void* stream) {
-  int r = b2m_route(c, layer, x, router_in, kind, in_dtype, T, seq_len, stream);
+  int r = check_layer(c, layer);
   if (r) return r;
-  r = b2m_run_experts(c, layer, T, stream);
-  if (r) return r;
+  if (c->cfg.shared_inter > 0 && T > 0 && T <= c->cap_T && x) {
+    // the shared experts (deepseek.py:133-136) depend on x only: fork them onto a side stream so that their two GEMM
+    // launches overlap the gate / top-k / permute kernels of the routed path; b2m_combine joins
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(c, cudaEventRecord(c->ev_fork, st));
+    CK(c, cudaStreamWaitEvent(c->shared_stream, c->ev_fork, 0));
+    r = run_shared(c, layer, x, T, c->shared_stream);
+    if (r) return r;
+    CK(c, cudaEventRecord(c->ev_join, c->shared_stream));
+    c->shared_in_flight = true;
+  }
+  r = b2m_route(c, layer, x, router_in, kind, in_dtype, T, seq_len, stream);
+  if (!r) r = b2m_run_experts(c, layer, T, stream);
+  if (r) {
+    if (c->shared_in_flight) { cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join, 0); c->shared_in_flight = false; }
+    return r;
+  }
   return b2m_combine(c, layer, x, T, out, stream);
 }
 
