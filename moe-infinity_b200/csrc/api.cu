@@ -246,14 +246,15 @@ int pick_nt(int T) {
     if (T <= NT_LIST[i]) return NT_LIST[i];
   return 128;
 }
-// tensor-bound regime, DOWN projection only: 256-token tiles when the average expert sees at least two of them
+// tensor-bound regime: 256-token tiles when the average expert sees at least one full tile
 // (B2M_NT256=0 disables).  Measured (profiles/r01f_prefill.txt): down 3.40 -> 2.65 ms (1.45 PFLOP/s, tensor pipe 92 %).
 // The gate/up GEMM's two 256-column accumulators leave no second TMEM stage, so its SwiGLU epilogue serialises with the
 // MMAs: with the precise expf/div epilogue it got slower (7.2 -> 8.1 ms), with the MUFU epilogue faster (-> 6.6 ms).
 int pick_nt_model(const b2m_config& f, int T) {
   static const bool on = !(getenv("B2M_NT256") && getenv("B2M_NT256")[0] == '0');
   const long long avg = (long long)T * f.top_k / f.num_experts;
-  if (on && avg >= 512 && f.hidden >= 256) return 256;
+  static const long long min_avg = getenv("B2M_NT256_MIN_AVG") ? atoll(getenv("B2M_NT256_MIN_AVG")) : 256;   // DeepSeek-V2-Lite prefill (avg 384): 27.6 -> 25.1 ms
+  if (on && avg >= min_avg && f.hidden >= 256) return 256;
   return pick_nt(T);
 }
 

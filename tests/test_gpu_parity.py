@@ -247,7 +247,7 @@ def test_switch_capacity_drop(lib_built):
     hidden_close(out, ref, None, c["dtype"], "switch capacity")
 
 
-@pytest.mark.parametrize("T", [1, 7, 33, 300, 1000, 2100])   # 2100: 256-token tiles (avg >= 512 tokens per expert)
+@pytest.mark.parametrize("T", [1, 7, 33, 300, 1000, 1100, 2100])   # >= 1024: 256-token tiles (avg >= 256 tokens per expert)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_mixtral_random_vs_oracle(T, dtype, lib_built):
     """Seeded random case checked against the CPU oracle (multi-CTA routing path for T > 256)."""
