@@ -812,6 +812,9 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       // FLOP per operand byte; decode keeps single tiles (finer split-K balance, HBM bound anyway)
       const bool pair = nt_dn >= 128 && s.H >= 256 && T_hint_large;
       dn.dual_m = pair ? 1 : 0;
+      // decode: let the down projection start under the tail of the gate/up GEMM and prefetch its first weight tiles
+      static const bool early_a = getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '1';
+      dn.early_a = (early_a && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
       if (mc2 && nt_dn == 128) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
     }

@@ -197,7 +197,7 @@ inline bool pdl_enabled() {
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                  int cluster_x, Args&&... args) {
+                                  int cluster_x, bool force_pdl, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -205,7 +205,7 @@ inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block,
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled() || force_pdl) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -223,7 +223,7 @@ inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block,
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  return launch_cluster(kern, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
+  return launch_cluster(kern, grid, block, smem, st, 1, false, static_cast<Args&&>(args)...);
 }
 
 }  // namespace b2m

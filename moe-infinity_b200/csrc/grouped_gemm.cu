@@ -154,7 +154,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  pdl_wait();   // everything above is on-chip; from here on we touch memory the previous kernel produced
+  // everything above is on-chip; from here on we touch memory earlier kernels produced.  In early_a mode (down projection
+  // launched with a programmatic edge behind the gate/up GEMM) only the token-tile loads depend on the predecessor: the
+  // producer prefetches weight tiles first and waits later; the routing tables read below are older than the predecessor.
+  if (!p.early_a) pdl_wait();
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
   } else {
@@ -187,6 +190,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool waited = !p.early_a;
+      int npend = 0, pend_stage[Cfg::STAGES], pend_kb[Cfg::STAGES], pend_row[Cfg::STAGES];
       for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -211,13 +216,33 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
               tma_load_3d_mc(&tmA1, &full_bar[stage], sA1 + hoff, kb * BLOCK_K,
                              t.m0 + (p.dual_m ? BLOCK_M : 0) + half, t.slot, (uint16_t)0x3, wh);
           }
-          tma_load_2d(&tmB, &full_bar[stage], sB, kb * BLOCK_K, t.row0, CACHE_EVICT_LAST);
+          if (!waited) {
+            // weight tiles of the first pipeline fill are in flight before the predecessor has finished; their token
+            // tiles follow once it has
+            pend_stage[npend] = stage; pend_kb[npend] = kb; pend_row[npend] = t.row0;
+            if (++npend == Cfg::STAGES) {
+              pdl_wait();
+              for (int i = 0; i < npend; ++i)
+                tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
+                            pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
+              waited = true;
+            }
+          } else {
+            tma_load_2d(&tmB, &full_bar[stage], sB, kb * BLOCK_K, t.row0, CACHE_EVICT_LAST);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      if (!waited) {   // fewer work items than pipeline stages
+        pdl_wait();
+        for (int i = 0; i < npend; ++i)
+          tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
+                      pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one lane) =====================
+    if (p.early_a) pdl_wait();
     constexpr uint32_t idesc = make_idesc_f16(DT, BLOCK_M, NT);
     int stage = 0;
     uint32_t phase = 0;
@@ -256,6 +281,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    if (p.early_a) pdl_wait();
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int cgrp = (warp - 4) >> 2;    // with 8 epilogue warps two warps share a quadrant and alternate 16-column chunks
     const int r = q * 32 + lane;         // weight row inside the tile
@@ -400,7 +426,7 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr_done = true;
   }
   if (MC > 1) grid -= grid % MC;
-  return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, a0, a1, b, p);
+  return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, p.early_a != 0, a0, a1, b, p);
 }
 
 template <int DT>
