@@ -803,6 +803,8 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     // the variant is opt-in: B2M_MC2=1
     static const bool mc2_on = getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '1';
     const bool mc2 = mc2_on && nt == 128 && T_hint_large;
+    static const bool pdl_k3 = getenv("B2M_PDL_K3") && getenv("B2M_PDL_K3")[0] == '1';
+    up.pdl_edge = (pdl_k3 && !T_hint_large) ? 1 : 0;
     if (phases & 1) {
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
@@ -813,7 +815,8 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       const bool pair = nt_dn >= 128 && s.H >= 256 && T_hint_large;
       dn.dual_m = pair ? 1 : 0;
       // decode: let the down projection start under the tail of the gate/up GEMM and prefetch its first weight tiles
-      static const bool early_a = getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '1';
+      // measured on B200 (profiles/r01g_pdl_edges.txt): 12.945 -> 12.855 ms/step; B2M_EARLY_A=0 disables
+      static const bool early_a = !(getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '0');
       dn.early_a = (early_a && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
       if (mc2 && nt_dn == 128) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));

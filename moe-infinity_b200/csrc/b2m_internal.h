@@ -39,6 +39,7 @@ struct GemmParams {
   int ld_out;
   int single_n;         // >= 0: one expert (E must be 1) with single_n rows in slot single_slot; offsets/slot_of unused
   int single_slot;
+  int pdl_edge;         // launch with a programmatic edge (prologue overlaps the predecessor's tail; waits before any global access)
   int early_a;          // launched with a programmatic edge: weight tiles may be fetched before the predecessor finishes
   int dual_m;           // DUAL kernel, EPI_LINEAR_F32: A1 = rows m0+128.. of the same matrix (two m-tiles share a token tile)
 };

@@ -426,7 +426,7 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr_done = true;
   }
   if (MC > 1) grid -= grid % MC;
-  return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, p.early_a != 0, a0, a1, b, p);
+  return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, p.early_a != 0 || p.pdl_edge != 0, a0, a1, b, p);
 }
 
 template <int DT>
