@@ -146,6 +146,8 @@ struct b2m_ctx {
     int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
+  int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
+  bool k3_early_ok = false;      // offsets of the current routing were published before the permute kernel
   int* d_dest_of = nullptr;      // [cap_R]
   b2m_stats stats;
 };
@@ -413,6 +415,7 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
   p.topk_idx = c->d_topk_idx; p.topk_w = c->d_topk_w; p.row_of = c->d_row_of; p.perm_token = c->d_perm_token;
   p.counts = c->d_counts; p.offsets = c->d_offsets; p.chunk_counts = c->d_chunk_counts;
   p.xp = c->d_xp;
+  p.ticket = c->d_ticket;
   return p;
 }
 
@@ -548,6 +551,8 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_offsets, sizeof(int) * (E + 1)));
   CKC(cudaMemset(c->d_offsets, 0, sizeof(int) * (E + 1)));
   CKC(cudaMalloc((void**)&c->d_offsets_src, sizeof(int) * (E + 1)));
+  CKC(cudaMalloc((void**)&c->d_ticket, sizeof(int)));
+  CKC(cudaMemset(c->d_ticket, 0, sizeof(int)));
   CKC(cudaMalloc((void**)&c->d_dest_of, sizeof(int) * R));
   CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
   CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
@@ -589,7 +594,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_offsets_src, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
@@ -748,6 +753,12 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     return fail(c, B2M_EINVAL, "T=%d is not a multiple of seq_len=%d", T, p.seq_len);
   plan_gemm(c, T);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
+  // small batches, all experts resident: let the last gate/top-k CTA publish the offsets so that the gate/up GEMM can be
+  // launched with a programmatic edge behind the permute kernel and stream weights while rows are still being gathered
+  static const bool k3_early = !(getenv("B2M_EARLY_K3") && getenv("B2M_EARLY_K3")[0] == '0');
+  c->k3_early_ok = k3_early && T >= 1 && T <= 256 && c->cfg.router != B2M_ROUTER_SWITCH_TOP1 && !ep_dispatch && !c->offload &&
+                   !c->ep_mode && c->cfg.gemm_impl == 0;
+  p.offsets_early = c->k3_early_ok ? 1 : 0;
   if (ep_dispatch) {
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;
@@ -768,6 +779,7 @@ int b2m_route_from_mask(b2m_ctx* c, int layer, const void* x, const uint8_t* mas
   RouteParams p = base_route_params(c, layer, x, T, T);
   p.scores = nullptr;
   p.logits_out = nullptr;
+  c->k3_early_ok = false;
   plan_gemm(c, T);
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
   CK(c, launch_route_from_mask(p, mask, st));
@@ -805,6 +817,7 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     const bool mc2 = mc2_on && nt == 128 && T_hint_large;
     static const bool pdl_k3 = getenv("B2M_PDL_K3") && getenv("B2M_PDL_K3")[0] == '1';
     up.pdl_edge = (pdl_k3 && !T_hint_large) ? 1 : 0;
+    up.early_a = (c->k3_early_ok && &a == &c->arena && phases == 3) ? 1 : 0;   // routed experts right behind the permute kernel
     if (phases & 1) {
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
@@ -1147,6 +1160,7 @@ static int ep_check(b2m_ctx* c, int nranks, int rank, int cap) {
 }
 
 int b2m_ep_pack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, void* send_rows, int32_t* send_counts, void* stream) {
+  if (c) c->k3_early_ok = false;
   int r = ep_check(c, nranks, rank, cap);
   if (r) return r;
   if (T_local * c->cfg.top_k > cap) return fail(c, B2M_EINVAL, "cap=%d < T_local*top_k=%d", cap, T_local * c->cfg.top_k);
@@ -1162,6 +1176,7 @@ int b2m_ep_pack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, void* se
 }
 
 int b2m_ep_regroup(b2m_ctx* c, int nranks, int rank, int cap, int T_total, const void* recv_rows, const int32_t* recv_counts, void* stream) {
+  if (c) c->k3_early_ok = false;
   int r = ep_check(c, nranks, rank, cap);
   if (r) return r;
   if (T_total < 1 || T_total > c->cap_T) return fail(c, B2M_EINVAL, "T_total=%d exceeds workspace capacity %d", T_total, c->cap_T);
@@ -1273,6 +1288,7 @@ static int p2p_ready(b2m_ctx* c) {
 }
 
 int b2m_ep_p2p_dispatch(b2m_ctx* c, int T_local, void* stream) {
+  if (c) c->k3_early_ok = false;
   int r = p2p_ready(c);
   if (r) return r;
   if (T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "cap=%d < T_local*top_k", c->p2p.cap);
@@ -1303,6 +1319,7 @@ int b2m_ep_p2p_combine(b2m_ctx* c, int layer, const void* x, int T_local, void* 
 }
 
 int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {
+  if (c) c->k3_early_ok = false;
   int r = p2p_ready(c);
   if (r) return r;
   if (T_total < 1 || T_total > c->cap_T) return fail(c, B2M_EINVAL, "T_total=%d exceeds workspace capacity %d", T_total, c->cap_T);

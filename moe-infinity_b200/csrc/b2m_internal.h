@@ -115,6 +115,9 @@ struct RouteParams {
   void* xp;                  // [T*k, H] gathered activations
   float* y_zero;             // optional fp32 buffer to clear (split-K accumulator), y_zero_elems floats
   size_t y_zero_elems;
+  int* ticket;               // small-T path: CTA arrival counter (0 between launches)
+  int offsets_early;         // small-T path: the last gate/top-k CTA already publishes counts/offsets (so the gate/up GEMM can
+                             // start fetching weights while the permute kernel is still gathering rows)
   int ep_dispatch;           // 1 (T <= 256 only): gathered rows go straight to the owning ranks' buffers (ep)
   EpParams ep;
 };

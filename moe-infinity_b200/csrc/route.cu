@@ -572,18 +572,71 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
     }
   }
   __syncthreads();
-  if (warp != 0) return;
-  if (p.logits_out && !scores_in) {
-    for (int e = lane; e < p.E; e += 32) {
-      const float lv = s_logits[e];
-      if (p.router == ROUTER_MIXTRAL)
-        reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
-            p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
-      else
-        reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
+  if (warp == 0) {
+    if (p.logits_out && !scores_in) {
+      for (int e = lane; e < p.E; e += 32) {
+        const float lv = s_logits[e];
+        if (p.router == ROUTER_MIXTRAL)
+          reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e] =
+              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(lv) : Half16<DT_F16>::from_f(lv);
+        else
+          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e] = lv;
+      }
     }
+    route_token_warp(p, t, s_logits, scores_in, s_scr, p.topk_idx + (size_t)t * p.k, p.topk_w + (size_t)t * p.k);
   }
-  route_token_warp(p, t, s_logits, scores_in, s_scr, p.topk_idx + (size_t)t * p.k, p.topk_w + (size_t)t * p.k);
+  if (!p.offsets_early) return;
+  // ---- the last CTA to finish publishes counts[E] / offsets[E+1] for the whole batch: the grouped GEMM only needs these
+  // (not the gathered rows) to start streaming weights, so it can overlap the permute kernel
+  __shared__ int s_last;
+  __shared__ int s_idx2[FUSED_MAX_T * MAX_K];
+  __shared__ int s_cnt2[RT_WARPS][MAX_PL * 32];
+  __shared__ int s_tot2[MAX_PL * 32];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int npairs = p.T * p.k;
+  const int nchunks = (p.T + CHUNK - 1) / CHUNK;
+  for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx2[i] = __ldcg(p.topk_idx + i);   // other CTAs' results: L2
+  __syncthreads();
+  if (warp < nchunks) chunk_count_warp(s_idx2, warp * CHUNK, p.T, p.k, p.E, s_cnt2[warp]);
+  __syncthreads();
+  if (threadIdx.x < p.E) {
+    int run = 0;
+    for (int c = 0; c < nchunks; ++c) run += s_cnt2[c][threadIdx.x];
+    s_tot2[threadIdx.x] = run;
+    p.counts[threadIdx.x] = run;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int v[MAX_PL], run = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane * MAX_PL + i;
+      v[i] = e < p.E ? s_tot2[e] : 0;
+      run += v[i];
+    }
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    int base = incl - run;
+#pragma unroll
+    for (int i = 0; i < MAX_PL; ++i) {
+      const int e = lane * MAX_PL + i;
+      if (e < p.E) p.offsets[e] = base;
+      base += v[i];
+    }
+    if (lane == 31) p.offsets[p.E] = incl;
+    if (lane == 0) *p.ticket = 0;
+  }
 }
 
 __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RouteParams p) {
@@ -659,8 +712,10 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   __syncthreads();
   if (blockIdx.x == 0) {
     for (int e = threadIdx.x; e <= p.E; e += RT_THREADS) {   // E may equal the block size: stride loop, not tid <= E
-      p.offsets[e] = s_off[e];
-      if (e < p.E) p.counts[e] = s_tot[e];
+      if (!p.offsets_early) {   // otherwise the gate/top-k kernel published them (and the GEMM may be reading them now)
+        p.offsets[e] = s_off[e];
+        if (e < p.E) p.counts[e] = s_tot[e];
+      }
       if (p.ep_dispatch) p.ep.offsets_src[e] = s_off[e];
     }
   }
