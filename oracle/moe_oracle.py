@@ -11,12 +11,16 @@ Where the arithmetic lives: the reference performs all math through libtorch/ATe
 The same library is importable here, so this restatement calls the *same operators*
 in the same order and dtypes as the reference call sites cited below.
 
-Parity status: **parity unpinned** -- the reference ships no golden vectors, KATs or
-fixtures for this path.  The pin is (a) tests/test_oracle_vs_literal.py,
-which runs the literal reference block files (mixtral.py, deepseek.py, MoEGate) from
-/root/reference in the dev container and demands bit equality with this module, and
-(b) the fixtures under tests/golden/ generated from those literal files by
-tests/golden/make_golden.py.
+Parity status: the reference ships no golden vectors, KATs or fixtures for this path, so the
+pin is made from outputs of the reference itself run in the dev container:
+  (a) expert FFN (D1-D3): the reference's OWN core/parallel/expert_module.cpp is compiled as-is into
+      oracle/_ref/ref_expert_module.so (oracle/ref_build/Makefile); tests/test_oracle_expert_ref.py demands bit equality
+      of `expert_ffn` with it for all six expert types x three dtypes, live and through tests/golden/expert_ffn_ref.pt;
+  (b) routing / mask build / combine (A1-A5, G1-G2): the literal reference block files (mixtral.py, deepseek.py, MoEGate)
+      are executed on CPU through tests/shims/ref_loader.py; tests/test_oracle_golden.py demands bit equality with this
+      module and tests/golden/*.pt hold their outputs (tests/golden/make_golden.py);
+  (c) Switch routing (A6) is **parity unpinned**: HF 5.5's router signature differs from the 4.x one the reference
+      block expects, so the literal block cannot run here; its fixtures come from this restatement only.
 
 Determinism choices (the reference itself is nondeterministic):
   * experts are combined in ascending expert id (reference: thread completion order,
@@ -176,11 +180,11 @@ def expert_ffn(x: torch.Tensor, weights: Sequence[torch.Tensor], expert_type: in
         g = F.gelu(torch.matmul(x, wi_0.transpose(0, 1)))
         return torch.matmul(torch.mul(g, torch.matmul(x, wi_1.transpose(0, 1))), wo.transpose(0, 1))  # :54-59
     if expert_type in (NLLB_MOE_DENSE_ACT_DENSE, FSGPT_MOE_DENSE_ACT_DENSE):
-        fc1, fc1_bias, fc2, fc2_bias = weights                  # :70-77
-        if x.dtype != fc1.dtype:
-            x = x.to(fc1.dtype)
+        fc1, fc1_bias, fc2, fc2_bias = weights                  # :70-77, :104-111
+        if expert_type == FSGPT_MOE_DENSE_ACT_DENSE and x.dtype != fc1.dtype:
+            x = x.to(fc1.dtype)                                 # :122-123 (only the FSGPT module casts)
         return torch.matmul(torch.relu(torch.matmul(x, fc1.transpose(0, 1)) + fc1_bias),
-                            fc2.transpose(0, 1)) + fc2_bias     # :88-92
+                            fc2.transpose(0, 1)) + fc2_bias     # :88-92, :124-128
     raise ValueError(f"unknown expert type {expert_type}")
 
 
