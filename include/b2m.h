@@ -44,8 +44,8 @@ extern "C" {
 /* expert-type ints == reference core/parallel/expert_module.h:13-18 */
 #define B2M_EXPERT_SWITCH_DENSE_ACT_DENSE 0       /* wi, wo; ReLU            (expert_module.cpp:24-35)  */
 #define B2M_EXPERT_SWITCH_DENSE_GATED_ACT_DENSE 1 /* wi_0, wi_1, wo; GELU    (:54-59)                   */
-#define B2M_EXPERT_NLLB_MOE_DENSE_ACT_DENSE 2     /* biases: B2M_EUNSUPPORTED                          */
-#define B2M_EXPERT_FSGPT_MOE_DENSE_ACT_DENSE 3    /* biases: B2M_EUNSUPPORTED                          */
+#define B2M_EXPERT_NLLB_MOE_DENSE_ACT_DENSE 2     /* fc1, fc1_bias, fc2, fc2_bias; ReLU (:79-129)        */
+#define B2M_EXPERT_FSGPT_MOE_DENSE_ACT_DENSE 3    /* fc1, fc1_bias, fc2, fc2_bias; ReLU (:79-129)        */
 #define B2M_EXPERT_MIXTRAL_MOE_DENSE_ACT_DENSE 4  /* w1, w2, w3; SiLU        (:147-175)                 */
 #define B2M_EXPERT_DEEPSEEK_MOE_DENSE_ACT_DENSE 5 /* gate, up, down; SiLU    (:193-203)                 */
 

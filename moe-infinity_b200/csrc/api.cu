@@ -44,6 +44,8 @@ struct ExpertShape {
   bool dual = true;
   int act = ACT_SILU;
   size_t off_gate = 0, off_up = 0, off_down = 0, bytes = 0;
+  bool has_bias = false;          // fc1 | fc1_bias | fc2 | fc2_bias (NLLB / FSGPT)
+  size_t off_bias1 = 0, off_bias2 = 0;
 };
 
 struct Arena {
@@ -187,6 +189,12 @@ bool make_shape(int expert_type, int H, int I, ExpertShape* s) {
       return true;
     case B2M_EXPERT_SWITCH_DENSE_ACT_DENSE:  // wi | wo  (:17-23)
       s->dual = false; s->act = ACT_RELU; s->off_gate = 0; s->off_up = 0; s->off_down = m; s->bytes = 2 * m;
+      return true;
+    case B2M_EXPERT_NLLB_MOE_DENSE_ACT_DENSE:   // fc1 | fc1_bias | fc2 | fc2_bias  (:70-77; forward :88-92)
+    case B2M_EXPERT_FSGPT_MOE_DENSE_ACT_DENSE:  // same binding (:104-111; forward :124-128, ReLU as well)
+      s->dual = false; s->act = ACT_RELU; s->has_bias = true;
+      s->off_gate = 0; s->off_up = 0; s->off_bias1 = m; s->off_down = m + (size_t)I * 2;
+      s->off_bias2 = s->off_down + m; s->bytes = s->off_bias2 + (size_t)H * 2;   // H, I multiples of 8: all 16-B aligned
       return true;
     default:
       return false;
@@ -427,6 +435,7 @@ void plan_gemm(b2m_ctx* c, int T) {
   static const bool up256 = !(getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '0');
   c->cur_nt = (up256 && c->cur_nt_dn == 256) ? 256 : pick_nt(T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
+  if (c->arena.shape.has_bias) c->cur_ksplit = 1;   // `+ fc2_bias` is applied once, in the epilogue of the whole-K product
 }
 
 int route_launch_count(int T, int router, bool fused_gate) {
@@ -456,7 +465,7 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
     return fail(nullptr, B2M_EINVAL, "bad model dimensions");
   ExpertShape shape;
   if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape))
-    return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is not supported (bias experts are out of scope)", cfg->expert_type);
+    return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is unknown (expert_module.h:13-18 defines 0..5)", cfg->expert_type);
   if (cfg->router < 0 || cfg->router > 3) return fail(nullptr, B2M_EINVAL, "bad router kind");
   if (cfg->router == B2M_ROUTER_SWITCH_TOP1 && cfg->top_k != 1) return fail(nullptr, B2M_EINVAL, "switch router needs top_k=1");
 
@@ -802,6 +811,14 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
   GemmParams dn = base;
   dn.M = s.H; dn.K = s.I; dn.ksplit = ksplit; dn.epi = EPI_LINEAR_F32; dn.act = ACT_NONE; dn.mimic = 0;
   dn.out = y; dn.ld_out = s.H;
+  if (s.has_bias) {
+    up.bias_base = dn.bias_base = a.base;
+    up.bias_slot_elems = dn.bias_slot_elems = a.slot_bytes / 2;
+    up.bias_off = s.off_bias1 / 2;
+    dn.bias_off = s.off_bias2 / 2;
+    dn.ksplit = 1;
+    dn.mimic = up.mimic;     // round(matmul) + bias -> round happens here; the combine's rounding is then the identity
+  }
   if (f.gemm_impl == 1) {
     const size_t slot_elems = a.slot_bytes / 2;
     if (phases & 1)

@@ -42,6 +42,11 @@ struct GemmParams {
   int pdl_edge;         // launch with a programmatic edge (prologue overlaps the predecessor's tail; waits before any global access)
   int early_a;          // launched with a programmatic edge: weight tiles may be fetched before the predecessor finishes
   int dual_m;           // DUAL kernel, EPI_LINEAR_F32: A1 = rows m0+128.. of the same matrix (two m-tiles share a token tile)
+  // bias experts (NLLB / FSGPT, expert_module.cpp:88-92,124-128): bias[m] of the expert in slot s lives at
+  // bias_base + s * bias_slot_elems + bias_off (16-bit elements of the model dtype); null = no bias.  Needs ksplit == 1.
+  const void* bias_base;
+  size_t bias_slot_elems;
+  size_t bias_off;
 };
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,

@@ -293,6 +293,12 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
       const int m = t.m0 + r;
       const bool row_ok = m < p.M;
+      float bias0 = 0.f, bias1 = 0.f;   // bias experts: one value per weight row = per TMEM lane
+      if (p.bias_base) {
+        const uint16_t* bp = reinterpret_cast<const uint16_t*>(p.bias_base) + (size_t)t.slot * p.bias_slot_elems + p.bias_off;
+        if (row_ok) bias0 = Half16<DT>::to_f(bp[m]);
+        if (DUAL && m + BLOCK_M < p.M) bias1 = Half16<DT>::to_f(bp[m + BLOCK_M]);
+      }
       for (int c0 = cgrp * 16; c0 < t.ncols; c0 += 16 * (Cfg::EPI_WARPS / 4)) {   // warp-uniform trip count
         uint32_t vg[16], vu[16];
         tmem_ld_x16(taddr + c0, vg);
@@ -305,11 +311,13 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             if (c0 + j < t.ncols) {
               float* dst = out + (size_t)(t.row0 + c0 + j) * p.ld_out + m;
               if (row_ok) {
-                const float v = __uint_as_float(vg[j]);
+                float v = __uint_as_float(vg[j]);
+                if (p.bias_base) v = p.mimic ? round_dt<DT>(round_dt<DT>(v) + bias0) : v + bias0;   // matmul, then `+ bias`
                 if (p.ksplit > 1) atomicAdd(dst, v); else *dst = v;
               }
               if (DUAL && m + BLOCK_M < p.M) {   // dual_m: second accumulator = rows m0+128..m0+255
-                const float v = __uint_as_float(vu[j]);
+                float v = __uint_as_float(vu[j]);
+                if (p.bias_base) v = p.mimic ? round_dt<DT>(round_dt<DT>(v) + bias1) : v + bias1;
                 if (p.ksplit > 1) atomicAdd(dst + BLOCK_M, v); else dst[BLOCK_M] = v;
               }
             }
@@ -334,6 +342,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
                 }
               } else {
                 if (p.mimic) g = round_dt<DT>(g);
+                if (p.bias_base) { g += bias0; if (p.mimic) g = round_dt<DT>(g); }
                 h = act_apply(g, p.act);
               }
               out[(size_t)(t.row0 + c0 + j) * p.ld_out + m] = Half16<DT>::from_f(h);
@@ -393,7 +402,11 @@ __global__ void grouped_gemm_simt_kernel(const uint16_t* __restrict__ arena, siz
       s1 += __shfl_xor_sync(0xffffffffu, s1, d);
     }
     if (lane == 0) {
+      float bias = 0.f;
+      if (p.bias_base)
+        bias = Half16<DT>::to_f(reinterpret_cast<const uint16_t*>(p.bias_base)[(size_t)slot * p.bias_slot_elems + p.bias_off + m]);
       if (p.epi == EPI_LINEAR_F32) {
+        if (p.bias_base) s0 = p.mimic ? round_dt<DT>(round_dt<DT>(s0) + bias) : s0 + bias;
         reinterpret_cast<float*>(p.out)[(size_t)row * p.ld_out + m] = s0;
       } else {
         float g = s0, h;
@@ -403,6 +416,7 @@ __global__ void grouped_gemm_simt_kernel(const uint16_t* __restrict__ arena, siz
           else h = act_apply(g, p.act) * u;
         } else {
           if (p.mimic) g = round_dt<DT>(g);
+          if (p.bias_base) { g += bias; if (p.mimic) g = round_dt<DT>(g); }
           h = act_apply(g, p.act);
         }
         reinterpret_cast<uint16_t*>(p.out)[(size_t)row * p.ld_out + m] = Half16<DT>::from_f(h);

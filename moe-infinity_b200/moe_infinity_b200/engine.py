@@ -82,8 +82,11 @@ class MoEEngine:
         self._h = h
         self._blobs: Dict[Tuple[int, int], torch.Tensor] = {}
         self._gates: Dict[int, torch.Tensor] = {}
-        nmat = 2 if expert_type == L.EXPERT_SWITCH else 3
-        self.expert_bytes = nmat * hidden * inter * 2
+        if expert_type in (L.EXPERT_NLLB, L.EXPERT_FSGPT):     # fc1 | fc1_bias | fc2 | fc2_bias (expert_module.cpp:70-77)
+            self.expert_bytes = 2 * hidden * inter * 2 + (inter + hidden) * 2
+        else:
+            nmat = 2 if expert_type == L.EXPERT_SWITCH else 3
+            self.expert_bytes = nmat * hidden * inter * 2
         self.shared_bytes = 3 * hidden * shared_inter * 2
 
     # ------------------------------------------------------------------ lifecycle
@@ -118,7 +121,7 @@ class MoEEngine:
 
     def register_expert(self, layer: int, expert: int, tensors: Sequence[torch.Tensor], pin: bool = True):
         """Host-backed expert (can be staged in and evicted).  tensors: Mixtral (w1,w2,w3),
-        DeepSeek (gate,up,down), Switch (wi,wo) -- nn.Linear [out,in] layout."""
+        DeepSeek (gate,up,down), Switch (wi,wo), NLLB/FSGPT (fc1,fc1_bias,fc2,fc2_bias) -- nn.Linear [out,in] layout."""
         blob = self._pack(tensors, self.expert_bytes, pin)
         self._blobs[(layer, expert)] = blob
         self._ck(self.lib.b2m_register_expert(self._h, layer, expert, C.c_void_p(blob.data_ptr()), blob.numel()))

@@ -96,7 +96,7 @@ def test_workspace_capacity_boundary_and_errors(lib_built):
 def test_unsupported_types_fail_loudly(lib_built):
     from moe_infinity_b200 import MoEEngine, B2MError, _lib as L
     with pytest.raises(B2MError):
-        MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, expert_type=L.EXPERT_NLLB)
+        MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, expert_type=6)   # expert_module.h: 0..5
     with pytest.raises(B2MError):
         MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, dtype=torch.float32)
     with pytest.raises(B2MError):
