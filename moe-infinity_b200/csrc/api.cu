@@ -848,6 +848,10 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       // measured on B200 (profiles/r01g_pdl_edges.txt): 12.945 -> 12.855 ms/step; B2M_EARLY_A=0 disables
       static const bool early_a = !(getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '0');
       dn.early_a = (early_a && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
+      // split-K at decode: equal contiguous shares of all (tile, k-block) units per CTA instead of a fixed factor, so no
+      // SM is left with an extra slice in the last wave (B2M_STREAMK=0: fixed factor)
+      static const bool streamk = !(getenv("B2M_STREAMK") && getenv("B2M_STREAMK")[0] == '0');
+      dn.stream_k = (streamk && dn.ksplit > 1 && !(mc2 && nt_dn == 128)) ? 1 : 0;
       if (mc2 && nt_dn == 128) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
       else CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
     }

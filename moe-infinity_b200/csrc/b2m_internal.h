@@ -32,6 +32,8 @@ struct GemmParams {
   int M;                // weight rows per expert
   int K;                // reduction length
   int ksplit;           // split-K factor (EPI_LINEAR_F32 only)
+  int stream_k;         // with ksplit > 1: ignore the factor and give every CTA an equal, contiguous share of all
+                        // (tile, k-block) units; a CTA red.adds one partial per tile segment it crosses
   int epi;              // EPI_*
   int act;              // ACT_*
   int mimic;            // replay the reference's per-op rounding to the model dtype

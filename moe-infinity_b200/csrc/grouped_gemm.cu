@@ -63,8 +63,21 @@ struct TileWalker {
   const int* slots;       // smem [E]
   int E, NTv, ksplit, kblocks, e_cur, m_step;
   int mc, rank;   // multicast cluster size (1|2) and this CTA's rank: the CTAs of a cluster take adjacent token tiles
+  // stream-K (split-K GEMM at decode): this CTA owns the k-block units [u_cur, u_end) of the concatenation of all tiles;
+  // get() then ignores `tile` and hands out the next segment (part of one tile) of that range
+  int stream;
+  int u_cur, u_end;
   __device__ __forceinline__ bool get(int tile, TileInfo& t) {
-    if (tile >= tile_start[E]) return false;
+    int kb0 = 0, kb1 = 0;
+    if (stream) {
+      if (u_cur >= u_end) return false;
+      tile = u_cur / kblocks;
+      kb0 = u_cur - tile * kblocks;
+      kb1 = min(kblocks, kb0 + (u_end - u_cur));
+      u_cur += kb1 - kb0;
+    } else if (tile >= tile_start[E]) {
+      return false;
+    }
     while (tile >= tile_start[e_cur + 1]) ++e_cur;
     const int e = e_cur;
     const int n_e = offs[e + 1] - offs[e];
@@ -83,6 +96,7 @@ struct TileWalker {
     t.ncols = max(0, min(NTv, n_e - n * NTv));   // 0: ghost tile of an odd group (loads + MMA still run in lock step)
     t.kb_begin = s * kb_per;
     t.kb_end = min(kblocks, t.kb_begin + kb_per);
+    if (stream) { t.kb_begin = kb0; t.kb_end = kb1; }
     return true;
   }
 };
@@ -170,7 +184,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     for (int e = 0; e < E; ++e) {
       tile_start[e] = acc;
       const int n_e = offs[e + 1] - offs[e];
-      if (n_e > 0 && slots[e] >= 0) acc += m_tiles * (((n_e + NT - 1) / NT + MC - 1) / MC) * p.ksplit;
+      if (n_e > 0 && slots[e] >= 0) acc += m_tiles * (((n_e + NT - 1) / NT + MC - 1) / MC) * (p.stream_k ? 1 : p.ksplit);
     }
     tile_start[E] = acc;
   }
@@ -181,7 +195,13 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   if (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast targets them
 
-  TileWalker walker{tile_start, offs, slots, E, NT, p.ksplit, kblocks, 0, m_step, MC, crank};
+  TileWalker walker{tile_start, offs, slots, E, NT, p.stream_k ? 1 : p.ksplit, kblocks, 0, m_step, MC, crank, 0, 0, 0};
+  if (MC == 1 && p.stream_k) {
+    const long long units = (long long)tile_start[E] * kblocks;
+    walker.stream = 1;
+    walker.u_cur = (int)(units * blockIdx.x / gridDim.x);
+    walker.u_end = (int)(units * (blockIdx.x + 1) / gridDim.x);
+  }
   TileInfo t;
   const int tile0 = blockIdx.x / MC, tile_stride = gridDim.x / MC;   // tiles are dealt to clusters
 

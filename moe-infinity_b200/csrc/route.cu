@@ -144,58 +144,139 @@ __device__ __forceinline__ void gate_dot8_warp(const RouteParams& p, int t, int 
   else gate_dot8_impl<false>(p, t, e0, out);
 }
 
-// Large-T gate (prefill): one warp per token, 8 experts per pass.  The token row is the HBM stream: eight 16-byte loads
-// of x are issued back to back per lane (MLP), the gate rows (E*H elements, cache resident) are read as they are used.
-__global__ void __launch_bounds__(256) gate_logits_kernel(const RouteParams p) {
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (t >= p.T) return;
-  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H;
-  const bool wf32 = p.gate_dtype == DT_F32;
-  for (int e0 = 0; e0 < p.E; e0 += 8) {
-    float acc[8];
+// Large-T gate (prefill): a small fp32 GEMM logits[T,E] = x[T,H] . Wg[E,H]^T on the CUDA cores (fp32 FMA: the expert
+// indices derived from it must match the reference's fp32 linear, so no reduced-precision tensor-core inputs).
+// A CTA owns 32 tokens (8 warps x GATE_TW) and walks (8-expert group, 256-element slice of H) chunks of the gate matrix:
+// each chunk (8 KB fp32 / 4 KB 16-bit) is staged ONCE per CTA in shared memory by cp.async (3-deep ring, one
+// __syncthreads per chunk) and used by all 8 warps for GATE_TW x 8 x 8 FMAs per lane.  The first version read the gate
+// rows per token straight from L2 (2 GB of L2 traffic per DeepSeek-V2-Lite layer at T=4096; 158 us); a register-only
+// variant with 4-8 tokens per warp was still L2-bound at ~6 TB/s (94-102 us).  Expert groups are split over blockIdx.y
+// when the token blocks alone would not fill the GPU.
+constexpr int GATE_TW = 4;
+constexpr int GATE_TOK_PER_CTA = 8 * GATE_TW;
+constexpr int GATE_RING = 3;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int WDT, int XDT>
+__device__ __forceinline__ void gate_logits_impl(const RouteParams& p, uint4* ring /*[GATE_RING][WF32 ? 512 : 256]*/) {
+  constexpr bool WF32 = WDT == DT_F32;
+  constexpr int PIECES = WF32 ? 512 : 256;                 // 16-byte pieces per chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ngroups = (p.E + 7) / 8;
+  const int nh = (p.H + 255) / 256;
+  const int t0 = blockIdx.x * GATE_TOK_PER_CTA + warp * GATE_TW;
+  // this CTA's expert groups: blockIdx.y, blockIdx.y + gridDim.y, ...
+  const int npass = (ngroups - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int nchunks = npass * nh;
+  const uint16_t* xrow[GATE_TW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int hb = lane * 8; hb < p.H; hb += 256 * 8) {
-      uint4 xv[8];
+  for (int q = 0; q < GATE_TW; ++q)
+    xrow[q] = reinterpret_cast<const uint16_t*>(p.x) + (size_t)min(t0 + q, p.T - 1) * p.H;   // clamped: no predicates on addresses
+  const bool hvalid_all = (p.H % 256) == 0;
+
+  auto issue = [&](int c) {   // stage chunk c = (pass c / nh, slice c % nh) into ring slot c % GATE_RING
+    if (c < nchunks) {
+      const int e0 = ((int)blockIdx.y + (c / nh) * (int)gridDim.y) * 8;
+      const int h0 = (c % nh) * 256;
+      uint4* dst = ring + (size_t)(c % GATE_RING) * PIECES;
+      for (int pc = threadIdx.x; pc < PIECES; pc += 256) {
+        int i, l, half = 0;
+        if (WF32) { i = pc >> 6; l = (pc & 63) >> 1; half = pc & 1; } else { i = pc >> 5; l = pc & 31; }
+        const int h = h0 + l * 8;
+        const bool ok = h < p.H;
+        const char* src = reinterpret_cast<const char*>(p.gate_w) +
+                          ((size_t)min(e0 + i, p.E - 1) * p.H + (ok ? h : 0)) * (WF32 ? 4 : 2) + half * 16;
+        // fp32: [i][half][lane] so that the 32 lanes of a warp read 512 contiguous bytes (no bank conflicts)
+        cp_async_16(dst + (WF32 ? ((i * 2 + half) * 32 + l) : (i * 32 + l)), src, ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue(0);
+  issue(1);
+  float acc[GATE_TW][8];
+  uint4 xnext[GATE_TW];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int h = hb + q * 256;
-        xv[q] = h < p.H ? *reinterpret_cast<const uint4*>(x + h) : make_uint4(0, 0, 0, 0);
+  for (int q = 0; q < GATE_TW; ++q)
+    xnext[q] = (lane * 8 < p.H) ? *reinterpret_cast<const uint4*>(xrow[q] + lane * 8) : make_uint4(0u, 0u, 0u, 0u);
+  for (int c = 0; c < nchunks; ++c) {
+    const int hc = c % nh;
+    if (hc == 0) {
+#pragma unroll
+      for (int q = 0; q < GATE_TW; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+    }
+    // token slices are requested one chunk ahead (their L2 latency hides under this chunk's FMAs)
+    uint4 xv[GATE_TW];
+#pragma unroll
+    for (int q = 0; q < GATE_TW; ++q) xv[q] = xnext[q];
+    {
+      const int hn = ((c + 1) % nh) * 256 + lane * 8;
+      if (c + 1 < nchunks) {
+#pragma unroll
+        for (int q = 0; q < GATE_TW; ++q)
+          xnext[q] = (hvalid_all || hn < p.H) ? *reinterpret_cast<const uint4*>(xrow[q] + hn) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    cp_async_wait<1>();        // chunk c has landed (chunk c+1 may still be in flight)
+    __syncthreads();           // ... for every thread's pieces; and every warp is done with chunk c-1
+    issue(c + 2);              // refills the slot chunk c-1 used
+    float xf[GATE_TW][8];
+#pragma unroll
+    for (int q = 0; q < GATE_TW; ++q) unpack8(xv[q], XDT, xf[q]);      // compile-time dtype: one shift per element
+    const uint4* w = ring + (size_t)(c % GATE_RING) * PIECES;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float wf[8];
+      if (WF32) {
+        const uint4 a = w[(i * 2) * 32 + lane], b = w[(i * 2 + 1) * 32 + lane];
+        wf[0] = __uint_as_float(a.x); wf[1] = __uint_as_float(a.y); wf[2] = __uint_as_float(a.z); wf[3] = __uint_as_float(a.w);
+        wf[4] = __uint_as_float(b.x); wf[5] = __uint_as_float(b.y); wf[6] = __uint_as_float(b.z); wf[7] = __uint_as_float(b.w);
+      } else {
+        unpack8(w[i * 32 + lane], WDT, wf);
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int h = hb + q * 256;
-        if (h >= p.H) break;
-        float xf[8];
-        unpack8(xv[q], p.dtype, xf);
+      for (int q = 0; q < GATE_TW; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[q][i] = fmaf(xf[q][j], wf[j], acc[q][i]);
+    }
+    if (hc == nh - 1) {
+      const int e0 = ((int)blockIdx.y + (c / nh) * (int)gridDim.y) * 8;
+#pragma unroll
+      for (int q = 0; q < GATE_TW; ++q) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const size_t row = (size_t)min(e0 + i, p.E - 1) * p.H + h;
-          float wf[8];
-          if (wf32) {
-            const float* w = reinterpret_cast<const float*>(p.gate_w) + row;
-            const float4 a = *reinterpret_cast<const float4*>(w), c = *reinterpret_cast<const float4*>(w + 4);
-            wf[0] = a.x; wf[1] = a.y; wf[2] = a.z; wf[3] = a.w; wf[4] = c.x; wf[5] = c.y; wf[6] = c.z; wf[7] = c.w;
-          } else {
-            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gate_w) + row), p.gate_dtype, wf);
+          const float v = warp_sum(acc[q][i]);
+          const int t = t0 + q;
+          if (lane == 0 && t < p.T && e0 + i < p.E) {
+            if (p.router == ROUTER_MIXTRAL)
+              reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e0 + i] =
+                  p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v) : Half16<DT_F16>::from_f(v);
+            else
+              reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v;
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xf[j], wf[j], acc[i]);
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = warp_sum(acc[i]);
-      if (lane == 0 && e0 + i < p.E) {
-        if (p.router == ROUTER_MIXTRAL)
-          reinterpret_cast<uint16_t*>(p.logits_out)[(size_t)t * p.E + e0 + i] =
-              p.dtype == DT_BF16 ? Half16<DT_BF16>::from_f(v) : Half16<DT_F16>::from_f(v);
-        else
-          reinterpret_cast<float*>(p.logits_out)[(size_t)t * p.E + e0 + i] = v;
-      }
-    }
+  }
+  cp_async_wait<0>();
+}
+__global__ void __launch_bounds__(256, 2) gate_logits_kernel(const RouteParams p) {
+  __shared__ __align__(16) uint4 ring[GATE_RING * 512];
+  if (p.dtype == DT_BF16) {
+    if (p.gate_dtype == DT_F32) gate_logits_impl<DT_F32, DT_BF16>(p, ring);
+    else if (p.gate_dtype == DT_BF16) gate_logits_impl<DT_BF16, DT_BF16>(p, ring);
+    else gate_logits_impl<DT_F16, DT_BF16>(p, ring);
+  } else {
+    if (p.gate_dtype == DT_F32) gate_logits_impl<DT_F32, DT_F16>(p, ring);
+    else if (p.gate_dtype == DT_BF16) gate_logits_impl<DT_BF16, DT_F16>(p, ring);
+    else gate_logits_impl<DT_F16, DT_F16>(p, ring);
   }
 }
 
@@ -785,7 +866,20 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   RouteParams q = p;
   if (!p.logits) {
     if (!p.logits_out) return cudaErrorInvalidValue;
-    gate_logits_kernel<<<(p.T + 7) / 8, 256, 0, st>>>(p);
+    {
+      const int ngroups = (p.E + 7) / 8;
+      const int nblocks = (p.T + GATE_TOK_PER_CTA - 1) / GATE_TOK_PER_CTA;
+      // expert groups are split over blockIdx.y so that (rounds of resident CTAs) x (chunks per CTA) is smallest;
+      // 2 CTAs fit per SM.  Ties -> fewer splits (each split re-reads the token rows).
+      const long long slots = 2LL * 148;
+      int gsplit = 1;
+      long long best = -1;
+      for (int g = 1; g <= ngroups; ++g) {
+        const long long cost = (((long long)nblocks * g + slots - 1) / slots) * ((ngroups + g - 1) / g);
+        if (best < 0 || cost < best) { best = cost; gsplit = g; }
+      }
+      gate_logits_kernel<<<dim3(nblocks, gsplit), 256, 0, st>>>(p);
+    }
     q.logits = p.logits_out;
     q.logits_dtype = p.router == ROUTER_MIXTRAL ? p.dtype : DT_F32;
     q.logits_are_scores = 0;

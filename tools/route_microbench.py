@@ -1,4 +1,4 @@
-"""Warm-cache timing of the routing / combine kernels in isolation (CUDA events, 200 iterations)."""
+"""Warm-cache timing of the routing / combine kernels in isolation (CUDA events around a CUDA graph of 200 calls)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "moe-infinity_b200"))
@@ -7,16 +7,29 @@ from moe_infinity_b200 import MoEEngine, _lib as L
 
 
 def t(fn, n=200):
-    for _ in range(20):
+    """per-call time in us of `fn` replayed n times inside ONE CUDA graph (what a kernel costs inside the step graph:
+    its run time + the dependent-launch gap; no Python / driver launch cost)"""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fn()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(n):
+                fn()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g.replay()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(n):
-        fn()
+    for _ in range(5):
+        g.replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / n * 1e3
+    return a.elapsed_time(b) / (5 * n) * 1e3
 
 
 def run(name, **kw):
