@@ -768,6 +768,8 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   c->k3_early_ok = k3_early && T >= 1 && T <= 256 && c->cfg.router != B2M_ROUTER_SWITCH_TOP1 && !ep_dispatch && !c->offload &&
                    !c->ep_mode && c->cfg.gemm_impl == 0;
   p.offsets_early = c->k3_early_ok ? 1 : 0;
+  static const bool rows_by_gate = !(getenv("B2M_ROWS_BY_GATE") && getenv("B2M_ROWS_BY_GATE")[0] == '0');
+  p.rows_by_gate = (c->k3_early_ok && rows_by_gate) ? 1 : 0;
   if (ep_dispatch) {
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;

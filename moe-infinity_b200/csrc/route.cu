@@ -445,7 +445,7 @@ __device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, in
 #pragma unroll
   for (int j = 0; j < MAX_K; ++j) {
     if (j < k) {
-      s_rows[lane * k + j] = dest[j];
+      if (s_rows) s_rows[lane * k + j] = dest[j];
       if (t < p.T && write_global) {
         p.row_of[(size_t)t * k + j] = dest[j];
         if (dest[j] >= 0) p.perm_token[dest[j]] = t;
@@ -689,10 +689,11 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   __syncthreads();
   if (threadIdx.x < p.E) {
     int run = 0;
-    for (int c = 0; c < nchunks; ++c) run += s_cnt2[c][threadIdx.x];
+    for (int c = 0; c < nchunks; ++c) { const int v = s_cnt2[c][threadIdx.x]; s_cnt2[c][threadIdx.x] = run; run += v; }   // -> exclusive chunk bases
     s_tot2[threadIdx.x] = run;
     p.counts[threadIdx.x] = run;
   }
+  __shared__ int s_off2[MAX_PL * 32 + 1];
   __syncthreads();
   if (warp == 0) {
     int v[MAX_PL], run = 0;
@@ -712,11 +713,18 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
 #pragma unroll
     for (int i = 0; i < MAX_PL; ++i) {
       const int e = lane * MAX_PL + i;
-      if (e < p.E) p.offsets[e] = base;
+      if (e < p.E) { p.offsets[e] = base; s_off2[e] = base; }
       base += v[i];
     }
-    if (lane == 31) p.offsets[p.E] = incl;
+    if (lane == 31) { p.offsets[p.E] = incl; s_off2[p.E] = incl; }
     if (lane == 0) *p.ticket = 0;
+  }
+  if (!p.rows_by_gate) return;
+  // publish the row maps as well (stable ascending-token order inside each expert): the permute kernel then only copies
+  __syncthreads();
+  for (int c = warp; c < nchunks; c += RT_WARPS) {
+    const int* cb = s_cnt2[c];
+    chunk_rank_warp(p, c * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, nullptr, s_idx2, true);
   }
 }
 
@@ -731,6 +739,24 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   const int npairs = p.T * p.k;
   pdl_launch();
   pdl_wait();
+  if (p.rows_by_gate) {
+    // the gate/top-k kernel already published counts, offsets and the row maps: this kernel is a pure row copy
+    const int vpr = p.H / 8;
+    for (int i = blockIdx.x; i < npairs; i += gridDim.x) {
+      const int row = p.row_of[i];
+      if (row < 0) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)(i / p.k) * p.H);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+      for (int v = threadIdx.x; v < vpr; v += RT_THREADS) dst[v] = src[v];
+    }
+    if (p.y_zero) {
+      float4* z = reinterpret_cast<float4*>(p.y_zero);
+      const size_t n4 = p.y_zero_elems / 4;
+      for (size_t i = (size_t)blockIdx.x * RT_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * RT_THREADS)
+        z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx[i] = p.topk_idx[i];
   __syncthreads();
   if (p.router == ROUTER_SWITCH_TOP1) {
