@@ -454,6 +454,42 @@ __device__ void chunk_rank_warp(const RouteParams& p, int t0, BaseFn base_of, in
   }
 }
 
+// Expert-strided variants for the last gate/top-k CTA: the (chunk, expert subset) tasks are spread over all warps of
+// the CTA instead of one warp walking all E experts of a chunk (64 dependent ballots for DeepSeek).
+__device__ __forceinline__ void chunk_count_strided(const int* idx_src, int t0, int T, int k, int E, int* counts_out,
+                                                    int e_begin, int e_step) {
+  const int lane = threadIdx.x & 31;
+  const int t = t0 + lane;
+  int idx[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < T && j < k) ? idx_src[(size_t)t * k + j] : -1;
+  for (int e = e_begin; e < E; e += e_step) {
+    const uint32_t b = __ballot_sync(0xffffffffu, lane_has(idx, k, e));
+    if (lane == 0) counts_out[e] = __popc(b);
+  }
+}
+template <class BaseFn>
+__device__ __forceinline__ void chunk_rank_strided(const RouteParams& p, int t0, BaseFn base_of, const int* idx_src,
+                                                   int e_begin, int e_step) {
+  const int lane = threadIdx.x & 31;
+  const int t = t0 + lane;
+  const int k = p.k;
+  int idx[MAX_K];
+#pragma unroll
+  for (int j = 0; j < MAX_K; ++j) idx[j] = (t < p.T && j < k) ? idx_src[(size_t)t * k + j] : -1;
+  for (int e = e_begin; e < p.E; e += e_step) {
+    const bool h = lane_has(idx, k, e);
+    const uint32_t b = __ballot_sync(0xffffffffu, h);
+    if (h) {
+      const int row = base_of(e) + __popc(b & ((1u << lane) - 1u));
+#pragma unroll
+      for (int j = 0; j < MAX_K; ++j)
+        if (j < k && idx[j] == e) p.row_of[(size_t)t * k + j] = row;
+      p.perm_token[row] = t;
+    }
+  }
+}
+
 // Copy gathered rows x[t] -> xp[row] with 16-byte vectors; `nrows` (token,slot) pairs starting at token t0.
 __device__ void copy_rows_block(const RouteParams& p, int t0, int npairs, const int* s_rows, int warp0, int nwarps) {
   const int lane = threadIdx.x & 31;
@@ -685,7 +721,8 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   const int nchunks = (p.T + CHUNK - 1) / CHUNK;
   for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx2[i] = __ldcg(p.topk_idx + i);   // other CTAs' results: L2
   __syncthreads();
-  if (warp < nchunks) chunk_count_warp(s_idx2, warp * CHUNK, p.T, p.k, p.E, s_cnt2[warp]);
+  for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS)   // (chunk, expert subset) tasks over all warps
+    chunk_count_strided(s_idx2, (task / RT_WARPS) * CHUNK, p.T, p.k, p.E, s_cnt2[task / RT_WARPS], task % RT_WARPS, RT_WARPS);
   __syncthreads();
   if (threadIdx.x < p.E) {
     int run = 0;
@@ -722,9 +759,9 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   if (!p.rows_by_gate) return;
   // publish the row maps as well (stable ascending-token order inside each expert): the permute kernel then only copies
   __syncthreads();
-  for (int c = warp; c < nchunks; c += RT_WARPS) {
-    const int* cb = s_cnt2[c];
-    chunk_rank_warp(p, c * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, nullptr, s_idx2, true);
+  for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS) {
+    const int* cb = s_cnt2[task / RT_WARPS];
+    chunk_rank_strided(p, (task / RT_WARPS) * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, s_idx2, task % RT_WARPS, RT_WARPS);
   }
 }
 
