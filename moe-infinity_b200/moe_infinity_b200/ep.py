@@ -227,7 +227,8 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     launches0 = eng.stats()["kernel_launches"]
     step()
     launches_per_step = eng.stats()["kernel_launches"] - launches0
-    # one CUDA graph per 32-layer step (NCCL all-to-alls are captured too); fall back to eager launches
+    # one CUDA graph per 32-layer step (the exchange -- peer-to-peer kernels or NCCL all-to-alls -- is captured too);
+    # fall back to eager launches
     eager_step = step
     timed = "eager launches"
     if not os.environ.get("B2M_EP_NO_GRAPH"):
@@ -244,7 +245,8 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                 eager_step()
             torch.cuda.synchronize()
             step = graph.replay
-            timed = "CUDA graph replay of the step (kernels + NCCL all-to-all)"
+            timed = ("CUDA graph replay of the step (kernels incl. the peer-to-peer exchange)" if use_p2p
+                     else "CUDA graph replay of the step (kernels + NCCL all-to-all)")
             for _ in range(3):
                 step()
             torch.cuda.synchronize()
