@@ -104,3 +104,45 @@ def test_decode_session_graph_matches_eager(lib_built):
             torch.cuda.synchronize()
             assert torch.equal(out[l].cuda(), want), (it, l)
     assert eng.stats()["host_syncs"] == 0
+
+
+@pytest.mark.parametrize("router", ["mixtral", "deepseek"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("E,k,H,T", [(8, 2, 4096, 300), (12, 3, 200, 257), (64, 6, 2048, 700), (33, 5, 72, 1000),
+                                     (256, 8, 264, 513), (8, 2, 1000, 19), (64, 6, 200, 16)])
+def test_fused_gate_sweep(router, dtype, E, k, H, T, lib_built):
+    """K0 computed in-kernel (no router input): the prefill gate GEMM (T > 256: cp.async-staged gate chunks, expert groups
+    split over blockIdx.y, H and E tails) and the decode gate.  Logits vs an fp64 product: Mixtral rounds to the model
+    dtype (mixtral.py:46) -> within 1 ulp; DeepSeek keeps fp32 (modeling_deepseek.py:467-471) -> rel 2e-5.
+    Expert indices must equal the oracle's routing of the GPU's own logits exactly (ties excluded)."""
+    from moe_infinity_b200 import _lib as L
+    mix = router == "mixtral"
+    eng = _engine(E, k, H, L.ROUTER_MIXTRAL if mix else L.ROUTER_DEEPSEEK_GREEDY, dtype=dtype, max_tokens=1024)
+    g = torch.Generator().manual_seed(E * 7 + H + T)
+    x = torch.randn(T, H, generator=g).to(dtype)
+    w = (torch.randn(E, H, generator=g) * (2.0 / H ** 0.5)).to(dtype if mix else torch.float32)
+    eng.set_gate(0, w)
+    eng.route(0, x.cuda())
+    torch.cuda.synchronize()
+    lg = eng.ws("logits", T).cpu()
+    exact = x.double() @ w.double().t()
+    if mix:
+        eps = torch.finfo(dtype).eps
+        assert lg.dtype == dtype
+        assert torch.all((lg.double() - exact).abs() <= eps * exact.abs() + 1e-4), "gate logits beyond 1 ulp"
+        r = O.mixtral_route(lg, k, dtype)
+        check_indices(eng.ws("topk_idx", T), r.topk_idx, O.tied_tokens(r.scores, k))
+    else:
+        assert lg.dtype == torch.float32
+        assert torch.allclose(lg.double(), exact, rtol=2e-5, atol=2e-5)
+        scores = torch.softmax(lg, dim=-1, dtype=torch.float32)
+        r = O.deepseek_route(scores, k)
+        near = O.tied_tokens(r.scores, k)
+        gi = eng.ws("topk_idx", T).cpu().long()
+        # softmax on the GPU differs from CPU torch by <= 2 ulp(fp32): exclude tokens whose k-th/(k+1)-th scores are that close
+        srt = scores.sort(-1, descending=True).values
+        if E > k:
+            near |= (srt[:, k - 1] - srt[:, k]).abs() <= 4e-7 * srt[:, k - 1]
+        assert near.float().mean() < 0.05
+        assert torch.equal(gi[~near].sort(-1).values, r.topk_idx[~near].sort(-1).values)
+    check_permutation(eng, x.cuda(), T)
