@@ -56,3 +56,6 @@ def run(name, **kw):
 run("mixtral T=8 ", T=8, num_experts=8, hidden=4096, inter=14336, top_k=2)
 run("deepseek T=16", T=16, num_experts=64, hidden=2048, inter=1408, top_k=6, expert_type=L.EXPERT_DEEPSEEK,
     router=L.ROUTER_DEEPSEEK_GREEDY, shared_inter=2816)
+# what do the shared experts (side stream + join) cost a DeepSeek decode layer?
+run("deepseek T=16 (no shared experts)", T=16, num_experts=64, hidden=2048, inter=1408, top_k=6,
+    expert_type=L.EXPERT_DEEPSEEK, router=L.ROUTER_DEEPSEEK_GREEDY)
