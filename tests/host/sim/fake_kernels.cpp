@@ -1,0 +1,155 @@
+// TEST INFRASTRUCTURE ONLY: host stand-ins for the kernel launchers declared in csrc/b2m_internal.h, linked with
+// csrc/api.cu and fake_cudart.cpp into libb2m_hostsim.so.  The routing launchers compute what the host logic consumes
+// (top-k ids, per-expert counts, offsets, row maps) with plain loops; the GEMM / combine / exchange launchers do no
+// arithmetic but RECORD the launch (tile shape, split-K plan, programmatic-edge flags and the slot table the kernel
+// would have read) so that tests/test_host_sim.py can check the planning and residency decisions of api.cu on a CPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2m_internal.h"
+
+namespace {
+std::mutex g_mu;
+std::string g_log;
+
+float half_to_float(uint16_t h) {
+  const uint32_t s = (h >> 15) & 1, e = (h >> 10) & 31, m = h & 1023;
+  float v;
+  if (e == 0) v = std::ldexp((float)m, -24);
+  else if (e == 31) v = m ? NAN : INFINITY;
+  else v = std::ldexp((float)(m | 1024), (int)e - 25);
+  return s ? -v : v;
+}
+float as_float(const void* p, size_t i, int dt) {
+  if (dt == 1 /*DT_F32*/) return reinterpret_cast<const float*>(p)[i];
+  const uint16_t b = reinterpret_cast<const uint16_t*>(p)[i];
+  if (dt == 0 /*DT_BF16*/) { uint32_t u = (uint32_t)b << 16; float f; std::memcpy(&f, &u, 4); return f; }
+  return half_to_float(b);
+}
+void logf(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_log += buf;
+  g_log += '\n';
+}
+std::string ints(const int* p, int n) {
+  std::string s = "[";
+  for (int i = 0; i < n; ++i) { s += std::to_string(p ? p[i] : 0); if (i + 1 < n) s += ","; }
+  return s + "]";
+}
+
+// counts / offsets / stable row maps from topk_idx (what route.cu's rank kernels produce)
+void finish_routing(const b2m::RouteParams& p) {
+  std::vector<int> counts(p.E, 0);
+  for (int t = 0; t < p.T; ++t)
+    for (int j = 0; j < p.k; ++j) { const int e = p.topk_idx[(size_t)t * p.k + j]; if (e >= 0) ++counts[e]; }
+  int run = 0;
+  for (int e = 0; e < p.E; ++e) { p.counts[e] = counts[e]; p.offsets[e] = run; run += counts[e]; }
+  p.offsets[p.E] = run;
+  std::vector<int> next(p.offsets, p.offsets + p.E);
+  for (int t = 0; t < p.T; ++t)
+    for (int j = 0; j < p.k; ++j) {
+      const int e = p.topk_idx[(size_t)t * p.k + j];
+      int row = -1;
+      if (e >= 0) { row = next[e]++; p.perm_token[row] = t; }
+      p.row_of[(size_t)t * p.k + j] = row;
+    }
+  if (p.y_zero) std::memset(p.y_zero, 0, p.y_zero_elems * sizeof(float));
+}
+}  // namespace
+
+extern "C" {
+// hand the launch log to the test and clear it; returns the number of bytes the full log needs
+size_t b2m_sim_take_log(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const size_t n = g_log.size();
+  if (buf && cap) {
+    const size_t m = std::min(n, cap - 1);
+    std::memcpy(buf, g_log.data(), m);
+    buf[m] = 0;
+  }
+  g_log.clear();
+  return n;
+}
+}
+
+namespace b2m {
+
+cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
+  if (p.T == 0) { std::memset(p.offsets, 0, sizeof(int) * (p.E + 1)); return cudaSuccess; }
+  for (int t = 0; t < p.T; ++t) {
+    std::vector<float> s(p.E);
+    for (int e = 0; e < p.E; ++e) {
+      if (p.logits) {
+        s[e] = as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
+      } else {
+        double acc = 0;
+        for (int h = 0; h < p.H; ++h)
+          acc += (double)as_float(p.x, (size_t)t * p.H + h, p.dtype) * as_float(p.gate_w, (size_t)e * p.H + h, p.gate_dtype);
+        s[e] = (float)acc;
+      }
+    }
+    // softmax is monotonic: top-k of the logits, ties to the lowest index (oracle/moe_oracle.py topk_lowest_index)
+    std::vector<int> order(p.E);
+    for (int e = 0; e < p.E; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s[a] > s[b]; });
+    for (int j = 0; j < p.k; ++j) {
+      p.topk_idx[(size_t)t * p.k + j] = order[j];
+      p.topk_w[(size_t)t * p.k + j] = 1.0f / p.k;
+    }
+  }
+  finish_routing(p);
+  logf("route T=%d offsets_early=%d rows_by_gate=%d ep_dispatch=%d counts=%s", p.T, p.offsets_early, p.rows_by_gate,
+       p.ep_dispatch, ints(p.counts, p.E).c_str());
+  return cudaSuccess;
+}
+
+cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cudaStream_t) {
+  for (int t = 0; t < p.T; ++t) {
+    int j = 0;
+    for (int e = 0; e < p.E && j < p.k; ++e)
+      if (mask[(size_t)t * p.E + e]) { p.topk_idx[(size_t)t * p.k + j] = e; p.topk_w[(size_t)t * p.k + j] = 1.f; ++j; }
+    for (; j < p.k; ++j) { p.topk_idx[(size_t)t * p.k + j] = -1; p.topk_w[(size_t)t * p.k + j] = 0.f; }
+  }
+  finish_routing(p);
+  logf("route_from_mask T=%d counts=%s", p.T, ints(p.counts, p.E).c_str());
+  return cudaSuccess;
+}
+
+static cudaError_t log_gemm(const char* kind, int nt, bool dual, const GemmParams& p) {
+  logf("gemm impl=%s nt=%d dual=%d M=%d K=%d ksplit=%d stream_k=%d epi=%d act=%d mimic=%d early_a=%d dual_m=%d bias=%d "
+       "single_n=%d single_slot=%d slot_of=%s offsets=%s",
+       kind, nt, (int)dual, p.M, p.K, p.ksplit, p.stream_k, p.epi, p.act, p.mimic, p.early_a, p.dual_m,
+       p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.single_n >= 0 ? "[]" : ints(p.slot_of, p.E).c_str(),
+       p.single_n >= 0 ? "[]" : ints(p.offsets, p.E + 1).c_str());
+  return cudaSuccess;
+}
+cudaError_t launch_grouped_gemm_tc(int, int nt, bool dual, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                                   const GemmParams& p, int, cudaStream_t) { return log_gemm("tc", nt, dual, p); }
+cudaError_t launch_grouped_gemm_tc_mc2(int, bool dual, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                                       const GemmParams& p, int, cudaStream_t) { return log_gemm("tc_mc2", 128, dual, p); }
+cudaError_t launch_grouped_gemm_simt(int, const void*, size_t, size_t, size_t, const void*, int, const GemmParams& p,
+                                     bool dual, cudaStream_t) { return log_gemm("simt", 0, dual, p); }
+int gemm_tc_smem_bytes(int, bool) { return 200 * 1024; }
+
+cudaError_t launch_combine(const CombineParams& p, cudaStream_t) {
+  logf("combine T=%d mode=%d shared=%d ep_collect=%d", p.T, p.mode, p.y_shared ? 1 : 0, p.ep_collect);
+  return cudaSuccess;
+}
+cudaError_t launch_cast_rows(const float*, void*, size_t n, int, cudaStream_t) { logf("cast_rows n=%zu", n); return cudaSuccess; }
+cudaError_t launch_ep_pack(const EpParams&, int, cudaStream_t) { logf("ep_pack"); return cudaSuccess; }
+cudaError_t launch_ep_regroup(const EpParams&, cudaStream_t) { logf("ep_regroup"); return cudaSuccess; }
+cudaError_t launch_ep_ungroup(const EpParams&, int, cudaStream_t) { logf("ep_ungroup"); return cudaSuccess; }
+cudaError_t launch_ep_unpack(const EpParams&, int, int, cudaStream_t) { logf("ep_unpack"); return cudaSuccess; }
+
+}  // namespace b2m

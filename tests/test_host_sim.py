@@ -1,0 +1,314 @@
+"""CPU: the HOST logic of the C-ABI layer (moe-infinity_b200/csrc/api.cu, compiled unchanged) executed without a GPU.
+
+tests/host/sim/ links api.cu against a host emulation of the CUDA runtime (device memory = host memory, copies = memcpy,
+streams/events complete immediately) and stand-in kernel launchers that compute the routing tables with plain loops and
+RECORD every GEMM launch.  What is checked here is everything api.cu decides on the host:
+  * the HBM expert cache reproduces oracle/policy_oracle.py's hit / miss / eviction sequence and residency map, with
+    prefetch hints, protected candidates and wave splitting when one layer's active set exceeds the slot budget;
+  * a staged slot really holds the expert's host blob (right bytes in the right slot after evictions and re-use);
+  * launch planning: token-tile width, split-K / stream-K, programmatic-edge flags, slot tables handed to the kernels;
+  * argument / state errors are reported through return codes + b2m_last_error, never by aborting.
+The product library is not involved (it refuses to create a context without a GPU: tests/test_cabi_symbols.py)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "host", "sim"))
+
+import build_sim  # noqa: E402
+from moe_infinity_b200 import _lib as L  # noqa: E402
+from oracle.policy_oracle import CacheOracle  # noqa: E402
+
+_SO = build_sim.build()
+pytestmark = pytest.mark.skipif(_SO is None, reason="nvcc / g++ not available to build the host simulation")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    lib = C.CDLL(_SO)
+    for name, res, args in L.SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib.b2m_sim_take_log.restype, lib.b2m_sim_take_log.argtypes = C.c_size_t, [C.c_char_p, C.c_size_t]
+    lib.b2m_sim_h2d_bytes.restype = C.c_longlong
+    lib.b2m_sim_live_allocs.restype = C.c_longlong
+    return lib
+
+
+class Ctx:
+    """Minimal driver of the C ABI with host buffers (the simulation's 'device' pointers are host pointers)."""
+
+    def __init__(self, lib, L_=3, E=8, H=128, I=256, k=2, max_tokens=64, expert_type=L.EXPERT_MIXTRAL, **kw):
+        self.lib, self.L, self.E, self.H, self.I, self.k = lib, L_, E, H, I, k
+        cfg = L.Config()
+        cfg.struct_size = C.sizeof(L.Config)
+        cfg.num_layers, cfg.num_experts, cfg.hidden, cfg.inter, cfg.top_k = L_, E, H, I, k
+        cfg.dtype, cfg.expert_type, cfg.router, cfg.max_tokens = L.DTYPE_BF16, expert_type, kw.pop("router", L.ROUTER_MIXTRAL), max_tokens
+        cfg.gate_dtype = L.DTYPE_BF16
+        cfg.device_memory_ratio = 0.5
+        cfg.routed_scaling_factor = 1.0
+        for key, v in kw.items():
+            setattr(cfg, key, v)
+        self.h = C.c_void_p()
+        self.rc = lib.b2m_ctx_create(C.byref(cfg), C.byref(self.h))
+        self.blobs = {}
+
+    def err(self):
+        return (self.lib.b2m_last_error(self.h) or b"").decode()
+
+    def close(self):
+        if self.h:
+            self.lib.b2m_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def expert_bytes(self):
+        return 3 * self.H * self.I * 2          # w1 | w2 | w3 (the Mixtral blob these tests register)
+
+    def register_all(self, seed=0):
+        rng = np.random.default_rng(seed)
+        for l in range(self.L):
+            for e in range(self.E):
+                blob = rng.integers(0, 255, self.expert_bytes(), dtype=np.uint8)
+                self.blobs[(l, e)] = blob
+                assert self.lib.b2m_register_expert(self.h, l, e, blob.ctypes.data, blob.nbytes) == 0, self.err()
+
+    def forward(self, layer, logits_f32):
+        T = logits_f32.shape[0]
+        x = np.zeros((T, self.H), dtype=np.uint16)
+        out = np.zeros((T, self.H), dtype=np.uint16)
+        lg = np.ascontiguousarray(logits_f32, dtype=np.float32)
+        rc = self.lib.b2m_moe_forward(self.h, layer, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, out.ctypes.data, None)
+        return rc
+
+    def stats(self):
+        s = L.Stats()
+        assert self.lib.b2m_stats_get(self.h, C.byref(s)) == 0
+        return s.as_dict()
+
+    def counts(self):
+        # straight from the workspace (host memory in the simulation); b2m_last_counts only answers after an offload-mode call
+        p = C.c_void_p()
+        assert self.lib.b2m_ws_ptr(self.h, L.WS["counts"], C.byref(p)) == 0, self.err()
+        return list((C.c_int32 * self.E).from_address(p.value))
+
+    def resident(self, l, e):
+        return bool(self.lib.b2m_is_resident(self.h, l, e))
+
+    def slot_bytes(self, l, e):
+        p = C.c_void_p()
+        assert self.lib.b2m_expert_dev_ptr(self.h, l, e, C.byref(p)) == 0
+        return None if not p.value else np.ctypeslib.as_array((C.c_uint8 * self.expert_bytes()).from_address(p.value))
+
+
+def take_log(lib):
+    buf = C.create_string_buffer(1 << 20)
+    lib.b2m_sim_take_log(buf, len(buf))
+    return [ln for ln in buf.value.decode().split("\n") if ln]
+
+
+def _kv(line):
+    return {m.group(1): m.group(2) for m in re.finditer(r"(\w+)=(\[[^\]]*\]|\S+)", line)}
+
+
+def test_cache_policy_matches_oracle_on_cpu(sim):
+    for nslots, seed in ((10, 2), (9, 3), (8, 4)):
+        c = Ctx(sim, num_slots=nslots)
+        assert c.rc == 0, c.err()
+        c.register_all(seed)
+        orc = CacheOracle(c.L, c.E, nslots)
+        rng = np.random.default_rng(seed)
+        h2d0 = sim.b2m_sim_h2d_bytes()
+        for step in range(12):
+            for l in range(c.L):
+                lg = rng.standard_normal((5, c.E)).astype(np.float32)
+                before = {e: c.resident(l, e) for e in range(c.E)}
+                assert c.forward(l, lg) == 0, c.err()
+                cnt = c.counts()
+                active = [e for e in range(c.E) if cnt[e] > 0]
+                # the stand-in router is top-2 of the logits, lowest index on ties
+                want = sorted(set(np.argsort(-lg, axis=1, kind="stable")[:, :2].flatten().tolist()))
+                assert active == want
+                assert [(e, before[e]) for e in active] == orc.dispatch(l, active), (nslots, step, l)
+                for ll in range(c.L):
+                    for e in range(c.E):
+                        assert c.resident(ll, e) == orc.resident[ll * c.E + e]
+                # every resident expert's slot holds exactly its host blob
+                for e in active:
+                    assert np.array_equal(c.slot_bytes(l, e), c.blobs[(l, e)])
+        s = c.stats()
+        for key in ("dispatches", "hits", "misses", "evictions"):
+            assert s[key] == orc.stats[key], (nslots, key)
+        assert s["h2d_bytes"] == s["misses"] * c.expert_bytes()
+        assert s["host_syncs"] == 12 * c.L          # one count read-back per layer call (the reference's own sync point)
+        lc = (C.c_int32 * c.E)()
+        assert sim.b2m_last_counts(c.h, lc) == 0 and list(lc) == c.counts()
+        assert s["resident"] <= nslots
+        assert sim.b2m_sim_h2d_bytes() - h2d0 >= s["h2d_bytes"]
+        c.close()
+
+
+def test_all_resident_mode_never_syncs_on_cpu(sim):
+    c = Ctx(sim, num_slots=24)                 # L*E slots: every expert fits
+    c.register_all(4)
+    rng = np.random.default_rng(4)
+    for step in range(3):
+        for l in range(c.L):
+            assert c.forward(l, rng.standard_normal((5, c.E)).astype(np.float32)) == 0, c.err()
+    s = c.stats()
+    assert s["host_syncs"] == 0 and s["evictions"] == 0 and s["resident"] == 24
+    lc = (C.c_int32 * c.E)()
+    assert sim.b2m_last_counts(c.h, lc) != 0 and "sync-free" in c.err()
+    for (l, e), blob in c.blobs.items():
+        assert np.array_equal(c.slot_bytes(l, e), blob)
+    c.close()
+
+
+def test_prefetch_hints_protect_and_count_on_cpu(sim):
+    nslots = 11
+    c = Ctx(sim, num_slots=nslots)
+    c.register_all(9)
+    orc = CacheOracle(c.L, c.E, nslots)
+    rng = np.random.default_rng(0)
+    for step in range(10):
+        for l in range(c.L):
+            lg = rng.standard_normal((4, c.E)).astype(np.float32)
+            assert c.forward(l, lg) == 0, c.err()
+            cnt = c.counts()
+            orc.dispatch(l, [e for e in range(c.E) if cnt[e] > 0])
+            nl = (l + 1) % c.L
+            cand = rng.choice(c.E, size=3, replace=False).tolist()
+            scores = rng.random(3).astype(np.float32)
+            pairs = (C.c_int32 * 6)(*[v for e in cand for v in (nl, int(e))])
+            assert sim.b2m_prefetch_hint(c.h, 3, pairs, scores.ctypes.data_as(C.POINTER(C.c_float))) == 0, c.err()
+            assert sim.b2m_prefetch_drain(c.h) == 0, c.err()
+            orc.prefetch_hint([(nl, int(e)) for e in cand], scores.tolist())
+            for ll in range(c.L):
+                for e in range(c.E):
+                    assert c.resident(ll, e) == orc.resident[ll * c.E + e], (step, l, ll, e)
+    s = c.stats()
+    for key in ("dispatches", "hits", "misses", "evictions", "prefetch_issued", "prefetch_useful"):
+        assert s[key] == orc.stats[key], key
+    assert s["prefetch_issued"] > 0 and s["prefetch_useful"] > 0
+    c.close()
+
+
+def test_fewer_slots_than_active_experts_runs_in_waves_on_cpu(sim):
+    """With fewer slots than activated experts the GEMMs are launched wave by wave, each against a slot row that names only
+    that wave's experts (-1 elsewhere), and every activated expert is covered exactly once."""
+    for nslots in (1, 2, 3):
+        c = Ctx(sim, num_slots=nslots)
+        c.register_all(13)
+        orc = CacheOracle(c.L, c.E, nslots)
+        rng = np.random.default_rng(nslots)
+        take_log(sim)
+        for step in range(3):
+            for l in range(c.L):
+                lg = rng.standard_normal((6, c.E)).astype(np.float32)
+                assert c.forward(l, lg) == 0, c.err()
+                cnt = c.counts()
+                active = [e for e in range(c.E) if cnt[e] > 0]
+                orc.dispatch(l, active)
+                gemms = [_kv(ln) for ln in take_log(sim) if ln.startswith("gemm")]
+                ups = [g for g in gemms if g["epi"] == "0"]
+                assert len(ups) == len(gemms) // 2 and len(ups) >= -(-len(active) // nslots)
+                covered = []
+                for g in ups:
+                    row = eval(g["slot_of"])
+                    wave = [e for e in range(c.E) if row[e] >= 0]
+                    assert 1 <= len(wave) <= nslots and len(set(row[e] for e in wave)) == len(wave)
+                    covered += [e for e in wave if e in active]
+                assert sorted(covered) == active          # each activated expert in exactly one wave
+        s = c.stats()
+        for key in ("dispatches", "hits", "misses", "evictions"):
+            assert s[key] == orc.stats[key], (nslots, key)
+        c.close()
+
+
+def test_launch_planning_on_cpu(sim):
+    """Token-tile width, split-K / stream-K and programmatic-edge flags chosen by api.cu (pick_nt / pick_ksplit)."""
+    # Mixtral-8x7B shapes need 2.8 GB per layer of fake HBM; use the same ratios at 1/8 size: H=512, I=1792
+    c = Ctx(sim, L_=1, E=8, H=512, I=1792, k=2, max_tokens=4096, num_slots=8)
+    assert c.rc == 0, c.err()
+    c.register_all(1)
+    rng = np.random.default_rng(5)
+    take_log(sim)
+    plans = {}
+    for T in (1, 8, 40, 300, 4096):
+        assert c.forward(0, rng.standard_normal((T, c.E)).astype(np.float32)) == 0, c.err()
+        lines = take_log(sim)
+        route = _kv([ln for ln in lines if ln.startswith("route")][0])
+        up, dn = [_kv(ln) for ln in lines if ln.startswith("gemm")]
+        assert up["epi"] == "0" and dn["epi"] == "1" and up["dual"] == "1" and up["M"] == "1792" and dn["M"] == "512"
+        assert eval(up["offsets"])[-1] == T * 2
+        plans[T] = (int(up["nt"]), int(dn["nt"]), int(dn["ksplit"]), int(dn["stream_k"]), int(up["early_a"]), int(dn["early_a"]),
+                    int(route["offsets_early"]), int(dn["dual_m"]))
+    # decode-sized batches: 16-token tiles, split-K with the stream-K partition, both GEMMs on programmatic edges
+    for T in (1, 8):
+        nt, ntd, ks, sk, ea_up, ea_dn, early, dual_m = plans[T]
+        assert nt == 16 and ntd == 16 and ks > 1 and sk == 1 and ea_up == 1 and ea_dn == 1 and early == 1 and dual_m == 0
+    assert plans[300][0] in (64, 128) and plans[300][6] == 0
+    # few weight-row tiles (H=512 -> 4 m-tiles): even at T=4096 the planner splits K to fill the SMs
+    assert plans[4096][0] == 256 and plans[4096][2] > 1 and plans[4096][5] == 0 and plans[4096][6] == 0
+    c.close()
+    # prefill with Mixtral's hidden size (32 m-tiles x 8 experts x 4 token tiles = 1024 tiles): 256-token tiles once the
+    # average expert sees >= 256 tokens, no split-K, paired m-tiles (dual_m) in the down projection, no programmatic edges
+    c = Ctx(sim, L_=1, E=8, H=4096, I=256, k=2, max_tokens=4096, num_slots=8)
+    assert c.rc == 0, c.err()
+    c.register_all(2)
+    take_log(sim)
+    assert c.forward(0, rng.standard_normal((4096, c.E)).astype(np.float32)) == 0, c.err()
+    up, dn = [_kv(ln) for ln in take_log(sim) if ln.startswith("gemm")]
+    assert (up["nt"], dn["nt"], dn["ksplit"], dn["stream_k"], up["early_a"], dn["early_a"], dn["dual_m"]) == \
+        ("256", "256", "1", "0", "0", "0", "1")
+    c.close()
+
+
+def test_bias_experts_plan_whole_k_on_cpu(sim):
+    c = Ctx(sim, L_=1, E=4, H=128, I=256, k=2, num_slots=4, expert_type=L.EXPERT_NLLB)
+    assert c.rc == 0, c.err()
+    nbytes = 2 * 128 * 256 * 2 + (256 + 128) * 2
+    blob = np.zeros(nbytes, dtype=np.uint8)
+    assert sim.b2m_register_expert(c.h, 0, 0, blob.ctypes.data, nbytes - 2) != 0 and "bytes" in c.err()
+    for e in range(4):
+        assert sim.b2m_register_expert(c.h, 0, e, blob.ctypes.data, nbytes) == 0, c.err()
+    take_log(sim)
+    assert c.forward(0, np.random.default_rng(0).standard_normal((3, 4)).astype(np.float32)) == 0, c.err()
+    up, dn = [_kv(ln) for ln in take_log(sim) if ln.startswith("gemm")]
+    assert up["bias"] == "1" and dn["bias"] == "1" and dn["ksplit"] == "1" and dn["stream_k"] == "0" and up["dual"] == "0"
+    c.close()
+
+
+def test_errors_are_reported_not_fatal_on_cpu(sim):
+    bad = Ctx(sim, top_k=9)
+    assert bad.rc == L.B2M_EINVAL
+    assert Ctx(sim, dtype=L.DTYPE_F32).rc == L.B2M_EUNSUPPORTED
+    assert Ctx(sim, expert_type=6).rc != 0
+    c = Ctx(sim, num_slots=4)
+    assert c.rc == 0
+    lg = np.zeros((3, c.E), dtype=np.float32)
+    assert c.forward(0, lg) != 0 and "registered" in c.err()            # experts never registered
+    c.register_all(0)
+    assert c.forward(7, lg) != 0                                           # layer out of range
+    assert c.forward(0, np.zeros((65, c.E), dtype=np.float32)) != 0 and "capacity" in c.err()
+    assert sim.b2m_run_experts(c.h, 0, 5, None) != 0 and "routing call" in c.err()
+    assert c.forward(0, lg) == 0, c.err()                                  # the context is still usable
+    assert sim.b2m_register_expert(c.h, 0, 0, c.blobs[(0, 0)].ctypes.data, 10) != 0
+    c.close()
+    assert sim.b2m_ctx_destroy(None) in (0, L.B2M_EINVAL)
+
+
+def test_context_releases_everything_on_cpu(sim):
+    live0 = sim.b2m_sim_live_allocs()
+    for _ in range(3):
+        c = Ctx(sim, num_slots=6, shared_inter=0)
+        c.register_all(2)
+        assert c.forward(1, np.random.default_rng(1).standard_normal((9, c.E)).astype(np.float32)) == 0
+        c.close()
+    assert sim.b2m_sim_live_allocs() == live0, "device / pinned allocations leaked across ctx_create/destroy"
