@@ -312,3 +312,107 @@ def test_context_releases_everything_on_cpu(sim):
         assert c.forward(1, np.random.default_rng(1).standard_normal((9, c.E)).astype(np.float32)) == 0
         c.close()
     assert sim.b2m_sim_live_allocs() == live0, "device / pinned allocations leaked across ctx_create/destroy"
+
+
+def test_chunked_copies_and_pinned_experts_on_cpu(sim):
+    """h2d_chunk_bytes splits a staging copy into many pieces (so a miss can overtake a prefetch between pieces): the slot
+    must still end up holding the whole blob.  Experts pinned with b2m_make_resident(flags=1) are never chosen as victims."""
+    c = Ctx(sim, num_slots=9, h2d_chunk_bytes=64 * 1024)
+    c.register_all(21)
+    for e in (0, 1):
+        assert sim.b2m_make_resident(c.h, 0, e, 1, None) == 0, c.err()       # pin (0,0) and (0,1)
+    rng = np.random.default_rng(21)
+    for step in range(12):
+        for l in range(c.L):
+            lg = rng.standard_normal((6, c.E)).astype(np.float32)
+            lg[:, :2] -= 10.0                                                  # the pinned experts are never routed to
+            assert c.forward(l, lg) == 0, c.err()
+            cnt = c.counts()
+            for e in range(c.E):
+                if cnt[e] > 0:
+                    assert np.array_equal(c.slot_bytes(l, e), c.blobs[(l, e)])
+            assert c.resident(0, 0) and c.resident(0, 1), "a pinned expert was evicted"
+    s = c.stats()
+    assert s["evictions"] > 10 and s["h2d_bytes"] == (s["misses"] + 2) * c.expert_bytes()   # + the two explicit stagings
+    for e in (0, 1):
+        assert np.array_equal(c.slot_bytes(0, e), c.blobs[(0, e)])
+    c.close()
+
+
+def test_reference_prefetch_pair_and_count_reset_on_cpu(sim):
+    """replace_cache_candidates + enqueue_prefetch (archer_prefetch_handle.cpp:195-218) and clear_expert_cache_counts
+    (interface_example.py:39) against the policy oracle."""
+    nslots = 10
+    c = Ctx(sim, num_slots=nslots)
+    c.register_all(33)
+    orc = CacheOracle(c.L, c.E, nslots)
+    rng = np.random.default_rng(33)
+    for step in range(9):
+        for l in range(c.L):
+            lg = rng.standard_normal((4, c.E)).astype(np.float32)
+            assert c.forward(l, lg) == 0, c.err()
+            cnt = c.counts()
+            orc.dispatch(l, [e for e in range(c.E) if cnt[e] > 0])
+            nl = (l + 1) % c.L
+            cand = [(nl, int(e)) for e in rng.choice(c.E, size=2, replace=False)]
+            flat = (C.c_int32 * 4)(*[v for pr in cand for v in pr])
+            assert sim.b2m_replace_cache_candidates(c.h, 2, flat) == 0, c.err()
+            orc.replace_cache_candidates(cand)
+            for (ll, e) in cand:
+                assert sim.b2m_enqueue_prefetch(c.h, ll, e) == 0, c.err()
+            assert sim.b2m_prefetch_drain(c.h) == 0, c.err()
+            orc.prefetch(cand)
+            for ll in range(c.L):
+                for e in range(c.E):
+                    assert c.resident(ll, e) == orc.resident[ll * c.E + e], (step, l, ll, e)
+        if step == 4:
+            assert sim.b2m_clear_expert_cache_counts(c.h) == 0
+            orc.clear_counts()
+    s = c.stats()
+    for key in ("dispatches", "hits", "misses", "evictions", "prefetch_issued", "prefetch_useful"):
+        assert s[key] == orc.stats[key], key
+    c.close()
+
+
+def test_staged_calls_and_deepseek_shared_experts_on_cpu(sim):
+    """The reference-compatible staged sequence (set_inputs -> enqueue/wait -> python combine = b2m_route_from_mask ->
+    b2m_run_experts -> b2m_expert_outputs) and the DeepSeek flow with shared experts forked beside the routed path."""
+    E, H, I, T = 8, 128, 128, 7
+    c = Ctx(sim, L_=2, E=E, H=H, I=I, k=3, num_slots=16, expert_type=L.EXPERT_DEEPSEEK, router=L.ROUTER_DEEPSEEK_GREEDY,
+            shared_inter=2 * I, gate_dtype=L.DTYPE_F32)
+    assert c.rc == 0, c.err()
+    c.register_all(5)
+    shared = np.zeros(3 * H * 2 * I * 2, dtype=np.uint8)
+    assert sim.b2m_register_shared(c.h, 0, shared.ctypes.data, shared.nbytes - 16) != 0
+    for l in range(2):
+        assert sim.b2m_register_shared(c.h, l, shared.ctypes.data, shared.nbytes) == 0, c.err()
+    take_log(sim)
+    scores = np.random.default_rng(1).random((T, E)).astype(np.float32)
+    x = np.zeros((T, H), dtype=np.uint16)
+    out = np.zeros((T, H), dtype=np.uint16)
+    assert sim.b2m_moe_forward(c.h, 1, x.ctypes.data, scores.ctypes.data, 2, L.DTYPE_F32, T, 0, out.ctypes.data, None) == 0, c.err()
+    lines = take_log(sim)
+    gemms = [_kv(ln) for ln in lines if ln.startswith("gemm")]
+    assert len(gemms) == 4
+    shared_g = [g for g in gemms if g["single_n"] == str(T)]
+    assert len(shared_g) == 2 and all(g["single_slot"] == "1" for g in shared_g) and shared_g[0]["M"] == str(2 * I)
+    assert [ln for ln in lines if ln.startswith("combine")] == [f"combine T={T} mode=1 shared=1 ep_collect=0"]
+    # bf16 scores are refused (modeling_deepseek.py:473 computes them in fp32)
+    assert sim.b2m_moe_forward(c.h, 1, x.ctypes.data, scores.ctypes.data, 2, L.DTYPE_BF16, T, 0, out.ctypes.data, None) != 0
+    assert "fp32" in c.err()
+    take_log(sim)
+    # staged calls from a dense mask
+    mask = np.zeros((T, E), dtype=np.uint8)
+    mask[:, 2] = 1
+    mask[::2, 5] = 1
+    assert sim.b2m_route_from_mask(c.h, 0, x.ctypes.data, mask.ctypes.data, T, None) == 0, c.err()
+    assert sim.b2m_run_experts_ex(c.h, 0, T, 1, None) == 0, c.err()            # gate/up phase only
+    assert sim.b2m_run_experts_ex(c.h, 0, T, 2, None) == 0, c.err()            # down phase
+    rows = np.zeros((T * 3, H), dtype=np.uint16)
+    offs = (C.c_int * (E + 1))()
+    assert sim.b2m_expert_outputs(c.h, T, rows.ctypes.data, offs, None) == 0, c.err()
+    assert list(offs) == [0, 0, 0, T, T, T, T + 4, T + 4, T + 4]
+    lines = take_log(sim)
+    assert [ln.split()[0] for ln in lines] == ["route_from_mask", "gemm", "gemm", "cast_rows"]
+    assert _kv(lines[1])["epi"] == "0" and _kv(lines[2])["epi"] == "1" and _kv(lines[1])["early_a"] == "0"
+    c.close()
