@@ -40,7 +40,8 @@ def build() -> str | None:
                    check=True, capture_output=True)
     for src, obj in ((os.path.join(HERE, "fake_kernels.cpp"), k_o), (os.path.join(HERE, "fake_cudart.cpp"), r_o)):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", *inc, "-c", src, "-o", obj], check=True, capture_output=True)
-    subprocess.run(["g++", "-shared", "-o", SO, api_o, k_o, r_o], check=True, capture_output=True)
+    # -Bsymbolic: api.o must bind to THIS library's cuda* emulation even when a real libcudart (torch) is already loaded
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO, api_o, k_o, r_o], check=True, capture_output=True)
     return SO
 
 
