@@ -6,7 +6,9 @@ moe_infinity/distributed/expert_executor.py:19-58, restricted to what the MoE-bl
 (SURVEY.md §8 b.2).  Everything numerical is forwarded to libb2m.so through MoEEngine.
 
 Differences, on purpose:
-  * the SSD tier (core/aio) is out of scope: `offload` keeps tensors in (pinned) host DRAM;
+  * `offload` keeps tensors in host DRAM; with `persistent=True` it also maintains the reference's on-disk store
+    (store.py reads and writes `archer_index` / `archer_param_0` in the reference's format) -- the asynchronous disk
+    reader itself (core/aio) is out of scope;
   * errors raise RuntimeError/B2MError instead of aborting the process;
   * `wait_expert` returns experts in ascending expert id (the reference returns completion order, Q1).
 """
@@ -19,19 +21,44 @@ import torch
 
 from . import _lib as L
 from .engine import MoEEngine
+from .store import ArcherTensorStore
 
 _INT2DTYPE = {L.DTYPE_BF16: torch.bfloat16, L.DTYPE_F32: torch.float32, L.DTYPE_F16: torch.float16}
 _ROUTER_OF_TYPE = {L.EXPERT_MIXTRAL: L.ROUTER_MIXTRAL, L.EXPERT_DEEPSEEK: L.ROUTER_DEEPSEEK_GREEDY,
-                   L.EXPERT_SWITCH: L.ROUTER_SWITCH_TOP1, L.EXPERT_SWITCH_GATED: L.ROUTER_SWITCH_TOP1}
+                   L.EXPERT_SWITCH: L.ROUTER_SWITCH_TOP1, L.EXPERT_SWITCH_GATED: L.ROUTER_SWITCH_TOP1,
+                   # NLLB / FSGPT blocks route in Python (top-2 softmax) and reach the experts through dispatch_local
+                   L.EXPERT_NLLB: L.ROUTER_MIXTRAL, L.EXPERT_FSGPT: L.ROUTER_MIXTRAL}
+
+
+class _LazyTensors(dict):
+    """id -> host tensor; ids that only exist in the on-disk store are read on first use."""
+
+    def __init__(self, store: Optional[ArcherTensorStore]):
+        super().__init__()
+        self._store = store
+
+    def __missing__(self, tensor_id):
+        if self._store is None or tensor_id not in self._store:
+            raise KeyError(tensor_id)
+        t = self._store.read_tensor(tensor_id)
+        self[tensor_id] = t
+        return t
+
+    def __contains__(self, tensor_id):
+        return dict.__contains__(self, tensor_id) or (self._store is not None and tensor_id in self._store)
 
 
 class prefetch_handle:  # noqa: N801  (reference spelling)
     """py_archer_prefetch.cpp:11-80.  Host-DRAM tensor store + the residency/prefetch façade."""
 
-    def __init__(self, prefix: str, device_memory_ratio: float):
+    def __init__(self, prefix: str, device_memory_ratio: float, persistent: bool = False):
         self.prefix = prefix
         self.device_memory_ratio = float(device_memory_ratio)
-        self._tensors: Dict[int, torch.Tensor] = {}     # id -> host tensor  (offload)
+        # persistent=True: `prefix` is an offload directory in the reference's on-disk format (store.py): `offload`
+        # also writes there and a directory left by an earlier run (of this package or of the reference) is reused,
+        # tensors being read back on first use.  Default: host DRAM only, nothing touches the disk.
+        self._store = ArcherTensorStore(prefix) if persistent else None
+        self._tensors: Dict[int, torch.Tensor] = _LazyTensors(self._store)     # id -> host tensor  (offload)
         self._params: Dict[int, torch.Tensor] = {}      # id -> live Parameter.data placeholder (register)
         self._ptr2id: Dict[int, int] = {}
         self._node_of: Dict[int, Tuple[int, int]] = {}  # tensor id -> (layer, expert)
@@ -41,6 +68,13 @@ class prefetch_handle:  # noqa: N801  (reference spelling)
     # ---- tensor store (prefetch_handle.offload / register / is_tensor_*)
     def offload(self, tensor: torch.Tensor, tensor_id: int):
         self._tensors[int(tensor_id)] = tensor.detach().to("cpu").contiguous()
+        if self._store is not None:
+            self._store.store_tensor(int(tensor_id), tensor, flush=False)
+
+    def flush(self):
+        """Write the on-disk index once (the reference rewrites it inside every `offload`, O(n^2) in the tensor count)."""
+        if self._store is not None:
+            self._store.flush()
 
     def register(self, tensor: torch.Tensor, tensor_id: int):
         self._params[int(tensor_id)] = tensor
@@ -54,7 +88,9 @@ class prefetch_handle:  # noqa: N801  (reference spelling)
         return int(tensor_id) in self._tensors
 
     def is_tensor_index_initialized(self) -> bool:
-        return False   # no persistent store: the caller re-offloads from the checkpoint
+        # archer_tensor_handle.h:38: true iff an index file was found when the store was opened; without a persistent
+        # store the caller re-offloads from the checkpoint (model_offload.py:351)
+        return self._store is not None and self._store.is_initialized()
 
     def set_topology(self, topology):
         """[(name, [[ids...], ...]), ...]; a stage with >1 id-lists is an expert stage (model_topology.cpp:417-452)."""

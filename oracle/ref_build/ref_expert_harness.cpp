@@ -7,17 +7,20 @@
 // (:54-59), `NllbMoeDenseActDense` (:79-93), `FSGPTMoEDenseActDense` (:113-129), bound to their weights the way the
 // reference binds them (`SetTensorsFromBlob` through the global tensor index, :16-22, :45-51, :69-77, :139-145, ...).
 //
-// The only symbol the reference TU needs from the rest of its engine is the global `kTensorIndex`
-// (aio/archer_tensor_index.h:55; defined in prefetch/archer_prefetch_handle.cpp:22) -- defined here.
+// The only symbol that TU needs from the rest of the engine is the global `kTensorIndex` (aio/archer_tensor_index.h:55),
+// which the reference defines in aio/archer_tensor_index.cpp:103 -- that file is compiled in as well (as-is) and also
+// provides the reference's on-disk index format (`ArcherTensorIndex::Serialize/Deserialize`, :105-132), exposed below
+// for tests/test_store_format.py.
 #include <torch/extension.h>
 
 #include <memory>
+#include <string>
+#include <tuple>
 #include <vector>
 
 #include "aio/archer_tensor_index.h"
 #include "parallel/expert_module.h"
 
-std::unique_ptr<ArcherTensorIndex> kTensorIndex = std::make_unique<ArcherTensorIndex>();
 
 namespace {
 
@@ -30,6 +33,7 @@ torch::Tensor run(int dtype, const std::vector<std::uint32_t>& ids, const torch:
 
 // expert_type / dtype: the integers of expert_module.h:13-23.  `tensors` in the reference's tensor-id order.
 torch::Tensor expert_forward(int expert_type, int dtype, std::vector<torch::Tensor> tensors, torch::Tensor x) {
+  if (!kTensorIndex) kTensorIndex = std::make_unique<ArcherTensorIndex>();   // archer_prefetch_handle.cpp:22
   kTensorIndex->clear();
   std::vector<std::uint32_t> ids;
   for (size_t i = 0; i < tensors.size(); ++i) {
@@ -51,9 +55,40 @@ torch::Tensor expert_forward(int expert_type, int dtype, std::vector<torch::Tens
   }
 }
 
+// ---- on-disk index format (aio/archer_tensor_index.cpp:51-132), driven exactly like ArcherTensorHandle::StoreTensor
+// fills it (archer_tensor_handle.cpp:53-86): meta = {file_id, offset, nbytes, sizes, options of the stored tensor}
+void index_serialize(const std::string& path,
+                     const std::vector<std::tuple<std::uint32_t, std::uint32_t, std::int64_t, torch::Tensor>>& entries) {
+  ArcherTensorIndex index;
+  for (const auto& [id, file_id, offset, t] : entries) {
+    TensorStorageMeta meta{file_id, offset, t.nbytes(), t.sizes().vec()};
+    meta.options = t.options();
+    meta.id = id;
+    index.insert(std::make_pair(id, meta));
+  }
+  index.Serialize(path.c_str());
+}
+
+// -> [(id, file_id, offset, size, shape, scalar_type, device_type, device_index, layout, requires_grad, pinned)]
+std::vector<std::tuple<std::uint32_t, std::uint32_t, std::int64_t, std::uint64_t, std::vector<std::int64_t>, int, int, int, int,
+                       bool, bool>>
+index_deserialize(const std::string& path) {
+  ArcherTensorIndex index;
+  index.Deserialize(path.c_str());
+  std::vector<std::tuple<std::uint32_t, std::uint32_t, std::int64_t, std::uint64_t, std::vector<std::int64_t>, int, int, int,
+                         int, bool, bool>> out;
+  for (const auto& [id, m] : index)
+    out.emplace_back(id, m.file_id, m.offset, (std::uint64_t)m.size, m.shape, (int)m.options.dtype().toScalarType(),
+                     (int)m.options.device().type(), (int)m.options.device().index(), (int)m.options.layout(),
+                     m.options.requires_grad(), m.options.pinned_memory());
+  return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(ref_expert_module, m) {
   m.doc() = "reference expert modules (core/parallel/expert_module.cpp) compiled as-is; test oracle only";
   m.def("expert_forward", &expert_forward, "run the reference's expert module of the given type on CPU");
+  m.def("index_serialize", &index_serialize, "ArcherTensorIndex::Serialize of metas built like StoreTensor builds them");
+  m.def("index_deserialize", &index_deserialize, "ArcherTensorIndex::Deserialize -> list of meta tuples");
 }

@@ -20,8 +20,9 @@ def build(reference_root: str = "/root/reference", verbose: bool = False) -> str
     src = os.path.join(reference_root, "core", "parallel", "expert_module.cpp")
     if not os.path.exists(src):
         return SO if os.path.exists(SO) else None
-    if os.path.exists(SO) and os.path.getmtime(SO) >= max(
-            os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "ref_build", "ref_expert_harness.cpp"))):
+    deps = [src, os.path.join(reference_root, "core", "aio", "archer_tensor_index.cpp"),
+            os.path.join(HERE, "ref_build", "ref_expert_harness.cpp"), os.path.join(HERE, "ref_build", "Makefile")]
+    if os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps):
         return SO
     r = subprocess.run(["make", "-C", os.path.join(HERE, "ref_build"), f"REF={reference_root}"],
                        capture_output=not verbose, text=True)
