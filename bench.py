@@ -55,11 +55,12 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, if any."""
-    path = os.path.join(ROOT, "profiles", "r01_k3_dram_traffic.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f).get("traffic_bytes_per_launch")
+    """dram bytes per launch of the dominant kernel (K3) from the newest committed ncu --set full summary, if any."""
+    for name in ("r01k_dram_traffic.json", "r01_k3_dram_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f).get("traffic_bytes_per_launch")
     return None
 
 
