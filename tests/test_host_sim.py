@@ -416,3 +416,48 @@ def test_staged_calls_and_deepseek_shared_experts_on_cpu(sim):
     assert [ln.split()[0] for ln in lines] == ["route_from_mask", "gemm", "gemm", "cast_rows"]
     assert _kv(lines[1])["epi"] == "0" and _kv(lines[2])["epi"] == "1" and _kv(lines[1])["early_a"] == "0"
     c.close()
+
+
+def test_expert_parallel_call_sequence_and_errors_on_cpu(sim):
+    """Host side of the NCCL-style expert-parallel sequence (include/b2m.h: route -> ep_pack -> exchange -> ep_regroup ->
+    run_experts -> ep_ungroup -> exchange -> ep_unpack -> combine): argument checks, the switch to EP mode (local experts
+    all resident, never the on-demand path, no count read-back) and the peer-to-peer set-up failing cleanly when CUDA IPC
+    is unavailable (the emulated runtime reports cudaErrorNotSupported; ep.py then falls back to NCCL)."""
+    nranks, rank, T = 2, 1, 6
+    E, H, k = 8, 128, 2
+    c = Ctx(sim, L_=1, E=E, H=H, I=128, k=k, num_slots=4, max_tokens=64)       # this rank owns experts 4..7
+    assert c.rc == 0, c.err()
+    rng = np.random.default_rng(3)
+    for e in range(4, 8):
+        blob = rng.integers(0, 255, c.expert_bytes(), dtype=np.uint8)
+        c.blobs[(0, e)] = blob
+        assert sim.b2m_register_expert(c.h, 0, e, blob.ctypes.data, blob.nbytes) == 0, c.err()
+        assert sim.b2m_make_resident(c.h, 0, e, 1, None) == 0, c.err()
+    cap = T * k
+    rows = np.zeros((nranks, cap + 1, H), dtype=np.uint16)
+    x = np.zeros((T, H), dtype=np.uint16)
+    lg = rng.standard_normal((T, E)).astype(np.float32)
+    assert sim.b2m_route(c.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, None) == 0, c.err()
+    assert sim.b2m_ep_pack(c.h, nranks, rank, cap - 1, T, rows.ctypes.data, None, None) != 0 and "cap" in c.err()
+    assert sim.b2m_ep_pack(c.h, 3, rank, cap, T, rows.ctypes.data, None, None) != 0             # 8 experts over 3 ranks
+    assert sim.b2m_ep_pack(c.h, nranks, 2, cap, T, rows.ctypes.data, None, None) != 0           # rank out of range
+    take_log(sim)
+    assert sim.b2m_ep_pack(c.h, nranks, rank, cap, T, rows.ctypes.data, None, None) == 0, c.err()
+    assert sim.b2m_ep_regroup(c.h, nranks, rank, cap, nranks * T, rows.ctypes.data, None, None) == 0, c.err()
+    syncs0 = c.stats()["host_syncs"]
+    assert sim.b2m_run_experts(c.h, 0, nranks * T, None) == 0, c.err()
+    assert sim.b2m_ep_ungroup(c.h, nranks, rank, cap, rows.ctypes.data, None) == 0, c.err()
+    assert sim.b2m_ep_unpack(c.h, nranks, rank, cap, T, rows.ctypes.data, None) == 0, c.err()
+    out = np.zeros((T, H), dtype=np.uint16)
+    assert sim.b2m_combine(c.h, 0, x.ctypes.data, T, out.ctypes.data, None) == 0, c.err()
+    names = [ln.split()[0] for ln in take_log(sim)]
+    assert names == ["ep_pack", "ep_regroup", "gemm", "gemm", "ep_ungroup", "ep_unpack", "combine"]
+    s = c.stats()
+    assert s["host_syncs"] == syncs0 and s["misses"] == 0 and s["evictions"] == 0      # EP mode: never the on-demand path
+    # an unregistered local expert is an error in EP mode, not a silent skip
+    c2 = Ctx(sim, L_=1, E=E, H=H, I=128, k=k, num_slots=8, max_tokens=64)
+    handle = (C.c_char * 64)()
+    assert sim.b2m_ep_p2p_init(c2.h, nranks, rank, cap, handle) != 0 and c2.err() != ""
+    assert sim.b2m_route(c2.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, None) == 0   # context still usable
+    c.close()
+    c2.close()
