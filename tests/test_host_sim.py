@@ -461,3 +461,74 @@ def test_expert_parallel_call_sequence_and_errors_on_cpu(sim):
     assert sim.b2m_route(c2.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, None) == 0   # context still usable
     c.close()
     c2.close()
+
+
+def test_random_call_sequences_never_crash_on_cpu(sim):
+    """Stateful fuzz of the C ABI's host logic: random (often invalid) calls in random order.  Every call must return a
+    status code (0 or < 0 with a message), the cache invariants must hold after every step, and a valid forward must keep
+    working afterwards.  (Run under ASan/UBSan during development: clean.)"""
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        Lr, E, k = int(rng.integers(1, 4)), int(rng.choice([2, 4, 8, 16])), 0
+        k = int(rng.integers(1, min(E, 4) + 1))
+        nslots = int(rng.integers(1, Lr * E + 3))
+        chunk = int(rng.choice([0, 4096, 100000]))
+        c = Ctx(sim, L_=Lr, E=E, H=64, I=64, k=k, num_slots=nslots, max_tokens=32, h2d_chunk_bytes=chunk,
+                max_inflight_prefetch=int(rng.integers(0, 4)))
+        assert c.rc == 0, c.err()
+        registered = set()
+        x = np.zeros((40, 64), dtype=np.uint16)
+        out = np.zeros((40, 64), dtype=np.uint16)
+        last_T = None
+        for step in range(400):
+            op = int(rng.integers(0, 12))
+            l = int(rng.integers(-1, Lr + 1))
+            e = int(rng.integers(-1, E + 1))
+            T = int(rng.integers(0, 36))
+            rc = 0
+            if op <= 1:
+                blob = rng.integers(0, 255, c.expert_bytes() if rng.random() < 0.9 else 10, dtype=np.uint8)
+                rc = sim.b2m_register_expert(c.h, l, e, blob.ctypes.data, blob.nbytes)
+                if rc == 0:
+                    c.blobs[(l, e)] = blob
+                    registered.add((l, e))
+            elif op <= 4:
+                lg = rng.standard_normal((max(T, 1), E)).astype(np.float32)
+                rc = sim.b2m_moe_forward(c.h, l, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, out.ctypes.data, None)
+                if rc == 0:
+                    last_T = T
+            elif op == 5:
+                lg = rng.standard_normal((max(T, 1), E)).astype(np.float32)
+                rc = sim.b2m_route(c.h, l, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, None)
+                if rc == 0:
+                    rc = sim.b2m_run_experts_ex(c.h, l, T, int(rng.choice([1, 2, 3])), None)
+            elif op == 6:
+                n = int(rng.integers(0, 5))
+                pairs = (C.c_int32 * (2 * max(n, 1)))(*[int(v) for _ in range(max(n, 1)) for v in (rng.integers(-1, Lr + 1), rng.integers(-1, E + 1))])
+                scores = rng.random(max(n, 1)).astype(np.float32)
+                rc = sim.b2m_prefetch_hint(c.h, n, pairs, scores.ctypes.data_as(C.POINTER(C.c_float)))
+            elif op == 7:
+                rc = sim.b2m_enqueue_prefetch(c.h, l, e)
+            elif op == 8:
+                rc = sim.b2m_prefetch_drain(c.h) if rng.random() < 0.5 else sim.b2m_prefetch_pump(c.h)
+            elif op == 9:
+                rc = sim.b2m_make_resident(c.h, l, e, int(rng.integers(0, 4)), None)
+            elif op == 10:
+                rc = sim.b2m_clear_expert_cache_counts(c.h)
+            else:
+                rc = sim.b2m_run_experts(c.h, l, T, None)            # usually without a matching routing call
+            assert rc <= 0
+            if rc != 0:
+                assert c.err() != "", (trial, step, op)
+            s = c.stats()
+            assert s["resident"] <= s["slots"] == min(nslots, Lr * E)      # more slots than experts are not allocated
+            assert s["hits"] + s["misses"] == s["dispatches"]
+        # residency map and slot contents are consistent after the storm
+        seen_slots = {}
+        for (l, e) in registered:
+            if c.resident(l, e):
+                b = c.slot_bytes(l, e)
+                assert b is not None
+                seen_slots.setdefault(b.ctypes.data, []).append((l, e))
+        assert all(len(v) == 1 for v in seen_slots.values()), "two experts share one HBM slot"
+        c.close()
