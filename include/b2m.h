@@ -119,7 +119,8 @@ int b2m_ctx_destroy(b2m_ctx* ctx);
 
 /* replaces: prefetch_handle.offload/register + set_topology for an expert stage + expert_dispatcher.register_expert
  * (core/parallel/expert_dispatcher.cpp:160-173; blob layout core/model/model_topology.cpp:429-431:
- * tensors concatenated in tensor_ids order -- Mixtral w1|w2|w3, DeepSeek gate|up|down, Switch wi|wo).
+ * tensors concatenated in tensor_ids order -- Mixtral w1|w2|w3, DeepSeek gate|up|down, Switch wi|wo, gated Switch
+ * wi_0|wi_1|wo, NLLB/FSGPT fc1|fc1_bias|fc2|fc2_bias -- packed without the reference's 4 KiB padding between tensors).
  * `host_blob` must stay valid (and should be pinned, see b2m_host_pin) for the life of the context; may be NULL
  * for an expert that only ever lives in HBM (then it is never evicted). */
 int b2m_register_expert(b2m_ctx* ctx, int layer, int expert, const void* host_blob, size_t bytes);
