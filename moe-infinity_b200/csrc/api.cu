@@ -835,6 +835,9 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     static const bool mc2_on = getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '1';
     const bool mc2 = mc2_on && nt == 128 && T_hint_large;
     static const bool pdl_k3 = getenv("B2M_PDL_K3") && getenv("B2M_PDL_K3")[0] == '1';
+    // experimental, default off and not yet measured: per-tile MMA width (ragged last token tiles of prefill-sized experts)
+    static const bool dyn_n = getenv("B2M_DYN_N") && getenv("B2M_DYN_N")[0] == '1';
+    up.dyn_n = dn.dyn_n = (dyn_n && T_hint_large && !mc2) ? 1 : 0;
     up.pdl_edge = (pdl_k3 && !T_hint_large) ? 1 : 0;
     up.early_a = (c->k3_early_ok && &a == &c->arena && phases == 3) ? 1 : 0;   // routed experts right behind the permute kernel
     if (phases & 1) {

@@ -224,6 +224,11 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * Cfg::ACC_COLS;
+      uint32_t idesc_t = idesc;
+      if (p.dyn_n) {   // opt-in: N of this tile's MMAs = its own token count (multiple of 16, >= 16)
+        const int n_eff = t.ncols <= 16 ? 16 : ((t.ncols + 15) & ~15);
+        idesc_t = make_idesc_f16(DT, BLOCK_M, n_eff < NT ? n_eff : NT);
+      }
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -238,8 +243,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t accum = (kb > t.kb_begin || k > 0) ? 1u : 0u;
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance start address inside the SW128 atom
-            tc_mma_f16(d0, da0 + koff, db + koff, idesc, accum);
-            if (DUAL) tc_mma_f16(d0 + NT, da1 + koff, db + koff, idesc, accum);
+            tc_mma_f16(d0, da0 + koff, db + koff, idesc_t, accum);
+            if (DUAL) tc_mma_f16(d0 + NT, da1 + koff, db + koff, idesc_t, accum);
           }
           if (MC == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           else tc_commit_mc(&empty_bar[stage], (uint16_t)0x3);   // ... in both CTAs: the peer multicasts into it too
