@@ -36,4 +36,11 @@ python tools/ncu_summarize.py launches "$OUT/${TAG}_launches.csv" "$OUT/${TAG}_l
 run ncu_full 600 ncu --set full --clock-control none --import-source on -k regex:grouped_gemm_tc_kernel -s 4 -c 2 \
     -o "$OUT/${TAG}_k3k4" -f python bench.py --steps 1 --warmup 1
 ls -la "$OUT/${TAG}_k3k4.ncu-rep" 2>/dev/null
+# optional: the reference's own native engine beside ours (REF_ENGINE=1; needs oracle/_ref/prefetch_op.so and an
+# O_DIRECT-capable directory; aborts on any DLOG_FATAL, hence last and in its own process)
+if [ "${REF_ENGINE:-0}" = 1 ]; then
+  run ref_engine 900 python tools/ref_engine_harness.py --layers 4 --tokens 8 --steps 16 --ratio 0.9 --dir "$OUT/ref_store"
+  tail -2 "$OUT/${TAG}_ref_engine.log"
+  rm -rf "$OUT/ref_store"
+fi
 echo "done: $TAG"
