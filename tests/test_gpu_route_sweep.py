@@ -146,3 +146,32 @@ def test_fused_gate_sweep(router, dtype, E, k, H, T, lib_built):
         assert near.float().mean() < 0.05
         assert torch.equal(gi[~near].sort(-1).values, r.topk_idx[~near].sort(-1).values)
     check_permutation(eng, x.cuda(), T)
+
+
+@pytest.mark.parametrize("E,k", [(8, 2), (64, 6), (256, 8), (33, 5)])
+@pytest.mark.parametrize("T", [1, 32, 33, 64, 100, 200, 256])
+def test_decode_routing_all_resident_sweep(E, k, T, lib_built):
+    """All experts resident and T <= 256: the decode routing path of the fused call -- the last gate/top-k CTA publishes
+    counts, offsets AND the row maps (count/rank spread over its warps, 1..8 token chunks), the permute kernel only copies
+    rows.  (The sweeps above run with one HBM slot, i.e. in offload mode, where every permute CTA ranks for itself.)"""
+    from moe_infinity_b200 import MoEEngine, _lib as L
+    H = 64
+    eng = MoEEngine(num_layers=1, num_experts=E, hidden=H, inter=128, top_k=k, dtype=torch.bfloat16,
+                    expert_type=L.EXPERT_MIXTRAL, router=L.ROUTER_MIXTRAL, max_tokens=256, num_slots=E)
+    for e in range(E):
+        eng.load_expert(0, e).zero_()
+    assert eng.stats()["slots"] == E
+    g = torch.Generator().manual_seed(E * 131 + k * 17 + T)
+    x = torch.randn(T, H, generator=g).to(torch.bfloat16)
+    logits = (torch.randn(T, E, generator=g) * 2).to(torch.bfloat16)
+    r = O.mixtral_route(logits, k, torch.bfloat16)
+    eng.route(0, x.cuda(), router_logits=logits.cuda())
+    torch.cuda.synchronize()
+    tied = O.tied_tokens(r.scores, k)
+    check_indices(eng.ws("topk_idx", T), r.topk_idx, tied)
+    check_permutation(eng, x.cuda(), T)
+    if not bool(tied.any()):
+        counts = torch.bincount(r.topk_idx.flatten(), minlength=E)
+        assert eng.ws("counts", T).cpu().tolist() == counts.tolist()
+        assert eng.ws("offsets", T).cpu().tolist() == [0] + torch.cumsum(counts, 0).tolist()
+    assert eng.stats()["host_syncs"] == 0
