@@ -59,6 +59,12 @@ extern "C" {
 #define B2M_NUMERICS_REFERENCE 0 /* replay the reference's per-ATen-op rounding to the model dtype */
 #define B2M_NUMERICS_FP32 1      /* keep fp32 until the single final rounding (fewer roundings)    */
 
+/* on-demand cache accounting */
+#define B2M_CACHE_REFERENCE 0 /* byte budget charged exactly like cache_sizes_ in core/parallel/expert_dispatcher.cpp:228,257,266:
+                                 every dispatched expert (hit or miss) costs one expert, an eviction refunds one, a miss evicts
+                                 exactly one victim iff the budget is used up */
+#define B2M_CACHE_SLOTS 1     /* evict only when no physical HBM slot is free (hits are not charged) */
+
 typedef struct b2m_ctx b2m_ctx;
 
 typedef struct b2m_config {
@@ -88,7 +94,7 @@ typedef struct b2m_config {
   int32_t max_inflight_prefetch; /* concurrent prefetch copies on the side stream (default 2) */
   int32_t h2d_chunk_bytes;  /* H2D copy granularity in bytes (0 = whole expert in one cudaMemcpyAsync) */
   int32_t gemm_impl;        /* 0 = tcgen05 (product); 1 = CUDA-core cross-check kernel (bring-up only) */
-  int32_t reserved;
+  int32_t cache_policy;     /* B2M_CACHE_* : on-demand budget accounting */
 } b2m_config;
 
 /* cache / traffic counters; columns mirror the reference's per-node counters exported by get_hit_rate
@@ -166,6 +172,9 @@ int b2m_combine(b2m_ctx* ctx, int layer, const void* x, int T, void* out, void* 
 /* replaces OutputFunc/Wait (expert_dispatcher.cpp:397-450): expert outputs in the model dtype, rows grouped by
  * ascending expert id, ascending token order inside an expert; `offsets_host` (E+1 ints) may be NULL */
 int b2m_expert_outputs(b2m_ctx* ctx, int T, void* out_rows, int* offsets_host, void* stream);
+/* synchronises `stream` and reports (then clears) the sticky device error word; B2M_EINVAL when a mask handed to
+ * b2m_route_from_mask had a row with more than top_k experts (the reference would run them all: expert_dispatcher.cpp:274-285) */
+int b2m_check_errors(b2m_ctx* ctx, void* stream);
 
 /* workspace access for tests / EP plumbing (device pointers owned by the context) */
 #define B2M_WS_TOPK_IDX 0   /* int32 [T,k]  (descending score; -1 = dropped) */

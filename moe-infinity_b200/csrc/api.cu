@@ -149,8 +149,14 @@ struct b2m_ctx {
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
+  int* d_err = nullptr;          // sticky device error word (RouteParams::err_flag)
+  int* h_err = nullptr;          // pinned readback of d_err
   bool k3_early_ok = false;      // offsets of the current routing were published before the permute kernel
   int* d_dest_of = nullptr;      // [cap_R]
+  // on-demand budget in expert units, accounted exactly as the reference's cache_sizes_[gpu] (expert_dispatcher.cpp:228,
+  // 257,266): -1 for EVERY dispatched expert (hit or miss -- the reference subtracts byte_size unconditionally), +1 per
+  // on-demand eviction; a miss evicts exactly one victim iff budget < 1.  Physical slots remain the hard limit.
+  long long budget_units = 0;
   b2m_stats stats;
 };
 
@@ -335,6 +341,27 @@ int acquire_slot(b2m_ctx* c, const std::vector<int>& in_use, bool prefetch) {
   return s;
 }
 
+// On-demand miss, the reference's way (GPUFetchFunc, expert_dispatcher.cpp:227-258): if the byte budget is used up
+// (cache_sizes_ < byte_size) evict exactly ONE victim -- even while the budget arithmetic and the physical slots
+// disagree (the reference charges hits too, see budget_units) -- then stage.  cfg.cache_policy == B2M_CACHE_SLOTS skips
+// the budget test and evicts only when no physical slot is free.
+int acquire_slot_on_demand(b2m_ctx* c, const std::vector<int>& in_use) {
+  const bool ref_acct = c->cfg.cache_policy == B2M_CACHE_REFERENCE;
+  if (c->free_slots.empty() || (ref_acct && c->budget_units < 1)) {
+    int v = pick_victim(c, in_use, false);
+    if (v < 0) v = pick_victim(c, in_use, true);   // overflow: on-demand beats protection
+    if (v >= 0) {
+      evict(c, v);
+      c->budget_units += 1;                        // cache_sizes_ += evict_node->byte_size (:257)
+    } else if (c->free_slots.empty()) {
+      return -1;                                   // nothing evictable in this wave
+    }                                              // (reference: assert(evict_node != nullptr); a free slot lets us go on)
+  }
+  const int s = c->free_slots.back();
+  c->free_slots.pop_back();
+  return s;
+}
+
 int issue_copy(b2m_ctx* c, int id, int slot, cudaStream_t st, bool do_copy) {
   Expert& x = c->experts[id];
   Slot& sl = c->slots[slot];
@@ -424,6 +451,7 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
   p.counts = c->d_counts; p.offsets = c->d_offsets; p.chunk_counts = c->d_chunk_counts;
   p.xp = c->d_xp;
   p.ticket = c->d_ticket;
+  p.err_flag = c->d_err;
   return p;
 }
 
@@ -433,9 +461,17 @@ void plan_gemm(b2m_ctx* c, int T) {
   // gate/up GEMM: 256-token tiles too (single TMEM stage, MUFU SiLU epilogue): 7.37 -> 6.61 ms at T=16384
   // (profiles/r01f_prefill.txt); B2M_NT256_UP=0 keeps the 128-token double-buffered tiles
   static const bool up256 = !(getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '0');
-  c->cur_nt = (up256 && c->cur_nt_dn == 256) ? 256 : pick_nt(T);
+  // reference numerics keep the precise SiLU, with which the single-stage 256-token tile is slower than the double-buffered
+  // 128-token tile (8.1 vs 7.2-7.4 ms): 256 for the gate/up GEMM only in B2M_NUMERICS_FP32 mode
+  c->cur_nt = (up256 && c->cur_nt_dn == 256 && c->cfg.numerics == B2M_NUMERICS_FP32) ? 256 : pick_nt(T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
   if (c->arena.shape.has_bias) c->cur_ksplit = 1;   // `+ fc2_bias` is applied once, in the epilogue of the whole-K product
+}
+
+// same switch as b2m_common.cuh:pdl_enabled() (that header is device code; this file also builds against the host emulation)
+bool pdl_enabled() {
+  static const bool on = getenv("B2M_PDL") && getenv("B2M_PDL")[0] == '1';
+  return on;
 }
 
 int route_launch_count(int T, int router, bool fused_gate) {
@@ -467,6 +503,7 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape))
     return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is unknown (expert_module.h:13-18 defines 0..5)", cfg->expert_type);
   if (cfg->router < 0 || cfg->router > 3) return fail(nullptr, B2M_EINVAL, "bad router kind");
+  if (cfg->cache_policy != B2M_CACHE_REFERENCE && cfg->cache_policy != B2M_CACHE_SLOTS) return fail(nullptr, B2M_EINVAL, "bad cache_policy");
   if (cfg->router == B2M_ROUTER_SWITCH_TOP1 && cfg->top_k != 1) return fail(nullptr, B2M_EINVAL, "switch router needs top_k=1");
 
   int ndev = 0;
@@ -562,6 +599,9 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_offsets_src, sizeof(int) * (E + 1)));
   CKC(cudaMalloc((void**)&c->d_ticket, sizeof(int)));
   CKC(cudaMemset(c->d_ticket, 0, sizeof(int)));
+  CKC(cudaMalloc((void**)&c->d_err, sizeof(int)));
+  CKC(cudaMemset(c->d_err, 0, sizeof(int)));
+  CKC(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
   CKC(cudaMalloc((void**)&c->d_dest_of, sizeof(int) * R));
   CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
   CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
@@ -592,6 +632,7 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->stats.slots = (uint64_t)nslots;
   c->stats.slot_bytes = shape.bytes;
+  c->budget_units = nslots;
 #undef CKC
   *out = c;
   return B2M_OK;
@@ -603,7 +644,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
@@ -611,6 +652,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->p2p.local_ctr) cudaFree(c->p2p.local_ctr);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_err) cudaFreeHost(c->h_err);
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
   if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
   if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
@@ -684,6 +726,7 @@ int b2m_make_resident(b2m_ctx* c, int layer, int expert, int flags, void* stream
     if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot for expert (%d,%d)", layer, expert);
     r = issue_copy(c, id, slot, c->fetch_stream, !no_copy);
     if (r) return r;
+    c->budget_units -= 1;   // the expert occupies budget like one staged by a dispatch
   }
   if (x.state == ST_LOADING) {
     CK(c, cudaEventSynchronize(x.ready));
@@ -765,8 +808,11 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   // small batches, all experts resident: let the last gate/top-k CTA publish the offsets so that the gate/up GEMM can be
   // launched with a programmatic edge behind the permute kernel and stream weights while rows are still being gathered
   static const bool k3_early = !(getenv("B2M_EARLY_K3") && getenv("B2M_EARLY_K3")[0] == '0');
-  c->k3_early_ok = k3_early && T >= 1 && T <= 256 && c->cfg.router != B2M_ROUTER_SWITCH_TOP1 && !ep_dispatch && !c->offload &&
-                   !c->ep_mode && c->cfg.gemm_impl == 0;
+  // Not with B2M_PDL=1: with a programmatic edge on EVERY kernel the permute kernel may start before the gate/top-k kernel
+  // has finished, so a GEMM that reads offsets/slot_of before its own griddepcontrol.wait could see the previous layer's
+  // tables.  Pre-wait reads may only touch data older than the predecessor's own launch.
+  c->k3_early_ok = k3_early && !pdl_enabled() && T >= 1 && T <= 256 && c->cfg.router != B2M_ROUTER_SWITCH_TOP1 && !ep_dispatch &&
+                   !c->offload && !c->ep_mode && c->cfg.gemm_impl == 0;
   p.offsets_early = c->k3_early_ok ? 1 : 0;
   static const bool rows_by_gate = !(getenv("B2M_ROWS_BY_GATE") && getenv("B2M_ROWS_BY_GATE")[0] == '0');
   p.rows_by_gate = (c->k3_early_ok && rows_by_gate) ? 1 : 0;
@@ -852,7 +898,7 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       // decode: let the down projection start under the tail of the gate/up GEMM and prefetch its first weight tiles
       // measured on B200 (profiles/r01g_pdl_edges.txt): 12.945 -> 12.855 ms/step; B2M_EARLY_A=0 disables
       static const bool early_a = !(getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '0');
-      dn.early_a = (early_a && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
+      dn.early_a = (early_a && !pdl_enabled() && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
       // split-K at decode: equal contiguous shares of all (tile, k-block) units per CTA instead of a fixed factor, so no
       // SM is left with an extra slice in the last wave (B2M_STREAMK=0: fixed factor)
       static const bool streamk = !(getenv("B2M_STREAMK") && getenv("B2M_STREAMK")[0] == '0');
@@ -923,7 +969,8 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
       if (!resident) {
         if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
         if (c->ep_mode) return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", id / E, id % E);
-        const int slot = acquire_slot(c, remaining, false);   // never evict an expert this layer still has to run
+        // never evict an expert this call still has to run (reference: those nodes hold their mutex, :239)
+        const int slot = on_demand ? acquire_slot_on_demand(c, remaining) : acquire_slot(c, remaining, false);
         if (slot < 0) continue;                               // no room in this wave: stays in `remaining`
         if (on_demand) c->stats.misses++;
         r = issue_copy(c, id, slot, c->fetch_stream, true);
@@ -936,6 +983,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
         c->stats.dispatches++;
         x.visits += 1;            // incache_visit_count += 1 for every dispatched expert (expert_dispatcher.cpp:264)
         x.total_visits += 1;
+        c->budget_units -= 1;     // cache_sizes_ -= byte_size for every dispatched expert, hit or miss (:266)
       }
       wave.push_back(id);
     }
@@ -1008,7 +1056,9 @@ int b2m_combine(b2m_ctx* c, int layer, const void* x, int T, void* out, void* st
 static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, void* stream, bool ep_collect) {
   int r = check_layer(c, layer);
   if (r) return r;
+  if (T < 0 || T > c->cap_T) return fail(c, B2M_EINVAL, "T=%d exceeds workspace capacity %d", T, c->cap_T);
   if (T == 0) return B2M_OK;
+  if (!out) return fail(c, B2M_EINVAL, "out is null");
   cudaStream_t st = (cudaStream_t)stream;
   const b2m_config& f = c->cfg;
   CombineParams p;
@@ -1067,6 +1117,8 @@ int b2m_moe_forward(b2m_ctx* c, int layer, const void* x, const void* router_in,
 
 int b2m_expert_outputs(b2m_ctx* c, int T, void* out_rows, int* offsets_host, void* stream) {
   if (!c) return B2M_EINVAL;
+  if (T < 0 || T > c->cap_T) return fail(c, B2M_EINVAL, "T=%d exceeds workspace capacity %d", T, c->cap_T);
+  if (T != c->cur_T) return fail(c, B2M_ESTATE, "b2m_expert_outputs(T=%d) does not follow a routing call with the same T (%d)", T, c->cur_T);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)T * c->cfg.top_k * c->cfg.hidden;
   if (out_rows && T > 0) {
@@ -1075,7 +1127,26 @@ int b2m_expert_outputs(b2m_ctx* c, int T, void* out_rows, int* offsets_host, voi
   }
   if (offsets_host) {
     CK(c, cudaMemcpyAsync(offsets_host, c->d_offsets, sizeof(int) * (c->cfg.num_experts + 1), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    if (*c->h_err) {
+      const int bits = *c->h_err;
+      CK(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+      return fail(c, B2M_EINVAL, "device error word %d: a router-mask row names more experts than top_k=%d (rows would be dropped)", bits, c->cfg.top_k);
+    }
+  }
+  return B2M_OK;
+}
+
+int b2m_check_errors(b2m_ctx* c, void* stream) {
+  if (!c) return B2M_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  if (*c->h_err) {
+    const int bits = *c->h_err;
+    CK(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+    return fail(c, B2M_EINVAL, "device error word %d: a router-mask row names more experts than top_k=%d", bits, c->cfg.top_k);
   }
   return B2M_OK;
 }
@@ -1236,6 +1307,7 @@ int b2m_ep_ungroup(b2m_ctx* c, int nranks, int rank, int cap, void* ret_rows, vo
 int b2m_ep_unpack(b2m_ctx* c, int nranks, int rank, int cap, int T_local, const void* back_rows, void* stream) {
   int r = ep_check(c, nranks, rank, cap);
   if (r) return r;
+  if (T_local < 0 || T_local * c->cfg.top_k > cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, cap);
   EpParams p = ep_base(c, nranks, rank, cap);
   p.back_rows = back_rows;
   p.inline_counts = c->ep_inline;
@@ -1341,6 +1413,7 @@ int b2m_ep_p2p_route(b2m_ctx* c, int layer, const void* x, const void* router_in
 int b2m_ep_p2p_combine(b2m_ctx* c, int layer, const void* x, int T_local, void* out, void* stream) {
   int r = p2p_ready(c);
   if (r) return r;
+  if (T_local < 0 || T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, c->p2p.cap);
   return combine_impl(c, layer, x, T_local, out, stream, true);
 }
 
@@ -1372,6 +1445,7 @@ int b2m_ep_p2p_return(b2m_ctx* c, void* stream) {
 int b2m_ep_p2p_collect(b2m_ctx* c, int T_local, void* stream) {
   int r = p2p_ready(c);
   if (r) return r;
+  if (T_local < 0 || T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, c->p2p.cap);
   EpParams p = ep_p2p_params(c);
   CK(c, launch_ep_unpack(p, c->cfg.dtype, T_local * c->cfg.top_k, (cudaStream_t)stream));
   c->stats.kernel_launches += 1;

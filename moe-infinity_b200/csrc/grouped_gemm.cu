@@ -60,9 +60,10 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-// SiLU with the MUFU approximations (ex2.approx, rcp.approx).  Used only by the 256-token-tile instantiation, whose single
-// TMEM stage makes the epilogue serialise with the MMAs: there the ~2 ulp(fp32) of the approximations are rounded away by
-// the following round-to-model-dtype in all but ~1e-3 of the elements, and the epilogue gets ~3x shorter.
+// SiLU with the MUFU approximations (ex2.approx, rcp.approx).  Used only by the 256-token-tile instantiation in
+// B2M_NUMERICS_FP32 mode (its single TMEM stage makes the epilogue serialise with the MMAs; the epilogue gets ~3x shorter).
+// B2M_NUMERICS_REFERENCE always uses the precise form: the ~2 ulp(fp32) of the approximations would survive the following
+// round-to-model-dtype in ~1e-3 of the elements.
 __device__ __forceinline__ float silu_mufu(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
@@ -309,11 +310,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
               if (DUAL) {
                 float u = __uint_as_float(vu[j]);
                 constexpr bool kFastAct = NT >= 256;
-                if (p.mimic) {   // reference rounding chain: each ATen op rounds to the model dtype
-                  g = round_dt<DT>(g);
+                if (p.mimic) {   // reference rounding chain: each ATen op rounds to the model dtype; precise SiLU at every tile
+                  g = round_dt<DT>(g);   // width, so "reference numerics" does not depend on T (the MUFU form is NUMERICS_FP32 only)
                   u = round_dt<DT>(u);
-                  const float a = (kFastAct && p.act == ACT_SILU) ? silu_mufu(g) : act_apply(g, p.act);
-                  h = round_dt<DT>(a) * u;
+                  h = round_dt<DT>(act_apply(g, p.act)) * u;
                 } else {
                   h = ((kFastAct && p.act == ACT_SILU) ? silu_mufu(g) : act_apply(g, p.act)) * u;
                 }

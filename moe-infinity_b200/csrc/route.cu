@@ -580,14 +580,19 @@ __global__ void __launch_bounds__(RT_THREADS) chunk_count_kernel(const RoutePara
 __global__ void __launch_bounds__(RT_THREADS) mask_to_topk_kernel(const RouteParams p, const uint8_t* __restrict__ mask) {
   const int t = blockIdx.x * RT_THREADS + threadIdx.x;
   if (t >= p.T) return;
-  int n = 0;
+  int n = 0, nset = 0;
   for (int e = 0; e < p.E; ++e) {
-    if (mask[(size_t)t * p.E + e] && n < p.k) {
+    if (!mask[(size_t)t * p.E + e]) continue;
+    ++nset;
+    if (n < p.k) {
       p.topk_idx[(size_t)t * p.k + n] = e;
       p.topk_w[(size_t)t * p.k + n] = 1.0f;
       ++n;
     }
   }
+  // more experts per token than the context's top_k: rows would be dropped silently -> raise the sticky error flag
+  // (reported as B2M_EINVAL by the next call that synchronises: b2m_expert_outputs / b2m_check_errors)
+  if (nset > p.k && p.err_flag) atomicOr(p.err_flag, 1);
   for (; n < p.k; ++n) {
     p.topk_idx[(size_t)t * p.k + n] = -1;
     p.topk_w[(size_t)t * p.k + n] = 0.0f;

@@ -15,6 +15,7 @@ DTYPE_BF16, DTYPE_F32, DTYPE_F16, DTYPE_FP8 = 0, 1, 2, 3
 EXPERT_SWITCH, EXPERT_SWITCH_GATED, EXPERT_NLLB, EXPERT_FSGPT, EXPERT_MIXTRAL, EXPERT_DEEPSEEK = 0, 1, 2, 3, 4, 5
 ROUTER_MIXTRAL, ROUTER_DEEPSEEK_GREEDY, ROUTER_DEEPSEEK_GROUP, ROUTER_SWITCH_TOP1 = 0, 1, 2, 3
 NUMERICS_REFERENCE, NUMERICS_FP32 = 0, 1
+CACHE_REFERENCE, CACHE_SLOTS = 0, 1
 WS = dict(topk_idx=0, topk_w=1, row_of=2, perm_token=3, counts=4, offsets=5, xp=6, hmid=7, y=8, scores=9, logits=10)
 
 
@@ -26,7 +27,7 @@ class Config(C.Structure):
         ("num_slots", C.c_int32), ("shared_inter", C.c_int32), ("n_group", C.c_int32), ("topk_group", C.c_int32),
         ("norm_topk_prob", C.c_int32), ("expert_capacity", C.c_int32), ("routed_scaling_factor", C.c_float),
         ("gate_dtype", C.c_int32), ("device_memory_ratio", C.c_double), ("max_inflight_prefetch", C.c_int32),
-        ("h2d_chunk_bytes", C.c_int32), ("gemm_impl", C.c_int32), ("reserved", C.c_int32),
+        ("h2d_chunk_bytes", C.c_int32), ("gemm_impl", C.c_int32), ("cache_policy", C.c_int32),
     ]
 
 
@@ -61,6 +62,7 @@ SYMBOLS = [
     ("b2m_run_experts_ex", _I, [_VP, _I, _I, _I, _VP]),
     ("b2m_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
     ("b2m_expert_outputs", _I, [_VP, _I, _VP, C.POINTER(C.c_int), _VP]),
+    ("b2m_check_errors", _I, [_VP, _VP]),
     ("b2m_ws_ptr", _I, [_VP, _I, C.POINTER(_VP)]),
     ("b2m_replace_cache_candidates", _I, [_VP, _I, C.POINTER(C.c_int32)]),
     ("b2m_enqueue_prefetch", _I, [_VP, _I, _I]),

@@ -12,7 +12,8 @@ SOURCES = ["grouped_gemm.cu", "route.cu", "ep.cu", "api.cu"]
 HEADERS = ["b2m_common.cuh", "b2m_internal.h", "tile_walker.cuh", "ep_device.cuh",
            os.path.join("..", "..", "include", "b2m.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+OBJ_DIR = os.path.join(CSRC, "_obj")     # git-ignored (*.o); one object per translation unit, compiled in parallel
 
 
 def _nvcc() -> str:
@@ -33,12 +34,32 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+    procs, objs = [], []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    errs = []
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            errs.append(f"---- {src}\n{out}")
+    if errs:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
+    cmd = [_nvcc()] + NVCC_FLAGS[:2] + ["-shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

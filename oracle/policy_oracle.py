@@ -5,18 +5,25 @@ moe-infinity_b200/csrc/api.cu, which is itself the *explicit* version of the ref
 (contradicting) eviction loops:
 
   on-demand fetch   core/parallel/expert_dispatcher.cpp:227-266
-      miss and no free budget -> scan experts (expert-major: `for i in experts: for j in layers`), take the
-      GPU-resident node with the smallest incache_visit_count (strict '<': first one wins ties), evict it;
-      incache_visit_count += 1 for every dispatched expert (:264), hit = node was on the GPU (:219).
+      miss and `cache_sizes_[gpu] < byte_size` (:228) -> scan experts (expert-major: `for i in experts: for j in
+      layers`, :233-252), take the GPU-resident, unlocked node with the smallest incache_visit_count (strict '<': first
+      one wins ties), evict exactly that ONE node and refund its bytes (:256-257);
+      incache_visit_count += 1 for every dispatched expert (:264), hit = node was on the GPU (:219);
+      `cache_sizes_[gpu] -= byte_size` for EVERY dispatched expert, hit or miss (:266) -- the budget is charged for
+      hits as well, so it only ever equals the free HBM while the cache fills by misses alone (policy="reference";
+      policy="slots" charges nothing for hits and evicts only when no physical slot is free).
+      Eviction does not reset incache_visit_count; only clear_expert_cache_counts does (:175-185).
   prefetch          core/prefetch/task_scheduler.h:66-79 (ReplaceCacheCandidates: new protected set, queued
       prefetches dropped), task_scheduler.cpp:82-118 (dedupe), :236-317 (evict-to-fit, skipping protected
       candidates and nodes in use).
 Explicit choices (documented in DESIGN.md): victims are never experts of the dispatch in flight; a prefetch never
 evicts a protected expert (it is dropped instead); an on-demand miss may, as a last resort.
 
-Parity status: parity unpinned -- the reference has no test of its cache behaviour; this
-oracle pins *our* stated policy, and tests/test_gpu_offload.py demands the CUDA engine reproduce its
-hit/miss/eviction sequence exactly on seeded routing traces.
+Parity status: pinned for the on-demand path -- tests/golden/policy_ref_trace.json holds hit / resident-set sequences
+recorded from the reference's own compiled engine (oracle/_ref/prefetch_op.so driven by tools/ref_engine_harness.py
+--mode policy on a B200); tests/test_oracle_policy_ref.py demands this oracle reproduce them and
+tests/test_gpu_offload.py demands the CUDA engine reproduce the oracle.  The prefetch side (protected candidates,
+evict-to-fit) has no reference test and pins our stated policy only.
 """
 from __future__ import annotations
 
@@ -24,8 +31,10 @@ from typing import Iterable, List, Optional, Sequence, Set, Tuple
 
 
 class CacheOracle:
-    def __init__(self, num_layers: int, num_experts: int, num_slots: int):
+    def __init__(self, num_layers: int, num_experts: int, num_slots: int, policy: str = "reference"):
         self.L, self.E, self.nslots = num_layers, num_experts, num_slots
+        self.policy = policy
+        self.budget = num_slots            # cache_sizes_[gpu] in expert units (expert_dispatcher.cpp:52-54)
         n = num_layers * num_experts
         self.resident = [False] * n
         self.visits = [0] * n
@@ -67,6 +76,24 @@ class CacheOracle:
         self.evicted_log.append((v // self.E, v % self.E))
         return True
 
+    def _acquire_on_demand(self, in_use: Sequence[int]) -> bool:
+        """expert_dispatcher.cpp:227-258: budget used up -> evict exactly one victim."""
+        if self.free == 0 or (self.policy == "reference" and self.budget < 1):
+            v = self._victim(in_use, False)
+            if v < 0:
+                v = self._victim(in_use, True)
+            if v >= 0:
+                self.resident[v] = False
+                self.prefetched_unused[v] = False
+                self.stats["evictions"] += 1
+                self.evicted_log.append((v // self.E, v % self.E))
+                self.free += 1
+                self.budget += 1                                   # :257
+            elif self.free == 0:
+                return False
+        self.free -= 1
+        return True
+
     def dispatch(self, layer: int, experts: Iterable[int]) -> List[Tuple[int, bool]]:
         """One MoE layer call with the given activated experts.  Returns [(expert, hit)] sorted by expert.
         If the active set does not fit next to itself it is processed in waves (csrc/api.cu b2m_run_experts_ex):
@@ -86,13 +113,14 @@ class CacheOracle:
                         self.prefetched_unused[i] = False
                     out.append((i % self.E, True))
                 else:
-                    if not self._acquire(remaining, False):
+                    if not self._acquire_on_demand(remaining):
                         continue
                     self.stats["misses"] += 1
                     self.resident[i] = True
                     out.append((i % self.E, False))
                 self.stats["dispatches"] += 1
-                self.visits[i] += 1
+                self.visits[i] += 1                                # :264
+                self.budget -= 1                                   # :266, hit or miss
                 wave.append(i)
             if not wave:
                 raise RuntimeError("no evictable slot")

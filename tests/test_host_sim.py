@@ -154,6 +154,38 @@ def test_cache_policy_matches_oracle_on_cpu(sim):
         c.close()
 
 
+def _one_hot_logits(T, E, experts):
+    lg = np.full((T, E), -30.0, dtype=np.float32)
+    for t in range(T):
+        lg[t, experts[t % len(experts)]] = 5.0
+        lg[t, experts[(t + 1) % len(experts)]] = 4.0
+    return lg
+
+
+def test_reference_budget_charges_hits_on_cpu(sim):
+    """expert_dispatcher.cpp:266 subtracts byte_size for every dispatched expert, hit or miss: with hits before the cache
+    is full the budget runs out while physical slots are still free, and the next miss evicts (policy 'reference');
+    B2M_CACHE_SLOTS evicts only when no slot is free."""
+    for policy, name in ((L.CACHE_REFERENCE, "reference"), (L.CACHE_SLOTS, "slots")):
+        c = Ctx(sim, L_=2, E=8, num_slots=6, cache_policy=policy)
+        assert c.rc == 0, c.err()
+        c.register_all(7)
+        orc = CacheOracle(c.L, c.E, 6, policy=name)
+        seq = [(0, [0, 1]), (0, [0, 1]), (0, [0, 1]), (1, [2, 3]), (1, [4, 5]), (0, [6, 7]), (1, [0, 1])]
+        for l, ex in seq:
+            before = {e: c.resident(l, e) for e in ex}
+            assert c.forward(l, _one_hot_logits(4, c.E, ex)) == 0, c.err()
+            assert [(e, before[e]) for e in ex] == orc.dispatch(l, ex)
+            for ll in range(c.L):
+                for e in range(c.E):
+                    assert c.resident(ll, e) == orc.resident[ll * c.E + e], (name, l, ex, ll, e)
+        s = c.stats()
+        assert s["evictions"] == orc.stats["evictions"] and s["misses"] == orc.stats["misses"]
+        if name == "reference":
+            assert s["evictions"] > 0 and s["resident"] < 6     # budget used up by hits: evicts with free slots left
+        c.close()
+
+
 def test_all_resident_mode_never_syncs_on_cpu(sim):
     c = Ctx(sim, num_slots=24)                 # L*E slots: every expert fits
     c.register_all(4)
@@ -255,19 +287,22 @@ def test_launch_planning_on_cpu(sim):
         assert nt == 16 and ntd == 16 and ks > 1 and sk == 1 and ea_up == 1 and ea_dn == 1 and early == 1 and dual_m == 0
     assert plans[300][0] in (64, 128) and plans[300][6] == 0
     # few weight-row tiles (H=512 -> 4 m-tiles): even at T=4096 the planner splits K to fill the SMs
-    assert plans[4096][0] == 256 and plans[4096][2] > 1 and plans[4096][5] == 0 and plans[4096][6] == 0
+    # reference numerics keep the precise SiLU -> double-buffered 128-token tiles for the gate/up GEMM, 256 for the down GEMM
+    assert plans[4096][0] == 128 and plans[4096][1] == 256 and plans[4096][2] > 1 and plans[4096][5] == 0 and plans[4096][6] == 0
     c.close()
     # prefill with Mixtral's hidden size (32 m-tiles x 8 experts x 4 token tiles = 1024 tiles): 256-token tiles once the
     # average expert sees >= 256 tokens, no split-K, paired m-tiles (dual_m) in the down projection, no programmatic edges
-    c = Ctx(sim, L_=1, E=8, H=4096, I=256, k=2, max_tokens=4096, num_slots=8)
-    assert c.rc == 0, c.err()
-    c.register_all(2)
-    take_log(sim)
-    assert c.forward(0, rng.standard_normal((4096, c.E)).astype(np.float32)) == 0, c.err()
-    up, dn = [_kv(ln) for ln in take_log(sim) if ln.startswith("gemm")]
-    assert (up["nt"], dn["nt"], dn["ksplit"], dn["stream_k"], up["early_a"], dn["early_a"], dn["dual_m"]) == \
-        ("256", "256", "1", "0", "0", "0", "1")
-    c.close()
+    # (gate/up: 256 only with B2M_NUMERICS_FP32, whose MUFU SiLU keeps the single-TMEM-stage epilogue short)
+    for numerics, up_nt in ((L.NUMERICS_FP32, "256"), (L.NUMERICS_REFERENCE, "128")):
+        c = Ctx(sim, L_=1, E=8, H=4096, I=256, k=2, max_tokens=4096, num_slots=8, numerics=numerics)
+        assert c.rc == 0, c.err()
+        c.register_all(2)
+        take_log(sim)
+        assert c.forward(0, rng.standard_normal((4096, c.E)).astype(np.float32)) == 0, c.err()
+        up, dn = [_kv(ln) for ln in take_log(sim) if ln.startswith("gemm")]
+        assert (up["nt"], dn["nt"], dn["ksplit"], dn["stream_k"], up["early_a"], dn["early_a"], dn["dual_m"]) == \
+            (up_nt, "256", "1", "0", "0", "0", "1")
+        c.close()
 
 
 def test_bias_experts_plan_whole_k_on_cpu(sim):
