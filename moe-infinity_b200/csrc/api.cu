@@ -179,8 +179,8 @@ int fail(b2m_ctx* c, int code, const char* fmt, ...) {
       return fail((c), B2M_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-bool make_shape(int expert_type, int H, int I, ExpertShape* s) {
-  const size_t m = (size_t)H * I * 2;
+bool make_shape(int expert_type, int H, int I, ExpertShape* s, size_t esize = 2) {
+  const size_t m = (size_t)H * I * esize;
   s->H = H;
   s->I = I;
   switch (expert_type) {
@@ -199,8 +199,8 @@ bool make_shape(int expert_type, int H, int I, ExpertShape* s) {
     case B2M_EXPERT_NLLB_MOE_DENSE_ACT_DENSE:   // fc1 | fc1_bias | fc2 | fc2_bias  (:70-77; forward :88-92)
     case B2M_EXPERT_FSGPT_MOE_DENSE_ACT_DENSE:  // same binding (:104-111; forward :124-128, ReLU as well)
       s->dual = false; s->act = ACT_RELU; s->has_bias = true;
-      s->off_gate = 0; s->off_up = 0; s->off_bias1 = m; s->off_down = m + (size_t)I * 2;
-      s->off_bias2 = s->off_down + m; s->bytes = s->off_bias2 + (size_t)H * 2;   // H, I multiples of 8: all 16-B aligned
+      s->off_gate = 0; s->off_up = 0; s->off_bias1 = m; s->off_down = m + (size_t)I * esize;
+      s->off_bias2 = s->off_down + m; s->bytes = s->off_bias2 + (size_t)H * esize;   // H, I multiples of 8: all 16-B aligned
       return true;
     default:
       return false;
@@ -446,7 +446,7 @@ RouteParams base_route_params(b2m_ctx* c, int layer, const void* x, int T, int s
   p.seq_len = seq_len > 0 ? seq_len : T;
   p.expert_capacity = f.expert_capacity;
   p.scores = c->d_scores;
-  p.logits_out = c->d_logits;
+  p.logits_out = f.dtype == B2M_DTYPE_F32 ? nullptr : c->d_logits;
   p.topk_idx = c->d_topk_idx; p.topk_w = c->d_topk_w; p.row_of = c->d_row_of; p.perm_token = c->d_perm_token;
   p.counts = c->d_counts; p.offsets = c->d_offsets; p.chunk_counts = c->d_chunk_counts;
   p.xp = c->d_xp;
@@ -466,6 +466,7 @@ void plan_gemm(b2m_ctx* c, int T) {
   c->cur_nt = (up256 && c->cur_nt_dn == 256 && c->cfg.numerics == B2M_NUMERICS_FP32) ? 256 : pick_nt(T);
   c->cur_ksplit = pick_ksplit(c, T, c->cfg.hidden, c->cfg.inter, c->cfg.num_experts, c->cfg.top_k, c->cur_nt_dn);
   if (c->arena.shape.has_bias) c->cur_ksplit = 1;   // `+ fc2_bias` is applied once, in the epilogue of the whole-K product
+  if (c->cfg.dtype == B2M_DTYPE_F32) c->cur_ksplit = 1;   // CUDA-core fp32 path: whole-K tiles
 }
 
 // same switch as b2m_common.cuh:pdl_enabled() (that header is device code; this file also builds against the host emulation)
@@ -492,15 +493,16 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   if (!cfg || !out) return fail(nullptr, B2M_EINVAL, "null argument");
   if (cfg->struct_size != (int)sizeof(b2m_config))
     return fail(nullptr, B2M_EINVAL, "b2m_config size mismatch (%d vs %d)", cfg->struct_size, (int)sizeof(b2m_config));
-  if (cfg->dtype == B2M_DTYPE_FP8_E4M3 || cfg->dtype == B2M_DTYPE_F32)
-    return fail(nullptr, B2M_EUNSUPPORTED, "dtype %d: the tensor-core path supports bf16 and f16 experts", cfg->dtype);
-  if (cfg->dtype != B2M_DTYPE_BF16 && cfg->dtype != B2M_DTYPE_F16) return fail(nullptr, B2M_EINVAL, "bad dtype");
+  if (cfg->dtype == B2M_DTYPE_FP8_E4M3)
+    return fail(nullptr, B2M_EUNSUPPORTED, "dtype %d (fp8): the reference's own torch::matmul has no Float8 kernel; bf16, f16 and f32 experts are supported", cfg->dtype);
+  if (cfg->dtype != B2M_DTYPE_BF16 && cfg->dtype != B2M_DTYPE_F16 && cfg->dtype != B2M_DTYPE_F32) return fail(nullptr, B2M_EINVAL, "bad dtype");
+  const size_t esize = cfg->dtype == B2M_DTYPE_F32 ? 4 : 2;
   if (cfg->num_layers < 1 || cfg->num_experts < 1 || cfg->num_experts > 256 || cfg->top_k < 1 || cfg->top_k > 8 ||
       cfg->top_k > cfg->num_experts || cfg->hidden < 64 || cfg->inter < 64 || cfg->hidden % 8 || cfg->inter % 8 ||
       cfg->max_tokens < 1)
     return fail(nullptr, B2M_EINVAL, "bad model dimensions");
   ExpertShape shape;
-  if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape))
+  if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape, esize))
     return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is unknown (expert_module.h:13-18 defines 0..5)", cfg->expert_type);
   if (cfg->router < 0 || cfg->router > 3) return fail(nullptr, B2M_EINVAL, "bad router kind");
   if (cfg->cache_policy != B2M_CACHE_REFERENCE && cfg->cache_policy != B2M_CACHE_SLOTS) return fail(nullptr, B2M_EINVAL, "bad cache_policy");
@@ -560,17 +562,18 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   c->offload = nslots < (long long)L * E;
   CKC(cudaMalloc((void**)&c->arena.base, (size_t)nslots * shape.bytes));
   c->arena.owned = true;
-  int r = build_arena_maps(c, &c->arena);
+  const bool tc = cfg->dtype != B2M_DTYPE_F32;   // fp32 experts run on the CUDA-core path (f32_path.cu): no TMA maps
+  int r = tc ? build_arena_maps(c, &c->arena) : B2M_OK;
   if (r) { g_create_error = c->err; b2m_ctx_destroy(c); return r; }
   if (cfg->shared_inter > 0) {
     ExpertShape ss;
-    make_shape(B2M_EXPERT_DEEPSEEK_MOE_DENSE_ACT_DENSE, H, cfg->shared_inter, &ss);
+    make_shape(B2M_EXPERT_DEEPSEEK_MOE_DENSE_ACT_DENSE, H, cfg->shared_inter, &ss, esize);
     c->shared_arena.shape = ss;
     c->shared_arena.slot_bytes = ss.bytes;
     c->shared_arena.nslots = L;
     CKC(cudaMalloc((void**)&c->shared_arena.base, (size_t)L * ss.bytes));
     c->shared_arena.owned = true;
-    r = build_arena_maps(c, &c->shared_arena);
+    r = tc ? build_arena_maps(c, &c->shared_arena) : B2M_OK;
     if (r) { g_create_error = c->err; b2m_ctx_destroy(c); return r; }
     c->shared_registered.assign(L, 0);
   }
@@ -606,17 +609,17 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
   CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
   CKC(cudaMalloc((void**)&c->d_logits, sizeof(float) * (size_t)T * E));
-  CKC(cudaMalloc(&c->d_xp, R * H * 2));
-  CKC(cudaMalloc(&c->d_hmid, R * I * 2));
+  CKC(cudaMalloc(&c->d_xp, R * H * esize));
+  CKC(cudaMalloc(&c->d_hmid, R * I * esize));
   CKC(cudaMalloc((void**)&c->d_y, R * H * sizeof(float)));
-  CKC(cudaMemset(c->d_xp, 0, R * H * 2));
-  CKC(cudaMemset(c->d_hmid, 0, R * I * 2));
+  CKC(cudaMemset(c->d_xp, 0, R * H * esize));
+  CKC(cudaMemset(c->d_hmid, 0, R * I * esize));
   if (cfg->shared_inter > 0) {
-    CKC(cudaMalloc(&c->d_hmid_s, (size_t)T * cfg->shared_inter * 2));
-    CKC(cudaMemset(c->d_hmid_s, 0, (size_t)T * cfg->shared_inter * 2));
+    CKC(cudaMalloc(&c->d_hmid_s, (size_t)T * cfg->shared_inter * esize));
+    CKC(cudaMemset(c->d_hmid_s, 0, (size_t)T * cfg->shared_inter * esize));
     CKC(cudaMalloc((void**)&c->d_y_s, (size_t)T * H * sizeof(float)));
   }
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; tc && i < 5; ++i) {
     r = build_act_map(c, &c->tm_xp[i], c->d_xp, H, (int)R, NT_LIST[i]);
     if (!r) r = build_act_map(c, &c->tm_hmid[i], c->d_hmid, I, (int)R, NT_LIST[i]);
     if (!r && cfg->shared_inter > 0) r = build_act_map(c, &c->tm_hmid_s[i], c->d_hmid_s, cfg->shared_inter, T, NT_LIST[i]);
@@ -793,6 +796,8 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   cudaStream_t st = (cudaStream_t)stream;
   RouteParams p = base_route_params(c, layer, x, T, seq_len);
   if (kind == 0) {
+    if (c->cfg.dtype == B2M_DTYPE_F32)
+      return fail(c, B2M_EUNSUPPORTED, "fp32 contexts take router logits / scores (or a mask): the fused gate kernel reads 16-bit activations");
     if (!p.gate_w) return fail(c, B2M_ESTATE, "layer %d has no gate weight (b2m_set_gate) and no router input", layer);
   } else {
     if (!router_in) return fail(c, B2M_EINVAL, "router_in is null");
@@ -859,15 +864,24 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
   GemmParams dn = base;
   dn.M = s.H; dn.K = s.I; dn.ksplit = ksplit; dn.epi = EPI_LINEAR_F32; dn.act = ACT_NONE; dn.mimic = 0;
   dn.out = y; dn.ld_out = s.H;
+  const size_t esz = f.dtype == B2M_DTYPE_F32 ? 4 : 2;
   if (s.has_bias) {
     up.bias_base = dn.bias_base = a.base;
-    up.bias_slot_elems = dn.bias_slot_elems = a.slot_bytes / 2;
-    up.bias_off = s.off_bias1 / 2;
-    dn.bias_off = s.off_bias2 / 2;
+    up.bias_slot_elems = dn.bias_slot_elems = a.slot_bytes / esz;
+    up.bias_off = s.off_bias1 / esz;
+    dn.bias_off = s.off_bias2 / esz;
     dn.ksplit = 1;
     dn.mimic = up.mimic;     // round(matmul) + bias -> round happens here; the combine's rounding is then the identity
   }
-  if (f.gemm_impl == 1) {
+  if (f.dtype == B2M_DTYPE_F32) {
+    // fp32 experts: CUDA-core fp32 FMA path (f32_path.cu); whole-K tiles, fp32 intermediate
+    const size_t slot_elems = a.slot_bytes / 4;
+    dn.ksplit = 1;
+    if (phases & 1)
+      CK(c, launch_grouped_gemm_f32(a.base, slot_elems, s.off_gate / 4, s.off_up / 4, b_up, ldb_up, up, s.dual, c->num_sms, st));
+    if (phases & 2)
+      CK(c, launch_grouped_gemm_f32(a.base, slot_elems, s.off_down / 4, s.off_down / 4, b_down, s.I, dn, false, c->num_sms, st));
+  } else if (f.gemm_impl == 1) {
     const size_t slot_elems = a.slot_bytes / 2;
     if (phases & 1)
       CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_gate / 2, s.off_up / 2, b_up, ldb_up, up, s.dual, st));
@@ -1035,9 +1049,10 @@ static int run_shared(b2m_ctx* c, int layer, const void* x, int T, cudaStream_t 
   const int nt = pick_nt(T);
   const int ks = pick_ksplit(c, T, c->cfg.hidden, c->cfg.shared_inter, 1, 1, nt);
   CUtensorMap tm_x;
-  int r = build_act_map(c, &tm_x, const_cast<void*>(x), c->cfg.hidden, T, nt);
+  memset(&tm_x, 0, sizeof tm_x);
+  int r = c->cfg.dtype == B2M_DTYPE_F32 ? B2M_OK : build_act_map(c, &tm_x, const_cast<void*>(x), c->cfg.hidden, T, nt);
   if (r) return r;
-  if (ks > 1) CK(c, cudaMemsetAsync(c->d_y_s, 0, (size_t)T * c->cfg.hidden * sizeof(float), st));
+  if (ks > 1 && c->cfg.dtype != B2M_DTYPE_F32) CK(c, cudaMemsetAsync(c->d_y_s, 0, (size_t)T * c->cfg.hidden * sizeof(float), st));
   GemmParams base;
   memset(&base, 0, sizeof base);
   base.E = 1;
@@ -1249,6 +1264,7 @@ static EpParams ep_base(b2m_ctx* c, int nranks, int rank, int cap) {
 }
 static int ep_check(b2m_ctx* c, int nranks, int rank, int cap) {
   if (!c) return B2M_EINVAL;
+  if (c->cfg.dtype == B2M_DTYPE_F32) return fail(c, B2M_EUNSUPPORTED, "expert parallel exchange handles 16-bit models");
   if (nranks < 2 || nranks > 16 || rank < 0 || rank >= nranks || c->cfg.num_experts % nranks || cap < 1)
     return fail(c, B2M_EINVAL, "bad expert-parallel geometry (nranks=%d rank=%d cap=%d E=%d)", nranks, rank, cap, c->cfg.num_experts);
   if ((long long)nranks * cap > c->cap_R)

@@ -60,6 +60,9 @@ cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& 
 cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_elems, size_t offA0, size_t offA1,
                                      const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st);
 int gemm_tc_smem_bytes(int nt, bool dual);
+// fp32 experts (dtype int 1): CUDA-core fp32 FMA kernel, f32_path.cu.  Offsets/slot sizes in fp32 elements.
+cudaError_t launch_grouped_gemm_f32(const void* arena, size_t slot_elems, size_t offA0, size_t offA1, const void* B,
+                                    int ldb, const GemmParams& p, bool dual, int num_sms, cudaStream_t st);
 
 // ---- expert-parallel dispatch helpers (ep.cu) ----------------------------------------------
 struct EpParams {
@@ -151,6 +154,7 @@ struct CombineParams {
   EpParams ep;
 };
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
+cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t st);
 
 // fp32 [rows,H] -> model dtype [rows,H] (compat path: per-expert outputs handed back to Python)
 cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st);

@@ -28,6 +28,8 @@ __device__ __forceinline__ float load_as_float(const void* p, size_t i, int dt) 
   const uint16_t b = reinterpret_cast<const uint16_t*>(p)[i];
   return dt == DT_BF16 ? Half16<DT_BF16>::to_f(b) : Half16<DT_F16>::to_f(b);
 }
+// bytes of one hidden row of the model dtype (fp32 models: 4-byte elements; rows stay multiples of 16 B since H % 8 == 0)
+__device__ __forceinline__ size_t row_bytes(const RouteParams& p) { return (size_t)p.H * (p.dtype == DT_F32 ? 4 : 2); }
 __device__ __forceinline__ float round_to(float f, int dt) {
   if (dt == DT_BF16) return round_dt<DT_BF16>(f);
   if (dt == DT_F16) return round_dt<DT_F16>(f);
@@ -494,13 +496,14 @@ __device__ __forceinline__ void chunk_rank_strided(const RouteParams& p, int t0,
 __device__ void copy_rows_block(const RouteParams& p, int t0, int npairs, const int* s_rows, int warp0, int nwarps) {
   const int lane = threadIdx.x & 31;
   const int warp = (threadIdx.x >> 5) - warp0;
-  const int vec_per_row = p.H / 8;   // uint4 = 8 x 16-bit
+  const size_t rb = row_bytes(p);
+  const int vec_per_row = (int)(rb / 16);   // uint4 = 8 x 16-bit (4 x fp32)
   for (int i = warp; i < npairs; i += nwarps) {
     const int row = s_rows[i];
     const int t = t0 + i / p.k;
     if (row < 0 || t >= p.T) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + (size_t)t * rb);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.xp) + (size_t)row * rb);
     int v = lane;
     for (; v + 96 < vec_per_row; v += 128) {   // 4 independent 16 B loads in flight per lane
       const uint4 a = src[v], b = src[v + 32], c = src[v + 64], d = src[v + 96];
@@ -783,12 +786,13 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   pdl_wait();
   if (p.rows_by_gate) {
     // the gate/top-k kernel already published counts, offsets and the row maps: this kernel is a pure row copy
-    const int vpr = p.H / 8;
+    const size_t rb = row_bytes(p);
+    const int vpr = (int)(rb / 16);
     for (int i = blockIdx.x; i < npairs; i += gridDim.x) {
       const int row = p.row_of[i];
       if (row < 0) continue;
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)(i / p.k) * p.H);
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + (size_t)(i / p.k) * rb);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.xp) + (size_t)row * rb);
       for (int v = threadIdx.x; v < vpr; v += RT_THREADS) dst[v] = src[v];
     }
     if (p.y_zero) {
@@ -882,12 +886,13 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   }
   __syncthreads();
   // gather: CTA b copies rows b, b+grid, ...; the whole CTA moves one row (H*2 bytes) with 16 B vectors
-  const int vec_per_row = p.H / 8;
+  const size_t rb = row_bytes(p);
+  const int vec_per_row = (int)(rb / 16);
   for (int i = blockIdx.x; i < npairs; i += gridDim.x) {
     const int row = s_rows[i];
     if (row < 0) continue;
     const int t = i / p.k;
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + (size_t)t * rb);
     uint4* dst;
     if (p.ep_dispatch) {
       // expert-parallel: the row goes to the rank that owns its expert (peer memory over NVLink, or the send buffer)
@@ -896,7 +901,7 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
       const int r = e / El;
       dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, r, row - s_off[r * El]));
     } else {
-      dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.xp) + (size_t)row * p.H);
+      dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.xp) + (size_t)row * rb);
     }
     for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
   }
@@ -923,6 +928,7 @@ static bool route_args_ok(const RouteParams& p) {
 
 cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   if (!route_args_ok(p)) return cudaErrorInvalidValue;
+  if (p.dtype == DT_F32 && (!p.logits || p.ep_dispatch)) return cudaErrorInvalidValue;   // fp32 models: router logits/scores come in
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
     cudaError_t e = launch_pdl(gate_topk_small_kernel, dim3(p.T), dim3(RT_THREADS), 0, st, p);
@@ -1127,6 +1133,7 @@ cudaError_t launch_combine(const CombineParams& p, cudaStream_t st) {
   if (p.k > MAX_K || p.H % 8 != 0) return cudaErrorInvalidValue;
   int gy = (p.H + CB_THREADS * 8 - 1) / (CB_THREADS * 8);
   dim3 grid(p.T, gy);
+  if (p.dtype == DT_F32) return launch_combine_f32(p, st);
   if (p.dtype == DT_BF16) return launch_pdl(combine_kernel<DT_BF16>, grid, dim3(CB_THREADS), 0, st, p);
   if (p.dtype == DT_F16) return launch_pdl(combine_kernel<DT_F16>, grid, dim3(CB_THREADS), 0, st, p);
   return cudaErrorInvalidValue;
@@ -1149,6 +1156,7 @@ cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cud
   if (n == 0) return cudaSuccess;
   if (n % 8) return cudaErrorInvalidValue;
   const int blocks = (int)((n / 8 + 255) / 256 < 148 * 8 ? (n / 8 + 255) / 256 : 148 * 8);
+  if (dtype == DT_F32) return cudaMemcpyAsync(out, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
   if (dtype == DT_BF16) cast_rows_kernel<DT_BF16><<<blocks, 256, 0, st>>>(y, (uint16_t*)out, n);
   else if (dtype == DT_F16) cast_rows_kernel<DT_F16><<<blocks, 256, 0, st>>>(y, (uint16_t*)out, n);
   else return cudaErrorInvalidValue;

@@ -11,6 +11,13 @@ Differences, on purpose:
     reader itself (core/aio) is out of scope;
   * errors raise RuntimeError/B2MError instead of aborting the process;
   * `wait_expert` returns experts in ascending expert id (the reference returns completion order, Q1).
+
+Construction is signature-compatible with the reference: `prefetch_handle(prefix, ratio)` and
+`expert_dispatcher(num_experts, num_layers, dtype, expert_type, num_threads)` (py_archer_prefetch.cpp:12,85), so
+moe_infinity/runtime/model_offload.py:143-145,471-477 runs unchanged.  The dispatcher finds its handle the way the
+reference does -- through process-wide state (the reference's kTopologyHandle / kArcherTensorHandle singletons,
+archer_prefetch_handle.cpp:18-28): the most recently constructed prefetch_handle -- and learns top_k from the router
+masks it is handed (the reference has no such notion: every set mask bit runs, expert_dispatcher.cpp:274-285).
 """
 from __future__ import annotations
 
@@ -48,10 +55,15 @@ class _LazyTensors(dict):
         return dict.__contains__(self, tensor_id) or (self._store is not None and tensor_id in self._store)
 
 
+_CURRENT_HANDLE: Optional["prefetch_handle"] = None     # the reference keeps exactly one per process (global singletons)
+
+
 class prefetch_handle:  # noqa: N801  (reference spelling)
     """py_archer_prefetch.cpp:11-80.  Host-DRAM tensor store + the residency/prefetch façade."""
 
     def __init__(self, prefix: str, device_memory_ratio: float, persistent: bool = False):
+        global _CURRENT_HANDLE
+        _CURRENT_HANDLE = self
         self.prefix = prefix
         self.device_memory_ratio = float(device_memory_ratio)
         # persistent=True: `prefix` is an offload directory in the reference's on-disk format (store.py): `offload`
@@ -150,41 +162,71 @@ class expert_dispatcher:  # noqa: N801
     def __init__(self, num_experts: int, num_layers: int, dtype: int, expert_type: int, num_threads: int = 8,
                  handle: Optional[prefetch_handle] = None, top_k: Optional[int] = None, max_tokens: int = 4096,
                  num_slots: int = 0, **engine_kw):
+        """The five positional arguments are the reference's (py_archer_prefetch.cpp:85); the keywords are optional
+        extras: `handle` (default: the process's current prefetch_handle), `top_k` (default: learnt from the masks),
+        workspace / cache sizing."""
         if dtype not in _INT2DTYPE:
             raise ValueError(f"dtype int {dtype} unsupported")
         self.num_experts, self.num_layers = num_experts, num_layers
         self.dtype, self.expert_type = _INT2DTYPE[dtype], expert_type
         self.num_threads = num_threads   # accepted for signature parity; the CUDA path needs no worker threads
-        self.handle = handle
+        self.handle = handle if handle is not None else _CURRENT_HANDLE
         self.top_k = top_k
         self.max_tokens, self.num_slots, self.engine_kw = max_tokens, num_slots, engine_kw
         self.engine: Optional[MoEEngine] = None
+        self._registered: Dict[Tuple[int, int], List[int]] = {}    # (layer, expert) -> tensor ids, in registration order
         self._queue: List[Tuple[int, int]] = []
         self._inputs = None
         self._expected = 0
-        if handle is not None:
-            handle._dispatcher = self
+        if self.handle is not None:
+            self.handle._dispatcher = self
 
-    def _ensure_engine(self, tensors: Sequence[torch.Tensor]):
+    def _default_k(self) -> int:
+        if self.top_k:
+            return self.top_k
+        if self.expert_type in (L.EXPERT_SWITCH, L.EXPERT_SWITCH_GATED):
+            return 1
+        return 6 if self.expert_type == L.EXPERT_DEEPSEEK else 2       # grows on demand (see _fit)
+
+    def _build_engine(self, k: int, max_tokens: int):
+        """(Re)create the CUDA context for (k, max_tokens) and hand it every registered expert."""
         if self.engine is not None:
-            return
-        inter, hidden = tensors[0].shape   # first tensor is [I,H] for every supported expert type
-        k = self.top_k or (1 if self.expert_type in (L.EXPERT_SWITCH, L.EXPERT_SWITCH_GATED) else 2)
+            self.engine.close()
+        any_ids = next(iter(self._registered.values()))
+        inter, hidden = self.handle._tensors[int(any_ids[0])].shape   # first tensor is [I,H] for every supported expert type
         ratio = self.handle.device_memory_ratio if self.handle else 0.0
+        self.max_tokens = max_tokens
         self.engine = MoEEngine(num_layers=self.num_layers, num_experts=self.num_experts, hidden=hidden, inter=inter,
                                 top_k=k, dtype=self.dtype, expert_type=self.expert_type,
-                                router=_ROUTER_OF_TYPE[self.expert_type], max_tokens=self.max_tokens,
+                                router=_ROUTER_OF_TYPE[self.expert_type], max_tokens=max_tokens,
                                 num_slots=self.num_slots, device_memory_ratio=ratio, **self.engine_kw)
+        for (l, e), ids in self._registered.items():
+            self.engine.register_expert(l, e, [self.handle._tensors[int(t)] for t in ids])
+
+    def _fit(self, k_needed: int, T: int):
+        """The reference runs every set mask bit for any number of tokens; our context is sized by (top_k, max_tokens):
+        grow it when a call needs more (rare: the first call of a model, or a longer prompt than any before)."""
+        if self.engine is None or k_needed > self.engine.k or T > self.max_tokens:
+            k = max(k_needed, self.engine.k if self.engine is not None else self._default_k())
+            mt = self.max_tokens
+            while mt < T:
+                mt *= 2
+            self._build_engine(k, mt)
 
     def register_expert(self, layer_idx: int, expert_idx: int, tensor_ids: Sequence[int]):
         """All ids belong to one expert, in named_parameters order (expert_dispatcher.cpp:160-173)."""
         if self.handle is None:
-            raise RuntimeError("expert_dispatcher needs the prefetch_handle that stores the tensors")
-        tensors = [self.handle._tensors[int(t)] for t in tensor_ids]
-        self._ensure_engine(tensors)
-        self.engine.register_expert(layer_idx, expert_idx, tensors)
-        for t in tensor_ids:
-            self.handle._node_of[int(t)] = (layer_idx, expert_idx)
+            raise RuntimeError("expert_dispatcher needs a prefetch_handle (construct it first, as model_offload.py does)")
+        ids = [int(t) for t in tensor_ids]
+        for t in ids:
+            if t not in self.handle._tensors:
+                raise RuntimeError(f"tensor id {t} was never offloaded")
+            self.handle._node_of[t] = (layer_idx, expert_idx)
+        self._registered[(layer_idx, expert_idx)] = ids
+        if self.engine is not None:
+            self.engine.register_expert(layer_idx, expert_idx, [self.handle._tensors[t] for t in ids])
+        elif self.top_k:
+            self._build_engine(self.top_k, self.max_tokens)    # sizes known up front: build now (and register this expert)
 
     def set_inputs(self, hidden_states: torch.Tensor, router_mask: torch.Tensor):
         self._inputs = (hidden_states, router_mask)   # no clones: reads are stream ordered (reference clones both)
@@ -209,6 +251,9 @@ class expert_dispatcher:  # noqa: N801
         sel = torch.zeros(E, dtype=torch.bool, device=m.device)
         sel[wanted] = True
         m = m.ne(0) & sel[None, :]
+        # experts per token this call needs (the reference's own dispatch_local already synchronises here, :34-39)
+        k_needed = int(m.sum(dim=-1).max().item()) if m.numel() else 0
+        self._fit(max(k_needed, 1), x.shape[0])
         T = self.engine.route_from_mask(layer, x, m)
         resident_before = {e: self.engine.is_resident(layer, e) for e in wanted}
         self.engine.run_experts(layer, T)

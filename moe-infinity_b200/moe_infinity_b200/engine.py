@@ -82,12 +82,13 @@ class MoEEngine:
         self._h = h
         self._blobs: Dict[Tuple[int, int], torch.Tensor] = {}
         self._gates: Dict[int, torch.Tensor] = {}
+        es = self.esize = 4 if dtype == torch.float32 else 2   # fp32 experts (dtype int 1) run on the CUDA-core fp32 path
         if expert_type in (L.EXPERT_NLLB, L.EXPERT_FSGPT):     # fc1 | fc1_bias | fc2 | fc2_bias (expert_module.cpp:70-77)
-            self.expert_bytes = 2 * hidden * inter * 2 + (inter + hidden) * 2
+            self.expert_bytes = 2 * hidden * inter * es + (inter + hidden) * es
         else:
             nmat = 2 if expert_type == L.EXPERT_SWITCH else 3
-            self.expert_bytes = nmat * hidden * inter * 2
-        self.shared_bytes = 3 * hidden * shared_inter * 2
+            self.expert_bytes = nmat * hidden * inter * es
+        self.shared_bytes = 3 * hidden * shared_inter * es
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -112,7 +113,7 @@ class MoEEngine:
         off = 0
         for t in tensors:
             t = t.detach().to("cpu", self.dtype).contiguous()
-            n = t.numel() * 2
+            n = t.numel() * self.esize
             blob[off:off + n] = t.view(torch.uint8).reshape(-1)
             off += n
         if off != nbytes:
@@ -134,7 +135,7 @@ class MoEEngine:
         self._ck(self.lib.b2m_expert_dev_ptr(self._h, layer, expert, C.byref(p)))
         if not p.value:
             return None
-        return _view(p.value, (self.expert_bytes // 2,), self.dtype, self.device)
+        return _view(p.value, (self.expert_bytes // self.esize,), self.dtype, self.device)
 
     def load_expert(self, layer: int, expert: int, tensors: Optional[Sequence[torch.Tensor]] = None):
         """HBM-only expert: claims a slot, pins it, fills it from `tensors` (any device) if given.

@@ -7,8 +7,9 @@ logits/scores, and the outputs of the literal reference block
 pure-torch `expert_executor` stand-in that calls the block's own HF expert modules in
 ascending expert order (the authors' commented loop, mixtral.py:103-113).
 Weights are not stored (regenerated from the seed; a checksum guards generator drift).
-Switch fixtures come from the oracle only: HF 5.5's router signature differs from the 4.x
-one the reference block expects, so the literal block cannot run here.
+Switch fixtures: the literal SyncSwitchTransformersSparseMLP (switch_transformers.py:41-113) runs on a 4.x-order router
+shim (tests/shims/ref_loader.py shim 5: HF 5.5's router returns a different tuple), with HF's own
+SwitchTransformersDenseActDense experts; generation asserts literal == oracle bit for bit.
 """
 from __future__ import annotations
 
@@ -127,6 +128,40 @@ def run_literal_deepseek(ns, H, I, E, k, n_shared, hidden, gate_w, experts, shar
     return out
 
 
+def run_literal_switch(ns, D, Fd, E, cap, hidden, gate_w, experts):
+    from transformers import SwitchTransformersConfig
+    cfg = SwitchTransformersConfig(d_model=D, d_ff=Fd, num_experts=E, expert_capacity=cap, router_bias=False,
+                                   router_jitter_noise=0.0, router_dtype="float32", dropout_rate=0.0,
+                                   dense_act_fn="relu", num_layers=1, num_sparse_encoder_layers=1)
+    blk = ns.switch.SyncSwitchTransformersSparseMLP(cfg)
+    blk = blk.to(hidden.dtype)
+    blk.eval()
+    with torch.no_grad():
+        blk.router.classifier.weight.copy_(gate_w)
+        for e in range(E):
+            blk.experts[f"expert_{e}"].wi.weight.copy_(experts[e][0])
+            blk.experts[f"expert_{e}"].wo.weight.copy_(experts[e][1])
+    ex = _StandInExecutor(blk)
+    ex.dispatch_local = lambda h, m, lid: [(blk.experts[f"expert_{e}"](h.reshape(-1, h.shape[-1])[m.reshape(-1, E)[:, e].bool()]),
+                                            lid, e, 1) for e in range(E) if bool(m.reshape(-1, E)[:, e].any())]
+    blk.expert_executor = ex
+    blk.layer_id = 0
+    # the block's last line moves its auxiliary outputs to "cuda:0" (switch_transformers.py:110-113): on CPU, stand in
+    orig_to = torch.Tensor.to
+
+    def _to(self, *a, **kw):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda") and not torch.cuda.is_available():
+            return self
+        return orig_to(self, *a, **kw)
+    torch.Tensor.to = _to
+    try:
+        with torch.no_grad():
+            out, (logits, expert_index) = blk(hidden)
+    finally:
+        torch.Tensor.to = orig_to
+    return out, logits, expert_index
+
+
 def build_mixtral(name):
     H, I, E, k, B, S, dtype, seed = MIXTRAL_CASES[name]
     experts = O.make_experts(E, H, I, dtype, seed, O.MIXTRAL_MOE_DENSE_ACT_DENSE, std=0.05)
@@ -150,7 +185,10 @@ def build_switch(name):
     D, Fd, E, cap, B, S, dtype, seed = SWITCH_CASES[name]
     experts = O.make_experts(E, D, Fd, dtype, seed, O.SWITCH_DENSE_ACT_DENSE, std=0.05)
     return dict(H=D, I=Fd, E=E, capacity=cap, B=B, S=S, dtype=dtype, seed=seed, experts=experts,
-                hidden=gen_hidden(B, S, D, dtype, seed), gate=gen_gate(E, D, torch.float32, seed, std=2.0))
+                hidden=gen_hidden(B, S, D, dtype, seed),
+                # the classifier is a parameter of a `dtype` model that the router up-casts to fp32 per call (HF
+                # _cast_classifier): its fp32 values are exactly representable in the model dtype
+                gate=gen_gate(E, D, dtype, seed, std=2.0).float())
 
 
 def main():
@@ -216,12 +254,20 @@ def main():
     for name in SWITCH_CASES:
         c = build_switch(name)
         out, (logits, expert_index), router_mask = O.switch_block(c["hidden"], c["gate"], c["experts"], c["capacity"])
-        torch.save(dict(kind="switch", source="oracle",
+        src = "oracle"
+        if ns is not None and hasattr(ns, "switch"):
+            l_out, l_logits, l_index = run_literal_switch(ns, c["H"], c["I"], c["E"], c["capacity"], c["hidden"], c["gate"],
+                                                          c["experts"])
+            assert torch.equal(l_logits.float(), logits.float()), f"{name}: literal router logits != oracle"
+            assert torch.equal(l_index, expert_index), f"{name}: literal expert index != oracle"
+            assert torch.equal(l_out, out), f"{name}: literal != oracle"
+            out, src = l_out, "literal"
+        torch.save(dict(kind="switch", source=src,
                         cfg={k: c[k] for k in ("H", "I", "E", "capacity", "B", "S", "seed")}, dtype=str(c["dtype"]),
                         weight_checksum=checksum([w for e in c["experts"] for w in e]), hidden=c["hidden"],
                         gate=c["gate"], router_logits=logits, expert_index=expert_index, router_mask=router_mask,
                         out=out), os.path.join(HERE, name + ".pt"))
-        print(name, "oracle ok")
+        print(name, src, "ok")
 
 
 if __name__ == "__main__":

@@ -116,7 +116,9 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
 
 cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cudaStream_t) {
   for (int t = 0; t < p.T; ++t) {
-    int j = 0;
+    int j = 0, nset = 0;
+    for (int e = 0; e < p.E; ++e) nset += mask[(size_t)t * p.E + e] ? 1 : 0;
+    if (nset > p.k && p.err_flag) *p.err_flag |= 1;
     for (int e = 0; e < p.E && j < p.k; ++e)
       if (mask[(size_t)t * p.E + e]) { p.topk_idx[(size_t)t * p.k + j] = e; p.topk_w[(size_t)t * p.k + j] = 1.f; ++j; }
     for (; j < p.k; ++j) { p.topk_idx[(size_t)t * p.k + j] = -1; p.topk_w[(size_t)t * p.k + j] = 0.f; }
@@ -140,10 +142,16 @@ cudaError_t launch_grouped_gemm_tc_mc2(int, bool dual, const CUtensorMap&, const
                                        const GemmParams& p, int, cudaStream_t) { return log_gemm("tc_mc2", 128, dual, p); }
 cudaError_t launch_grouped_gemm_simt(int, const void*, size_t, size_t, size_t, const void*, int, const GemmParams& p,
                                      bool dual, cudaStream_t) { return log_gemm("simt", 0, dual, p); }
+cudaError_t launch_grouped_gemm_f32(const void*, size_t, size_t, size_t, const void*, int, const GemmParams& p, bool dual,
+                                    int, cudaStream_t) { return log_gemm("f32", 0, dual, p); }
+cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t) {
+  logf("combine_f32 T=%d mode=%d", p.T, p.mode);
+  return cudaSuccess;
+}
 int gemm_tc_smem_bytes(int, bool) { return 200 * 1024; }
 
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t) {
-  logf("combine T=%d mode=%d shared=%d ep_collect=%d", p.T, p.mode, p.y_shared ? 1 : 0, p.ep_collect);
+  logf("combine T=%d mode=%d shared=%d ep_collect=%d dtype=%d", p.T, p.mode, p.y_shared ? 1 : 0, p.ep_collect, p.dtype);
   return cudaSuccess;
 }
 cudaError_t launch_cast_rows(const float*, void*, size_t n, int, cudaStream_t) { logf("cast_rows n=%zu", n); return cudaSuccess; }

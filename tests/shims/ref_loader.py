@@ -1,4 +1,5 @@
-"""Load the *literal* reference hot-path files from /root/reference on CPU (dev container only).
+"""Load the *literal* reference hot-path files: from /root/reference (dev container) or, where that does not exist (the
+GPU box), from their byte-compiled form under oracle/_ref/pyref/ (built by oracle/ref_build/stage_pyref.py).
 
 The reference package cannot be imported as is (no `accelerate`, transformers 5.5 vs the
 4.x names it uses, ExpertTracer allocating on cuda:0) -- SURVEY.md §8(c).  Four small
@@ -8,7 +9,11 @@ shims make the hot-path files load unmodified:
   2. a fake `accelerate` exposing the three names the reference touches;
   3. a 4.x-style `MixtralBlockSparseTop2MLP` (w1,w2,w3 nn.Linear) injected into
      transformers.models.mixtral.modeling_mixtral;
-  4. transformers.utils.import_utils.is_torch_fx_available = lambda: False.
+  4. transformers.utils.import_utils.is_torch_fx_available = lambda: False;
+  5. a 4.x-order `SwitchTransformersTop1Router` (returns `(expert_mask, router_probs, router_logits)`, the tuple
+     moe_infinity/models/switch_transformers.py:76 unpacks) installed in HF's modeling_switch_transformers: HF 5.5's
+     router returns `(probs, index, logits)` and computes the capacity cumsum over a size-1 axis.  The shim restates
+     the forward of transformers 4.37-4.4x (the version range the reference pins, requirements.txt:19).
 Nothing here is copied from the reference; the files are executed from where they lie.
 This module is test infrastructure and is never imported by the product package.
 """
@@ -19,11 +24,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("B2M_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_CANDIDATES = [os.environ.get("B2M_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "oracle", "_ref", "pyref")]
+REF_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "moe_infinity", "models"))), "/root/reference")
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "moe_infinity", "models"))
+
+
+def is_source_tree() -> bool:
+    """True when REF_ROOT holds the reference's .py sources (dev container), False for the byte-compiled staging."""
+    return os.path.exists(os.path.join(REF_ROOT, "moe_infinity", "models", "mixtral.py"))
 
 
 _loaded = {}
@@ -86,6 +98,42 @@ def load():
     if not hasattr(iu, "is_torch_fx_available"):
         iu.is_torch_fx_available = lambda: False
 
+    # shim 5: HF 4.x router output order and capacity semantics for the literal Switch block
+    import transformers.models.switch_transformers.modeling_switch_transformers as ms
+    if not getattr(ms.SwitchTransformersTop1Router, "_b2m_4x_order", False):
+        _Base = ms.SwitchTransformersTop1Router
+
+        class SwitchTransformersTop1Router(_Base):   # same name, same constructor
+            _b2m_4x_order = True
+
+            def forward(self, hidden_states):
+                self.input_dtype = hidden_states.dtype
+                hidden_states = hidden_states.to(self.dtype)
+                self.classifier = self.classifier.to(self.dtype)
+                router_logits = self.classifier(hidden_states)
+                router_probs = nn.functional.softmax(router_logits, dim=-1, dtype=self.dtype).to(self.input_dtype)
+                expert_index = torch.argmax(router_probs, dim=-1)
+                expert_index = torch.nn.functional.one_hot(expert_index, num_classes=self.num_experts)
+                token_priority = torch.cumsum(expert_index, dim=-2)          # per batch row, over the sequence
+                expert_capacity_mask = token_priority <= self.expert_capacity
+                expert_index = expert_index * expert_capacity_mask
+                router_probs = torch.max(router_probs, dim=-1).values.unsqueeze(-1)
+                return expert_index, router_probs, router_logits
+        ms.SwitchTransformersTop1Router = SwitchTransformersTop1Router
+
+    # byte-compiled staging only: HF's docstring decorators call inspect.getsource() on the decorated forward(); there is
+    # no source text on the GPU box, so fall back to the default indentation (affects generated docstrings only)
+    if not is_source_tree():
+        import transformers.utils.doc as hfdoc
+        _orig_indent = hfdoc.get_docstring_indentation_level
+
+        def _indent_or_default(fn):
+            try:
+                return _orig_indent(fn)
+            except OSError:
+                return 4
+        hfdoc.get_docstring_indentation_level = _indent_or_default
+
     # shim 1: stub packages
     base = os.path.join(REF_ROOT, "moe_infinity")
     _stub_pkg("moe_infinity", base)
@@ -109,7 +157,16 @@ def load():
         ns.expert_predictor = importlib.import_module("moe_infinity.memory.expert_predictor")
         ns.expert_prefetcher = importlib.import_module("moe_infinity.memory.expert_prefetcher")
         ns.expert_tracer = importlib.import_module("moe_infinity.memory.expert_tracer")
+        m = sys.modules["moe_infinity.memory"]
+        for n, mod in (("ExpertPredictor", ns.expert_predictor), ("ExpertPrefetcher", ns.expert_prefetcher),
+                       ("ExpertTracer", ns.expert_tracer)):
+            if not hasattr(m, n):
+                setattr(m, n, getattr(mod, n))
     except Exception as e:  # pragma: no cover - memory/* are optional for the block tests
         ns.memory_import_error = e
+    try:
+        ns.switch = importlib.import_module("moe_infinity.models.switch_transformers")   # needs memory.ExpertPredictor
+    except Exception as e:  # pragma: no cover
+        ns.switch_import_error = e
     _loaded["ns"] = ns
     return ns

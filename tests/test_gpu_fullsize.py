@@ -95,3 +95,101 @@ def test_fullsize_zero_and_scaling_properties(layer):
     b = eng.forward(0, x, router_logits=lg)
     torch.cuda.synchronize()
     assert _close(b, a, ulps=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4 at its stated shapes: DeepSeek-V2-Lite (H=2048, moe I=1408 = 22 k-blocks, 64 routed experts top-6,
+# 2 shared experts = one I=2816 MLP), decode T=16 and a prefill-sized call (256-token tiles, MUFU/precise epilogues).
+# The oracle is evaluated on the CPU for a subset of the tokens: a token's output does not depend on the others.
+# ---------------------------------------------------------------------------------------------------------------------
+DS = dict(H=2048, I=1408, E=64, k=6, n_shared=2)
+
+
+@pytest.fixture(scope="module")
+def ds_layer(lib_built):
+    from moe_infinity_b200 import MoEEngine, _lib as L
+    H_, I_, E_, k_ = DS["H"], DS["I"], DS["E"], DS["k"]
+    eng = MoEEngine(num_layers=1, num_experts=E_, hidden=H_, inter=I_, top_k=k_, dtype=DT, expert_type=L.EXPERT_DEEPSEEK,
+                    router=L.ROUTER_DEEPSEEK_GREEDY, shared_inter=I_ * DS["n_shared"], max_tokens=4096, num_slots=E_,
+                    routed_scaling_factor=1.0)
+    g = torch.Generator().manual_seed(5)
+    experts = [[(torch.randn(I_, H_, generator=g) * 0.02).to(DT), (torch.randn(I_, H_, generator=g) * 0.02).to(DT),
+                (torch.randn(H_, I_, generator=g) * 0.02).to(DT)] for _ in range(E_)]          # gate, up, down
+    Is = I_ * DS["n_shared"]
+    shared = [(torch.randn(Is, H_, generator=g) * 0.02).to(DT), (torch.randn(Is, H_, generator=g) * 0.02).to(DT),
+              (torch.randn(H_, Is, generator=g) * 0.02).to(DT)]
+    gate = (torch.randn(E_, H_, generator=g) * 0.05)                                             # fp32 (MoEGate upcasts)
+    for e in range(E_):
+        eng.load_expert(0, e, experts[e])
+    eng.register_shared(0, shared)
+    eng.set_gate(0, gate)
+    return eng, experts, shared, gate
+
+
+def _ds_check(eng, experts, shared, gate, T, subset, what):
+    H_, E_, k_ = DS["H"], DS["E"], DS["k"]
+    g = torch.Generator().manual_seed(100 + T)
+    x = torch.randn(1, T, H_, generator=g).to(DT)
+    # scores from the oracle's fp32 gate (CPU) so that both sides route identically; ties -> excluded
+    scores = O.deepseek_gate_scores(x.view(-1, H_), gate.to(DT))
+    out = eng.forward(0, x.cuda(), scores=scores.cuda())
+    torch.cuda.synchronize()
+    sub = torch.tensor(subset)
+    ref, r = O.deepseek_block(x[:, sub].contiguous(), gate.to(DT), experts, k_, shared, scores=scores[sub])
+    tied = O.tied_tokens(r.scores, k_)
+    idx = eng.ws("topk_idx", T).cpu().long()[sub].sort(-1).values
+    assert torch.equal(idx[~tied], r.topk_idx.sort(-1).values[~tied]), f"{what}: expert index sets differ"
+    o, rf = out.float().cpu().reshape(T, H_)[sub][~tied], ref.float().reshape(len(subset), H_)[~tied]
+    eps = torch.finfo(DT).eps
+    rms = rf.pow(2).mean().sqrt()
+    # k=6 experts accumulated in bf16 in a fixed order on both sides; GEMM accumulation order differs -> 1-ulp flips of
+    # intermediates; bound 2 ulp of the value + 2 ulp of the rms (tests/test_gpu_parity.py:hidden_close)
+    bad = (o - rf).abs() > 2 * eps * rf.abs() + 2 * eps * rms
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())}/{bad.numel()} beyond 2 ulp, max {(o - rf).abs().max():.3e} rms {rms:.3e}"
+    return float((o == rf).float().mean())
+
+
+def test_deepseek_v2_lite_fullsize_decode_matches_oracle(ds_layer):
+    eng, experts, shared, gate = ds_layer
+    frac = _ds_check(eng, experts, shared, gate, 16, list(range(16)), "DeepSeek-V2-Lite decode T=16")
+    print(f"DeepSeek-V2-Lite T=16: {frac * 100:.1f}% bit-identical to the CPU oracle")
+
+
+def test_deepseek_v2_lite_fullsize_prefill_tiles_match_oracle(ds_layer):
+    """T=4096 -> ~384 tokens per expert: one full and one ragged 256-token tile per expert in the down GEMM, 128-token
+    double-buffered tiles in the gate/up GEMM (reference numerics)."""
+    eng, experts, shared, gate = ds_layer
+    subset = list(range(0, 4096, 97))[:40]
+    frac = _ds_check(eng, experts, shared, gate, 4096, subset, "DeepSeek-V2-Lite prefill T=4096")
+    print(f"DeepSeek-V2-Lite T=4096: {frac * 100:.1f}% bit-identical to the CPU oracle on {len(subset)} sampled tokens")
+
+
+def test_mixtral_fullsize_prefill_tiles_match_oracle(lib_built):
+    """One full-size Mixtral expert pair at a prefill-sized batch (T=2048 over 2 experts -> 2048 rows each = eight
+    256-token tiles), both numerics modes: reference (precise SiLU, 128-token gate/up tiles) and fp32 (MUFU SiLU in the
+    256-token instantiation, grouped_gemm.cu silu_mufu) against the CPU oracle on sampled tokens."""
+    from moe_infinity_b200 import MoEEngine, _lib as L
+    E2, T = 2, 2048
+    g = torch.Generator().manual_seed(9)
+    experts = [[(torch.randn(I, H, generator=g) * 0.02).to(DT), (torch.randn(H, I, generator=g) * 0.02).to(DT),
+                (torch.randn(I, H, generator=g) * 0.02).to(DT)] for _ in range(E2)]
+    x = torch.randn(1, T, H, generator=g).to(DT)
+    logits = torch.randn(T, E2, generator=g).to(DT)
+    sub = torch.tensor(list(range(0, T, 131))[:12])
+    ref, _, r = O.mixtral_block(x[:, sub].contiguous(), None, experts, 2, router_logits=logits[sub])
+    y32 = O.combine_fp32(x[:, sub].contiguous(), experts, r.topk_idx, r.topk_weight, O.MIXTRAL_MOE_DENSE_ACT_DENSE).reshape(len(sub), H)
+    rf = ref.float().reshape(len(sub), H)
+    for numerics, name in ((L.NUMERICS_REFERENCE, "reference"), (L.NUMERICS_FP32, "fp32")):
+        eng = MoEEngine(num_layers=1, num_experts=E2, hidden=H, inter=I, top_k=2, dtype=DT, max_tokens=T, num_slots=E2,
+                        numerics=numerics)
+        for e in range(E2):
+            eng.load_expert(0, e, experts[e])
+        out = eng.forward(0, x.cuda(), router_logits=logits.cuda())
+        torch.cuda.synchronize()
+        o = out.float().cpu().reshape(T, H)[sub]
+        if numerics == L.NUMERICS_REFERENCE:
+            assert _close(o, rf), f"prefill tiles, {name} numerics: max diff {(o - rf).abs().max():.3e}"
+        e_ours = (o - y32).pow(2).mean().sqrt()
+        e_ref = (rf - y32).pow(2).mean().sqrt()
+        assert e_ours <= 1.1 * e_ref, f"prefill tiles, {name} numerics: rms err vs fp32 {e_ours:.3e} > 1.1 x reference {e_ref:.3e}"
+        eng.close()

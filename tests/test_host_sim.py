@@ -323,7 +323,7 @@ def test_bias_experts_plan_whole_k_on_cpu(sim):
 def test_errors_are_reported_not_fatal_on_cpu(sim):
     bad = Ctx(sim, top_k=9)
     assert bad.rc == L.B2M_EINVAL
-    assert Ctx(sim, dtype=L.DTYPE_F32).rc == L.B2M_EUNSUPPORTED
+    assert Ctx(sim, dtype=L.DTYPE_FP8).rc == L.B2M_EUNSUPPORTED
     assert Ctx(sim, expert_type=6).rc != 0
     c = Ctx(sim, num_slots=4)
     assert c.rc == 0
@@ -337,6 +337,39 @@ def test_errors_are_reported_not_fatal_on_cpu(sim):
     assert sim.b2m_register_expert(c.h, 0, 0, c.blobs[(0, 0)].ctypes.data, 10) != 0
     c.close()
     assert sim.b2m_ctx_destroy(None) in (0, L.B2M_EINVAL)
+
+
+def test_fp32_experts_take_the_cuda_core_path_on_cpu(sim):
+    """dtype int 1 (expert_module.h:21): 4-byte blobs, CUDA-core fp32 GEMMs with whole-K tiles, fp32 combine; the fused
+    gate is refused (router logits come in), a mask row with more than top_k experts raises the sticky error."""
+    c = Ctx(sim, L_=1, E=4, H=128, I=256, k=2, num_slots=4, dtype=L.DTYPE_F32, expert_type=L.EXPERT_SWITCH_GATED)
+    assert c.rc == 0, c.err()
+    rng = np.random.default_rng(3)
+    nbytes = 3 * 128 * 256 * 4
+    for e in range(4):
+        blob = rng.integers(0, 255, nbytes, dtype=np.uint8)
+        c.blobs[(0, e)] = blob
+        assert sim.b2m_register_expert(c.h, 0, e, blob.ctypes.data, blob.nbytes) == 0, c.err()
+    assert sim.b2m_register_expert(c.h, 0, 0, c.blobs[(0, 0)].ctypes.data, nbytes // 2) != 0     # 2-byte-sized blob refused
+    take_log(sim)
+    T = 6
+    x = np.zeros((T, 128), dtype=np.float32)
+    out = np.zeros((T, 128), dtype=np.float32)
+    lg = rng.standard_normal((T, 4)).astype(np.float32)
+    assert sim.b2m_moe_forward(c.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, out.ctypes.data, None) == 0, c.err()
+    lines = take_log(sim)
+    up, dn = [_kv(ln) for ln in lines if ln.startswith("gemm")]
+    assert up["impl"] == "f32" and dn["impl"] == "f32" and up["dual"] == "1" and dn["ksplit"] == "1" and dn["stream_k"] == "0"
+    assert any(ln.startswith("combine") and "dtype=1" in ln for ln in lines)   # launch_combine routes dtype 1 to the fp32 kernel
+    assert sim.b2m_moe_forward(c.h, 0, x.ctypes.data, None, 0, 0, T, 0, out.ctypes.data, None) == L.B2M_EUNSUPPORTED
+    # a mask naming 3 experts for a token of a top-2 context is reported, not truncated silently
+    mask = np.zeros((T, 4), dtype=np.uint8)
+    mask[:, :2] = 1
+    mask[3, 2] = 1
+    assert sim.b2m_route_from_mask(c.h, 0, x.ctypes.data, mask.ctypes.data, T, None) == 0, c.err()
+    assert sim.b2m_check_errors(c.h, None) == L.B2M_EINVAL and "top_k" in c.err()
+    assert sim.b2m_check_errors(c.h, None) == 0          # sticky word cleared by the report
+    c.close()
 
 
 def test_context_releases_everything_on_cpu(sim):
@@ -431,7 +464,7 @@ def test_staged_calls_and_deepseek_shared_experts_on_cpu(sim):
     assert len(gemms) == 4
     shared_g = [g for g in gemms if g["single_n"] == str(T)]
     assert len(shared_g) == 2 and all(g["single_slot"] == "1" for g in shared_g) and shared_g[0]["M"] == str(2 * I)
-    assert [ln for ln in lines if ln.startswith("combine")] == [f"combine T={T} mode=1 shared=1 ep_collect=0"]
+    assert [ln for ln in lines if ln.startswith("combine")] == [f"combine T={T} mode=1 shared=1 ep_collect=0 dtype=0"]
     # bf16 scores are refused (modeling_deepseek.py:473 computes them in fp32)
     assert sim.b2m_moe_forward(c.h, 1, x.ctypes.data, scores.ctypes.data, 2, L.DTYPE_BF16, T, 0, out.ctypes.data, None) != 0
     assert "fp32" in c.err()

@@ -1,6 +1,7 @@
-"""CPU: the oracle against the committed golden vectors, and (dev container only) against the literal
-reference block files executed from /root/reference."""
+"""CPU: the oracle against the committed golden vectors, and against the literal reference block files executed from
+/root/reference (dev container) or from their byte-compiled staging oracle/_ref/pyref (anywhere the snapshot travels)."""
 import os
+import sys
 
 import pytest
 import torch
@@ -9,6 +10,10 @@ from oracle import moe_oracle as O
 import make_golden as G
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims"))
+import ref_loader  # noqa: E402
+
+needs_reference = pytest.mark.skipif(not ref_loader.available(), reason="neither /root/reference nor oracle/_ref/pyref present")
 
 
 def _load(name):
@@ -81,10 +86,9 @@ def test_empty_and_single_expert_edge_cases():
     assert r.topk_idx.tolist() == [[0, 1]] * 5 and O.tied_tokens(r.scores, 2).all()
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/moe_infinity"), reason="reference tree not present (GPU box)")
+@needs_reference
 @pytest.mark.parametrize("name", ["mixtral_mini_bf16", "mixtral_ragged_bf16"])
 def test_literal_reference_block_equals_oracle(name):
-    import ref_loader
     ns = ref_loader.load()
     c = G.build_mixtral(name)
     l_out, l_logits = G.run_literal_mixtral(ns, c["H"], c["I"], c["E"], c["k"], c["hidden"], c["gate"], c["experts"])
@@ -94,9 +98,8 @@ def test_literal_reference_block_equals_oracle(name):
     assert torch.equal(l_out.reshape(-1, c["H"])[ok], o_out.reshape(-1, c["H"])[ok])
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/moe_infinity"), reason="reference tree not present (GPU box)")
+@needs_reference
 def test_literal_deepseek_block_equals_oracle():
-    import ref_loader
     ns = ref_loader.load()
     name = "deepseek_group_bf16"
     c = G.build_deepseek(name)
@@ -107,3 +110,20 @@ def test_literal_deepseek_block_equals_oracle():
     o_out, r = O.deepseek_block(c["hidden"], c["gate"], c["experts"], c["k"], c["shared"], **kw)
     ok = ~O.tied_tokens(r.scores, c["k"])
     assert torch.equal(l_out.reshape(-1, c["H"])[ok], o_out.reshape(-1, c["H"])[ok])
+
+
+@needs_reference
+@pytest.mark.parametrize("name", list(G.SWITCH_CASES))
+def test_literal_switch_block_equals_oracle(name):
+    """A6 pin: the reference's own SyncSwitchTransformersSparseMLP (switch_transformers.py:41-113) on the 4.x-order router
+    shim, bit for bit against the oracle -- outputs, router logits, expert index, including capacity drops."""
+    ns = ref_loader.load()
+    c = G.build_switch(name)
+    l_out, l_logits, l_index = G.run_literal_switch(ns, c["H"], c["I"], c["E"], c["capacity"], c["hidden"], c["gate"],
+                                                    c["experts"])
+    o_out, (o_logits, o_index), mask = O.switch_block(c["hidden"], c["gate"], c["experts"], c["capacity"])
+    assert torch.equal(l_logits.float(), o_logits.float())
+    assert torch.equal(l_index, o_index)
+    assert torch.equal(l_out, o_out)
+    fx = _load(name)
+    assert fx["source"] == "literal" and torch.equal(fx["out"], l_out)
