@@ -164,3 +164,50 @@ def test_unregistered_expert_is_an_error(lib_built):
     eng.set_gate(0, torch.randn(E, H))
     with pytest.raises(B2MError):
         eng.forward(0, torch.randn(4, H).to(DT).cuda())
+
+
+def test_cache_policy_matches_reference_engine_trace(lib_built):
+    """The CUDA engine, driven through the reference-signature `expert_dispatcher` exactly like the reference engine was
+    when tests/golden/policy_ref_trace.json was recorded on a B200 (tools/ref_engine_harness.py --mode policy, protocol
+    "sequential"), reproduces the hit flags and resident sets of the reference's real GPUFetchFunc."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_ref_trace.json")
+    if not os.path.exists(path):
+        pytest.skip("golden trace of the reference engine not recorded yet")
+    from moe_infinity_b200 import compat
+    with open(path) as f:
+        g = json.load(f)
+    c = g["config"]
+    Ln, En, Hn, In, T = c["layers"], c["experts"], c["hidden"], c["inter"], c["tokens"]
+    h = compat.prefetch_handle("/tmp/b2m_policy_unused", 0.0)
+    d = compat.expert_dispatcher(En, Ln, 0, 4, 8, num_slots=c["slots"], max_tokens=16)
+    gen = torch.Generator().manual_seed(c["seed"])
+    tid, ids = 0, {}
+    for l in range(Ln):
+        for e in range(En):
+            ids[(l, e)] = list(range(tid, tid + 3))
+            for shape in ((In, Hn), (Hn, In), (In, Hn)):
+                h.offload((torch.randn(*shape, generator=gen) * 0.05).to(DT), tid)
+                tid += 1
+            d.register_expert(l, e, ids[(l, e)])
+    x = torch.randn(T, Hn, generator=gen).to(DT).cuda()
+    cleared = set(g["clear_counts_at"])
+    last_n = -1
+    for rec in g["sequential"]:
+        if rec["n"] != last_n and rec["n"] in cleared:
+            d.clear_expert_cache_counts()
+        last_n = rec["n"]
+        l, e = rec["layer"], rec["expert"]
+        act = g["trace"][rec["n"]]["experts"]
+        mask = torch.zeros(T, En, dtype=torch.bool)
+        for t in range(T):
+            mask[t, act[t % len(act)]] = True
+            mask[t, act[(t + 1) % len(act)]] = True
+        d.set_inputs(x, mask.cuda())
+        d.set_expected_queue(1)
+        d.enqueue_expert(l, e, 0, False)
+        (y, rl, re_, hit), = d.wait_expert()
+        assert (rl, re_, int(hit)) == (l, e, rec["hit"]), rec
+        res = sorted([ll, ee] for (ll, ee) in ids if d.engine.is_resident(ll, ee))
+        assert res == rec["resident_after"], (rec["n"], l, e)

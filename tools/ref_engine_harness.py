@@ -117,10 +117,16 @@ class RefStack:
             dense.append(next_id)
             next_id += 1
         self.experts = {}
-        for l in range(L_):
+        big = H * I > (1 << 22)          # full-size experts: one seeded draw per layer, experts are rescaled copies (CPU randn
+        for l in range(L_):              # of 5.6 G values would cost a minute of GPU-box time and changes nothing measured)
+            if big:
+                base = [torch.randn(I, H, generator=g) * std, torch.randn(H, I, generator=g) * std, torch.randn(I, H, generator=g) * std]
             for e in range(E):
-                ws = [(torch.randn(I, H, generator=g) * std).to(dt), (torch.randn(H, I, generator=g) * std).to(dt),
-                      (torch.randn(I, H, generator=g) * std).to(dt)]              # w1, w2, w3 (expert_module.cpp:139-145)
+                if big:
+                    ws = [(b * (1.0 + 0.03 * e)).to(dt) for b in base]
+                else:
+                    ws = [(torch.randn(I, H, generator=g) * std).to(dt), (torch.randn(H, I, generator=g) * std).to(dt),
+                          (torch.randn(I, H, generator=g) * std).to(dt)]          # w1, w2, w3 (expert_module.cpp:139-145)
                 if keep_host_copy:
                     self.experts[(l, e)] = ws
                 self.ids[(l, e)] = list(range(next_id, next_id + 3))
@@ -269,6 +275,8 @@ def mode_timing(args):
     expert_bytes = 3 * H * I * 2
     store = pick_store_dir(args.dir, L_ * E * expert_bytes)
     P = load_reference_engine()
+    if args.budget_experts > 0:                                   # forced offload: HBM budget of N experts
+        args.ratio = (args.budget_experts + 0.5) * expert_bytes / torch.cuda.mem_get_info(0)[1]
     t0 = time.perf_counter()
     ref = RefStack(P, store, args.ratio, L_, E, H, I, dt, args.threads, std=0.02, seed=0, keep_host_copy=bool(args.compare))
     setup_s = time.perf_counter() - t0
@@ -316,7 +324,7 @@ def mode_timing(args):
         per_step.append((time.perf_counter() - t0) * 1e3)
     ref_ms = sum(per_step) / len(per_step)
     res = {"mode": "timing", "impl": "reference native engine (prefetch_op.so)", "layers": L_, "tokens": T, "ratio": args.ratio,
-           "hidden": H, "inter": I, "experts": E, "setup_s": setup_s,
+           "hidden": H, "inter": I, "experts": E, "setup_s": setup_s, "budget_experts": args.budget_experts, "store_dir": store,
            "ms_per_step": ref_ms, "ms_per_step_median": sorted(per_step)[len(per_step) // 2], "ms_per_layer": ref_ms / L_,
            "tokens_per_s_32_layers": T / (ref_ms / L_ * 32 / 1e3), "hit_rate": hits[0] / max(hits[1], 1),
            "resident_experts": len(ref.resident()), "threads": args.threads}
@@ -375,6 +383,7 @@ def main():
     ap.add_argument("--dir", default="")
     ap.add_argument("--out", default="")
     ap.add_argument("--threads", type=int, default=8)
+    ap.add_argument("--budget-experts", type=int, default=0, help="timing mode: derive --ratio from an HBM budget of N experts")
     ap.add_argument("--compare", type=int, default=1, help="timing mode: also run this repo's engine and compare hidden states")
     args = ap.parse_args()
     if args.mode == "policy":
