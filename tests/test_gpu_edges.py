@@ -97,8 +97,12 @@ def test_unsupported_types_fail_loudly(lib_built):
     from moe_infinity_b200 import MoEEngine, B2MError, _lib as L
     with pytest.raises(B2MError):
         MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, expert_type=6)   # expert_module.h: 0..5
-    with pytest.raises(B2MError):
-        MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, dtype=torch.float32)
+    with pytest.raises(ValueError):
+        MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, dtype=torch.float8_e4m3fn)   # dtype int 3: no Float8 matmul in the reference either
+    eng = MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=2, dtype=torch.float32)       # dtype int 1: CUDA-core fp32 path
+    with pytest.raises(B2MError):       # ... which takes router logits / scores / masks, not the fused 16-bit gate kernel
+        eng.forward(0, torch.zeros(4, 128, device="cuda"))
+    eng.close()
     with pytest.raises(B2MError):
         MoEEngine(num_layers=1, num_experts=8, hidden=128, inter=256, top_k=9)
 

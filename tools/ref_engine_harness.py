@@ -76,8 +76,8 @@ def _accepts_o_direct(d: str) -> bool:
 def pick_store_dir(want: str, need_bytes: int) -> str:
     """First candidate directory that accepts O_DIRECT and has room; else re-exec under the no-O_DIRECT preload shim."""
     import shutil
-    cands = [want, os.path.join(ROOT, "gpurun_out", "ref_store"), "/var/tmp/b2m_ref_store", "/root/b2m_ref_store",
-             "/tmp/b2m_ref_store", "/dev/shm/b2m_ref_store"]
+    cands = [want, "/var/tmp/b2m_ref_store", "/root/b2m_ref_store", "/tmp/b2m_ref_store",
+             os.path.join(ROOT, "gpurun_out", "ref_store"), "/dev/shm/b2m_ref_store"]
     preload = "libnodirect.so" in os.environ.get("LD_PRELOAD", "")
     for d in cands:
         if not d:
@@ -90,7 +90,9 @@ def pick_store_dir(want: str, need_bytes: int) -> str:
         if free < need_bytes * 1.1 + (1 << 30):
             continue
         if preload or _accepts_o_direct(d):
-            return d
+            # a fresh store per run: the reference reuses an existing archer_index and aborts on a size mismatch
+            # (archer_tensor_handle.cpp:40-50,69-72)
+            return tempfile.mkdtemp(prefix="run_", dir=d)
     if not preload:
         shim = os.path.join(ROOT, "oracle", "_ref", "libnodirect.so")
         if os.path.exists(shim):
@@ -264,6 +266,8 @@ def mode_policy(args):
         json.dump(out, f)
     print(json.dumps({"mode": "policy", "out": path, "dispatches": len(out["sequential"]),
                       "hits": sum(r["hit"] for r in out["sequential"]), **out["outputs_vs_ours"]}), flush=True)
+    import shutil
+    shutil.rmtree(store, ignore_errors=True)
     os._exit(0)
 
 
@@ -363,6 +367,8 @@ def mode_timing(args):
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         with open(args.out, "w") as f:
             json.dump(res, f)
+    import shutil
+    shutil.rmtree(store, ignore_errors=True)
     os._exit(0)            # never run the reference's destructors (see gotchas)
 
 
