@@ -462,8 +462,178 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def run_offload(args):
+    """--config offload = BASELINE configs[2]: Mixtral-8x7B bf16, device_memory_ratio 0.25 (forced offload), 32 layers, decode
+    batch 8 on the SURVEY 8(d) trace: per-layer Zipf-1 popular experts (router bias folded into the gate weight through a
+    constant hidden coordinate), hidden states AR(1) over decode steps (0.9) and over layers (0.9, the residual stream);
+    one T=16384 prefill first.  All 256 experts live in pinned host DRAM (90 GB); HBM holds ratio x total / 352 MB of them.
+    Two runs on the same trace: the reference's policy (on-demand fetch, evict min incache_visit_count,
+    expert_dispatcher.cpp:227-266; prefetch off as on the reference's Mixtral block) and ours (activation-aware cache +
+    router-logit look-ahead prefetch).  The step is bound by the host->device link: roofline = H2D bytes / time vs the
+    pinned-copy bandwidth measured in the same process."""
+    import ctypes as C
+    from moe_infinity_b200 import MoEEngine, _lib as L_
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cfg = dict(MIXTRAL)
+    if args.layers:
+        cfg["L"] = args.layers
+    L, E, H, I, k = cfg["L"], cfg["E"], cfg["H"], cfg["I"], cfg["k"]
+    T, dtype = BATCH, torch.bfloat16
+    steps, warm = args.steps, max(2, args.warmup)
+    ratio = args.ratio
+    # ---- measured link peak
+    nb = 1 << 30
+    hb = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    db = torch.empty(nb, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        db.copy_(hb, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        db.copy_(hb, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_peak = 4 * nb / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del hb, db
+    # ---- host weights: 256 pinned blobs (values from one seeded draw, per-expert offset so experts differ)
+    t0 = time.perf_counter()
+    nel = 3 * H * I
+    proto = (torch.randn(nel, generator=torch.Generator().manual_seed(3)) * 0.02).to(dtype)
+    blobs = {}
+    for l in range(L):
+        for e in range(E):
+            b = torch.empty(nel, dtype=dtype, pin_memory=True)
+            b.copy_(proto)
+            b[:4096] += 0.001 * (l * E + e)
+            blobs[(l, e)] = b
+    pin_s = time.perf_counter() - t0
+    # ---- trace: gates with a bias column, hidden states correlated over steps and layers
+    g = torch.Generator(device="cpu").manual_seed(11)
+    cconst = 4.0
+    gates = []
+    for l in range(L):
+        w = torch.randn(E, H, generator=g) * 0.02
+        perm = torch.randperm(E, generator=g)
+        bias = (-args.skew * torch.log(torch.arange(1, E + 1).float()))[perm]
+        w[:, H - 1] = bias / cconst
+        gates.append(w)
+    rho_s, rho_l = 0.9, 0.9
+    xs = torch.empty(steps + warm, L, T, H, dtype=dtype).pin_memory()
+    h = torch.randn(L, T, H, generator=g)
+    for s_ in range(steps + warm):
+        n = torch.randn(L, T, H, generator=g)
+        for l in range(1, L):
+            n[l] = rho_l * n[l - 1] + (1 - rho_l ** 2) ** 0.5 * n[l]
+        h = rho_s * h + (1 - rho_s ** 2) ** 0.5 * n
+        hs = h.clone()
+        hs[..., H - 1] = cconst
+        xs[s_] = hs.to(dtype)
+    xp = (torch.randn(args.prefill, H, generator=g)).to(dtype) if args.prefill else None
+    if xp is not None:
+        xp[:, H - 1] = cconst
+
+    def run(policy, lookahead, tag):
+        eng = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype,
+                        max_tokens=max(16, args.prefill), device_memory_ratio=ratio, cache_policy=policy,
+                        lookahead_prefetch=lookahead, max_inflight_prefetch=args.inflight,
+                        h2d_chunk_bytes=args.chunk_mb << 20)
+        for (l, e), b in blobs.items():
+            eng._blobs[(l, e)] = b
+            eng._ck(eng.lib.b2m_register_expert(eng._h, l, e, C.c_void_p(b.data_ptr()), b.numel() * 2))
+        for l in range(L):
+            eng.set_gate(l, gates[l].to(dtype))
+        x_dev = torch.empty(L, T, H, dtype=dtype, device=dev)
+        out_dev = torch.empty_like(x_dev)
+        out_host = torch.empty(L, T, H, dtype=dtype).pin_memory()
+        prefill_ms = None
+        if xp is not None:
+            xpd = xp.to(dev)
+            op = torch.empty_like(xpd)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for l in range(L):
+                eng.forward(l, xpd, out=op)
+            torch.cuda.synchronize()
+            prefill_ms = (time.perf_counter() - t0) * 1e3
+            del xpd, op
+            eng.clear_expert_cache_counts()          # what the reference's example does after prefill (interface_example.py:39)
+
+        def step(i):
+            x_dev.copy_(xs[i], non_blocking=True)
+            for l in range(L):
+                eng.forward(l, x_dev[l], out=out_dev[l])
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for i in range(warm):
+            step(i)
+        s0 = eng.stats()
+        times = []
+        for i in range(steps):
+            t0 = time.perf_counter()
+            step(warm + i)
+            times.append(time.perf_counter() - t0)
+        s1 = eng.stats()
+        d = {kk: s1[kk] - s0[kk] for kk in s1 if kk not in ("slots", "slot_bytes", "resident")}
+        tot = sum(times)
+        res = {"policy": tag, "slots": s1["slots"], "experts": L * E, "ms_per_step": tot / steps * 1e3,
+               "p50_ms": sorted(times)[len(times) // 2] * 1e3, "tokens_per_s": T * steps / tot,
+               "hit_rate": d["hits"] / max(1, d["dispatches"]), "dispatches_per_step": d["dispatches"] / steps,
+               "misses_per_step": d["misses"] / steps, "h2d_gb_per_step": d["h2d_bytes"] / steps / 1e9,
+               "h2d_gbs": d["h2d_bytes"] / tot / 1e9, "link_frac": d["h2d_bytes"] / tot / 1e9 / h2d_peak,
+               "prefetch_issued_per_step": d["prefetch_issued"] / steps, "prefetch_useful_per_step": d["prefetch_useful"] / steps,
+               "evictions_per_step": d["evictions"] / steps, "host_syncs_per_step": d["host_syncs"] / steps,
+               "kernel_launches_per_step": d["kernel_launches"] / steps, "prefill_ms": prefill_ms,
+               "out_checksum": float(out_host.float().abs().sum())}
+        eng.prefetch_drain()
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        return res
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ref = run(L_.CACHE_REFERENCE, False, "reference (on-demand, evict min incache_visit_count; prefetch off)")
+    ours = run(L_.CACHE_ACTIVATION_AWARE, True, "activation-aware cache + router-logit look-ahead prefetch")
+    extra = {}
+    if args.ablate:
+        extra["activation_aware_no_prefetch"] = run(L_.CACHE_ACTIVATION_AWARE, False, "activation-aware cache, prefetch off")
+        extra["reference_policy_with_lookahead"] = run(L_.CACHE_REFERENCE, True, "reference eviction + look-ahead prefetch")
+    clocks = sampler.stop()
+    line = {
+        "metric": METRIC, "value": ours["tokens_per_s"], "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": ours["ms_per_step"], "p50_token_latency_ms": ours["p50_ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Mixtral-8x7B MoE dispatch path, forced offload: device_memory_ratio={ratio} -> {ours['slots']} of "
+                               f"{L * E} experts HBM resident, the rest staged from pinned host DRAM on demand / ahead; decode "
+                               f"batch {BATCH}, {L} layers, Zipf-{args.skew} routing, hidden states AR(1) 0.9 over steps and layers, "
+                               f"after a T={args.prefill} prefill", "global_batch": BATCH, "layers": L, "parallelism": "single GPU",
+                   "l2": "inputs larger than L2 (every miss streams a 352 MB expert)", "numerics": "reference rounding chain",
+                   "timed_region": "host API per layer (MoEEngine.forward), inputs from pinned host memory, outputs back, host synchronised"},
+        "roofline": {"bound": "h2d link", "kernel": "cudaMemcpyAsync H2D (expert staging)", "achieved": ours["h2d_gbs"],
+                     "peak": h2d_peak, "unit": "GB/s", "frac": ours["link_frac"], "peak_source": "measured in this run (pinned 1 GiB copies)",
+                     "algorithmic_bytes_per_step": ours["misses_per_step"] * 3 * H * I * 2, "traffic": None},
+        "e2e": {"value": ours["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": L * T * H * 2 + int(ours["h2d_gb_per_step"] * 1e9),
+                "d2h_bytes_per_step": L * T * H * 2},
+        "gpu_launches": int(ours["kernel_launches_per_step"] * steps), "clocks": clocks,
+        "ours": ours, "reference_policy": ref, "speedup_vs_reference_policy": ours["tokens_per_s"] / ref["tokens_per_s"],
+        "same_outputs": abs(ours["out_checksum"] - ref["out_checksum"]) <= 1e-6 * abs(ref["out_checksum"]),
+        "pin_seconds": pin_s, **extra,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="mixtral", choices=["mixtral", "offload"],
+                    help="mixtral = BASELINE configs[1] (headline, default); offload = configs[2] (device_memory_ratio 0.25)")
+    ap.add_argument("--ratio", type=float, default=0.25, help="offload: device_memory_ratio")
+    ap.add_argument("--skew", type=float, default=1.0, help="offload: Zipf exponent of the per-layer expert popularity")
+    ap.add_argument("--prefill", type=int, default=16384, help="offload: tokens of the prefill that precedes the decode steps (0 = none)")
+    ap.add_argument("--inflight", type=int, default=2, help="offload: concurrent prefetch copies")
+    ap.add_argument("--chunk-mb", type=int, default=0, help="offload: H2D copy granularity (0 = whole expert)")
+    ap.add_argument("--ablate", action="store_true", help="offload: also run the two half-way configurations")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
@@ -477,6 +647,8 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path only"}))
         sys.exit(2)
+    if args.config == "offload":
+        return run_offload(args)
     run_ours(args)
 
 

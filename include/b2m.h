@@ -64,6 +64,12 @@ extern "C" {
                                  every dispatched expert (hit or miss) costs one expert, an eviction refunds one, a miss evicts
                                  exactly one victim iff the budget is used up */
 #define B2M_CACHE_SLOTS 1     /* evict only when no physical HBM slot is free (hits are not charged) */
+#define B2M_CACHE_ACTIVATION_AWARE 2 /* the "activation-aware expert cache" the reference specifies but never wires in
+                                 (moe_infinity/memory/expert_priority_score.py:84-172: layer-distance decay x activation
+                                 frequency; expert_cache.py:95-167): the victim is the resident expert with the largest
+                                 EXPECTED time to its next use = layers until its layer runs again (decode visits layers in
+                                 order) + L * (1/f - 1), f = moving average of "activated in a step" (cfg.freq_alpha).
+                                 Physical slots are the budget.  Measured against B2M_CACHE_REFERENCE by tools/policy_sim.py */
 
 typedef struct b2m_ctx b2m_ctx;
 
@@ -95,6 +101,13 @@ typedef struct b2m_config {
   int32_t h2d_chunk_bytes;  /* H2D copy granularity in bytes (0 = whole expert in one cudaMemcpyAsync) */
   int32_t gemm_impl;        /* 0 = tcgen05 (product); 1 = CUDA-core cross-check kernel (bring-up only) */
   int32_t cache_policy;     /* B2M_CACHE_* : on-demand budget accounting */
+  int32_t lookahead_prefetch; /* 1 (offload mode, T <= 256): every routing call also applies the NEXT layer's router weight
+                               (b2m_set_gate) to this layer's input and reads the predicted expert counts back with this
+                               layer's own counts (same synchronisation); predicted experts that are not resident are staged
+                               on the prefetch stream while this layer computes -- the router-logit driven prefetch of the
+                               north star; replaces expert_predictor.predict + prefetch_experts (expert_prefetcher.py:42-59)
+                               for callers that do not supply their own hints */
+  float freq_alpha;         /* B2M_CACHE_ACTIVATION_AWARE: weight of the newest step in the activation average (0 = 0.25) */
 } b2m_config;
 
 /* cache / traffic counters; columns mirror the reference's per-node counters exported by get_hit_rate
@@ -208,6 +221,9 @@ int b2m_stats_get(b2m_ctx* ctx, b2m_stats* out);
 /* activated experts of the last b2m_run_experts/b2m_moe_forward that had to read counts back (offload mode):
  * counts_host[E]; returns B2M_ESTATE if the last call ran sync-free */
 int b2m_last_counts(b2m_ctx* ctx, int32_t* counts_host);
+/* with cfg.lookahead_prefetch: per-expert token counts the NEXT layer's router predicted from the last call's input
+ * (look_host[E]); B2M_ESTATE if the last call made no prediction */
+int b2m_last_lookahead(b2m_ctx* ctx, int32_t* look_host);
 
 /* ---- expert parallel (BASELINE config 5): one process per GPU, rank r owns experts [r*E/N, (r+1)*E/N).
  * The reference has no live collective (README.md:18; dead code modeling_deepseek.py:657-721); these helpers

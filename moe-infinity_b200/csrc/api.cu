@@ -67,6 +67,7 @@ struct Expert {
   bool pinned = false;
   bool prefetched_unused = false;
   int visits = 0;               // incache_visit_count (model_topology.h:75-91)
+  float freq = 0.5f;            // B2M_CACHE_ACTIVATION_AWARE: moving average of "activated in a step"
   uint64_t total_visits = 0;
   cudaEvent_t ready = nullptr;  // H2D complete
   bool ready_pending = false;   // compute stream has not yet been ordered after `ready`
@@ -157,6 +158,11 @@ struct b2m_ctx {
   // 257,266): -1 for EVERY dispatched expert (hit or miss -- the reference subtracts byte_size unconditionally), +1 per
   // on-demand eviction; a miss evicts exactly one victim iff budget < 1.  Physical slots remain the hard limit.
   long long budget_units = 0;
+  int cur_layer = 0;             // layer of the dispatch in progress / last dispatched (next-use distance of the activation-aware policy)
+  int* d_look = nullptr;         // [E] look-ahead counts: next layer's router applied to this layer's input
+  int* h_look = nullptr;         // pinned [E]
+  bool look_pending = false;     // the last routing call launched the look-ahead kernel
+  bool last_look_valid = false;
   b2m_stats stats;
 };
 
@@ -316,6 +322,38 @@ int pick_victim(b2m_ctx* c, const std::vector<int>& in_use, bool allow_protected
   return best;
 }
 
+// B2M_CACHE_ACTIVATION_AWARE: expected time (in layer visits) to the next use of expert (l, e) seen from layer `cur`:
+// layers until l runs again (decode visits layers in order; the layer in progress comes back after a full cycle) plus
+// L * (1/f - 1) for the steps it is expected to sit out.  float32 throughout (oracle/policy_oracle.py mirrors it).
+inline float next_use_score(int l, int cur, int L, float freq) {
+  int d = (l - cur) % L;
+  if (d <= 0) d += L;
+  const float f = freq < 0.02f ? 0.02f : freq;
+  return (float)d + (float)L * (1.0f / f - 1.0f);
+}
+int pick_victim_next_use(b2m_ctx* c, const std::vector<int>& in_use, bool allow_protected, float* score_out = nullptr) {
+  const int L = c->cfg.num_layers, E = c->cfg.num_experts;
+  int best = -1;
+  float best_s = -1.0f;
+  for (int l = 0; l < L; ++l) {            // layer-major scan, strict '>' : first maximum wins
+    for (int e = 0; e < E; ++e) {
+      const int id = l * E + e;
+      const Expert& x = c->experts[id];
+      if (x.state != ST_RESIDENT || x.pinned || x.host == nullptr) continue;
+      if (!allow_protected && c->protected_set.count(id)) continue;
+      if (std::find(in_use.begin(), in_use.end(), id) != in_use.end()) continue;
+      const float s = next_use_score(l, c->cur_layer, L, x.freq);
+      if (s > best_s) { best = id; best_s = s; }
+    }
+  }
+  if (score_out) *score_out = best_s;
+  return best;
+}
+int pick_victim_policy(b2m_ctx* c, const std::vector<int>& in_use, bool allow_protected) {
+  return c->cfg.cache_policy == B2M_CACHE_ACTIVATION_AWARE ? pick_victim_next_use(c, in_use, allow_protected)
+                                                            : pick_victim(c, in_use, allow_protected);
+}
+
 void evict(b2m_ctx* c, int id) {
   Expert& x = c->experts[id];
   const int slot = x.slot;
@@ -331,8 +369,8 @@ void evict(b2m_ctx* c, int id) {
 
 int acquire_slot(b2m_ctx* c, const std::vector<int>& in_use, bool prefetch) {
   if (c->free_slots.empty()) {
-    int v = pick_victim(c, in_use, false);
-    if (v < 0 && !prefetch) v = pick_victim(c, in_use, true);   // overflow: on-demand beats protection
+    int v = pick_victim_policy(c, in_use, false);
+    if (v < 0 && !prefetch) v = pick_victim_policy(c, in_use, true);   // overflow: on-demand beats protection
     if (v < 0) return -1;
     evict(c, v);
   }
@@ -348,8 +386,8 @@ int acquire_slot(b2m_ctx* c, const std::vector<int>& in_use, bool prefetch) {
 int acquire_slot_on_demand(b2m_ctx* c, const std::vector<int>& in_use) {
   const bool ref_acct = c->cfg.cache_policy == B2M_CACHE_REFERENCE;
   if (c->free_slots.empty() || (ref_acct && c->budget_units < 1)) {
-    int v = pick_victim(c, in_use, false);
-    if (v < 0) v = pick_victim(c, in_use, true);   // overflow: on-demand beats protection
+    int v = pick_victim_policy(c, in_use, false);
+    if (v < 0) v = pick_victim_policy(c, in_use, true);   // overflow: on-demand beats protection
     if (v >= 0) {
       evict(c, v);
       c->budget_units += 1;                        // cache_sizes_ += evict_node->byte_size (:257)
@@ -505,7 +543,8 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   if (!make_shape(cfg->expert_type, cfg->hidden, cfg->inter, &shape, esize))
     return fail(nullptr, B2M_EUNSUPPORTED, "expert_type %d is unknown (expert_module.h:13-18 defines 0..5)", cfg->expert_type);
   if (cfg->router < 0 || cfg->router > 3) return fail(nullptr, B2M_EINVAL, "bad router kind");
-  if (cfg->cache_policy != B2M_CACHE_REFERENCE && cfg->cache_policy != B2M_CACHE_SLOTS) return fail(nullptr, B2M_EINVAL, "bad cache_policy");
+  if (cfg->cache_policy < B2M_CACHE_REFERENCE || cfg->cache_policy > B2M_CACHE_ACTIVATION_AWARE) return fail(nullptr, B2M_EINVAL, "bad cache_policy");
+  if (cfg->freq_alpha < 0.f || cfg->freq_alpha > 1.f) return fail(nullptr, B2M_EINVAL, "freq_alpha must be in [0,1]");
   if (cfg->router == B2M_ROUTER_SWITCH_TOP1 && cfg->top_k != 1) return fail(nullptr, B2M_EINVAL, "switch router needs top_k=1");
 
   int ndev = 0;
@@ -605,6 +644,9 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_err, sizeof(int)));
   CKC(cudaMemset(c->d_err, 0, sizeof(int)));
   CKC(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
+  CKC(cudaMalloc((void**)&c->d_look, sizeof(int) * E));
+  CKC(cudaMemset(c->d_look, 0, sizeof(int) * E));
+  CKC(cudaHostAlloc((void**)&c->h_look, sizeof(int) * E, cudaHostAllocDefault));
   CKC(cudaMalloc((void**)&c->d_dest_of, sizeof(int) * R));
   CKC(cudaMalloc((void**)&c->d_chunk_counts, sizeof(int) * ((size_t)(T + 31) / 32) * E));
   CKC(cudaMalloc((void**)&c->d_scores, sizeof(float) * (size_t)T * E));
@@ -647,7 +689,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_look, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
@@ -656,6 +698,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->h_look) cudaFreeHost(c->h_look);
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
   if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
   if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
@@ -830,6 +873,20 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   CK(c, launch_route(p, st));
   c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0);
   c->last_counts_valid = false;
+  // router-logit driven prefetch: the next layer's router applied to THIS layer's input predicts which experts the next
+  // layer will want; the counts ride back with this layer's own counts (b2m_run_experts reads both in one synchronisation)
+  c->look_pending = false;
+  const int nxt = (layer + 1) % c->cfg.num_layers;
+  if (c->cfg.lookahead_prefetch && c->offload && !c->ep_mode && T >= 1 && T <= 256 && c->cfg.dtype != B2M_DTYPE_F32 &&
+      c->cfg.num_layers > 1 && c->gate_w[nxt]) {
+    RouteParams q = p;
+    q.gate_w = c->gate_w[nxt];
+    q.logits = nullptr;
+    CK(c, cudaMemsetAsync(c->d_look, 0, sizeof(int) * c->cfg.num_experts, st));
+    CK(c, launch_lookahead_counts(q, c->d_look, st));
+    c->stats.kernel_launches += 1;
+    c->look_pending = true;
+  }
   return B2M_OK;
 }
 
@@ -945,11 +1002,27 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   } else if (on_demand) {
     // on-demand path: read the per-expert counts back (the reference's .cpu() in dispatch_local)
     CK(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
+    c->last_look_valid = false;
+    if (c->look_pending) CK(c, cudaMemcpyAsync(c->h_look, c->d_look, sizeof(int) * E, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     c->stats.host_syncs++;
     c->last_counts_valid = true;
-    for (int e = 0; e < E; ++e)
+    c->last_look_valid = c->look_pending;
+    c->look_pending = false;
+    c->cur_layer = layer;
+    const float alpha = c->cfg.freq_alpha > 0.f ? c->cfg.freq_alpha : 0.25f;
+    for (int e = 0; e < E; ++e) {
+      Expert& x = c->experts[(size_t)layer * E + e];
       if (c->h_counts[e] > 0) active.push_back(layer * E + e);
+      x.freq = (1.0f - alpha) * x.freq + (c->h_counts[e] > 0 ? alpha : 0.0f);
+    }
+    if (c->last_look_valid) {
+      // the predicted experts of the next layer must not be evicted to make room for this layer's misses
+      const int nxt = (layer + 1) % c->cfg.num_layers;
+      c->protected_set.clear();
+      for (int e = 0; e < E; ++e)
+        if (c->h_look[e] > 0) c->protected_set.insert(nxt * E + e);
+    }
   } else {
     for (int e = 0; e < E; ++e)
       if (!c->ep_mode || c->experts[(size_t)layer * E + e].state != ST_UNREGISTERED) active.push_back(layer * E + e);
@@ -1041,6 +1114,40 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
                     remaining.end());
   }
   c->last_active = wave;   // experts of the last wave are still being read by kernels in flight
+  if (on_demand && c->last_look_valid) {
+    // stage the next layer's predicted experts while this layer computes: most-wanted first; a prediction only displaces
+    // an expert whose own next use is expected at least a few layer visits later than the next layer
+    const int nxt = (layer + 1) % c->cfg.num_layers;
+    std::vector<int> order;
+    for (int e = 0; e < E; ++e)
+      if (c->h_look[e] > 0 && c->experts[(size_t)nxt * E + e].state == ST_HOST && c->experts[(size_t)nxt * E + e].host) order.push_back(e);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->h_look[a] > c->h_look[b]; });
+    r = pump(c);   // retire finished copies first
+    if (r) return r;
+    const int max_if = c->cfg.max_inflight_prefetch > 0 ? c->cfg.max_inflight_prefetch : 2;
+    for (int e : order) {
+      if ((int)c->inflight.size() >= max_if) break;
+      const int id = nxt * E + e;
+      int slot = -1;
+      if (!c->free_slots.empty()) {
+        slot = c->free_slots.back();
+        c->free_slots.pop_back();
+      } else {
+        float vs = 0.f;
+        const int v = c->cfg.cache_policy == B2M_CACHE_ACTIVATION_AWARE ? pick_victim_next_use(c, c->last_active, false, &vs)
+                                                                         : pick_victim(c, c->last_active, false);
+        if (v < 0 || (c->cfg.cache_policy == B2M_CACHE_ACTIVATION_AWARE && vs < 2.5f)) break;   // never trade away an expert that is itself expected within the next two layer visits
+        evict(c, v);
+        slot = c->free_slots.back();
+        c->free_slots.pop_back();
+      }
+      r = issue_copy(c, id, slot, c->prefetch_stream, true);
+      if (r) return r;
+      c->experts[id].prefetched_unused = true;
+      c->inflight.push_back(id);
+      c->stats.prefetch_issued++;
+    }
+  }
   return B2M_OK;
 }
 
@@ -1243,6 +1350,13 @@ int b2m_stats_get(b2m_ctx* c, b2m_stats* out) {
   for (auto& x : c->experts) res += (x.state == ST_RESIDENT || x.state == ST_LOADING) ? 1 : 0;
   c->stats.resident = res;
   *out = c->stats;
+  return B2M_OK;
+}
+
+int b2m_last_lookahead(b2m_ctx* c, int32_t* look_host) {
+  if (!c || !look_host) return B2M_EINVAL;
+  if (!c->last_look_valid) return fail(c, B2M_ESTATE, "the last call made no look-ahead prediction (cfg.lookahead_prefetch, offload mode, T <= 256, next layer's gate set)");
+  memcpy(look_host, c->h_look, sizeof(int) * c->cfg.num_experts);
   return B2M_OK;
 }
 

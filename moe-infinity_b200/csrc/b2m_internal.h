@@ -137,6 +137,9 @@ struct RouteParams {
   EpParams ep;
 };
 cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
+// look-ahead: top-k of the NEXT layer's router (p.gate_w = its weight) on this layer's input p.x -> counts_out[E] += 1 per
+// selected (token, expert); counts_out must be zero.  T <= 256.
+cudaError_t launch_lookahead_counts(const RouteParams& p, int* counts_out, cudaStream_t st);
 // routing from a caller-supplied dense mask (reference compat: ExpertDispatcher::SetInputs + per-expert gather,
 // core/parallel/expert_dispatcher.h:66-70, expert_dispatcher.cpp:274-285)
 cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask /*[T,E]*/, cudaStream_t st);

@@ -914,6 +914,43 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   }
 }
 
+static bool route_args_ok(const RouteParams& p);
+
+// Look-ahead routing (cfg.lookahead_prefetch): one CTA per token applies the NEXT layer's router weight (p.gate_w) to this
+// layer's input row and counts its top-k choice per expert.  softmax is monotonic, so top-k of the logits is the top-k of
+// the scores (ties -> lowest index, like every routing kernel here); weights are not needed for a prefetch hint.
+__global__ void __launch_bounds__(RT_THREADS) lookahead_counts_kernel(const RouteParams p, int* __restrict__ counts_out) {
+  __shared__ float s_logits[MAX_PL * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  for (int e = warp; e < p.E; e += RT_WARPS) {
+    const float v = gate_dot_warp(p, t, e);
+    if (lane == 0) s_logits[e] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int j = 0; j < p.k; ++j) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int e = lane; e < p.E; e += 32) {
+        const float v = s_logits[e];
+        if (v > best) { best = v; bi = e; }       // ascending e within a lane: first maximum kept
+      }
+      warp_argmax(best, bi);
+      if (bi >= p.E) break;
+      if (lane == 0) { atomicAdd(counts_out + bi, 1); s_logits[bi] = -INFINITY; }
+      __syncwarp();
+    }
+  }
+}
+
+cudaError_t launch_lookahead_counts(const RouteParams& p, int* counts_out, cudaStream_t st) {
+  if (!route_args_ok(p) || !p.gate_w || !p.x || !counts_out || p.T < 1 || p.T > FUSED_MAX_T || p.dtype == DT_F32)
+    return cudaErrorInvalidValue;
+  lookahead_counts_kernel<<<p.T, RT_THREADS, 0, st>>>(p, counts_out);
+  return cudaGetLastError();
+}
+
 static int small_permute_grid(const RouteParams& p) {
   const int pairs = p.T * p.k;
   return pairs < 1 ? 1 : (pairs > 128 ? 128 : pairs);

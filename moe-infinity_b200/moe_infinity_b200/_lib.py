@@ -15,7 +15,7 @@ DTYPE_BF16, DTYPE_F32, DTYPE_F16, DTYPE_FP8 = 0, 1, 2, 3
 EXPERT_SWITCH, EXPERT_SWITCH_GATED, EXPERT_NLLB, EXPERT_FSGPT, EXPERT_MIXTRAL, EXPERT_DEEPSEEK = 0, 1, 2, 3, 4, 5
 ROUTER_MIXTRAL, ROUTER_DEEPSEEK_GREEDY, ROUTER_DEEPSEEK_GROUP, ROUTER_SWITCH_TOP1 = 0, 1, 2, 3
 NUMERICS_REFERENCE, NUMERICS_FP32 = 0, 1
-CACHE_REFERENCE, CACHE_SLOTS = 0, 1
+CACHE_REFERENCE, CACHE_SLOTS, CACHE_ACTIVATION_AWARE = 0, 1, 2
 WS = dict(topk_idx=0, topk_w=1, row_of=2, perm_token=3, counts=4, offsets=5, xp=6, hmid=7, y=8, scores=9, logits=10)
 
 
@@ -28,6 +28,7 @@ class Config(C.Structure):
         ("norm_topk_prob", C.c_int32), ("expert_capacity", C.c_int32), ("routed_scaling_factor", C.c_float),
         ("gate_dtype", C.c_int32), ("device_memory_ratio", C.c_double), ("max_inflight_prefetch", C.c_int32),
         ("h2d_chunk_bytes", C.c_int32), ("gemm_impl", C.c_int32), ("cache_policy", C.c_int32),
+        ("lookahead_prefetch", C.c_int32), ("freq_alpha", C.c_float),
     ]
 
 
@@ -73,6 +74,7 @@ SYMBOLS = [
     ("b2m_is_resident", _I, [_VP, _I, _I]),
     ("b2m_stats_get", _I, [_VP, C.POINTER(Stats)]),
     ("b2m_last_counts", _I, [_VP, C.POINTER(C.c_int32)]),
+    ("b2m_last_lookahead", _I, [_VP, C.POINTER(C.c_int32)]),
     ("b2m_ep_pack", _I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     ("b2m_ep_regroup", _I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     ("b2m_ep_ungroup", _I, [_VP, _I, _I, _I, _VP, _VP]),

@@ -45,7 +45,8 @@ class MoEEngine:
                  num_slots: int = 0, device_memory_ratio: float = 0.0, shared_inter: int = 0, n_group: int = 1,
                  topk_group: int = 1, norm_topk_prob: bool = False, routed_scaling_factor: float = 1.0,
                  expert_capacity: int = 0, gate_dtype: Optional[torch.dtype] = None, device: int = 0,
-                 max_inflight_prefetch: int = 2, h2d_chunk_bytes: int = 0, gemm_impl: int = 0):
+                 max_inflight_prefetch: int = 2, h2d_chunk_bytes: int = 0, gemm_impl: int = 0,
+                 cache_policy: int = L.CACHE_REFERENCE, lookahead_prefetch: bool = False, freq_alpha: float = 0.0):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise RuntimeError("moe_infinity_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -74,6 +75,9 @@ class MoEEngine:
         cfg.max_inflight_prefetch = max_inflight_prefetch
         cfg.h2d_chunk_bytes = h2d_chunk_bytes
         cfg.gemm_impl = gemm_impl
+        cfg.cache_policy = cache_policy
+        cfg.lookahead_prefetch = int(bool(lookahead_prefetch))
+        cfg.freq_alpha = freq_alpha
         self.cfg = cfg
         self.max_tokens = max_tokens
         h = C.c_void_p()
@@ -274,6 +278,11 @@ class MoEEngine:
         s = L.Stats()
         self._ck(self.lib.b2m_stats_get(self._h, C.byref(s)))
         return s.as_dict()
+
+    def last_lookahead(self) -> List[int]:
+        arr = (C.c_int32 * self.E)()
+        self._ck(self.lib.b2m_last_lookahead(self._h, arr))
+        return list(arr)
 
     def last_counts(self) -> List[int]:
         arr = (C.c_int32 * self.E)()

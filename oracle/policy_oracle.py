@@ -13,6 +13,11 @@ moe-infinity_b200/csrc/api.cu, which is itself the *explicit* version of the ref
       hits as well, so it only ever equals the free HBM while the cache fills by misses alone (policy="reference";
       policy="slots" charges nothing for hits and evicts only when no physical slot is free).
       Eviction does not reset incache_visit_count; only clear_expert_cache_counts does (:175-185).
+  activation-aware cache (policy="activation_aware"; B2M_CACHE_ACTIVATION_AWARE in include/b2m.h): the cache the reference
+      specifies in moe_infinity/memory/expert_priority_score.py:84-172 / expert_cache.py:95-167 (layer-distance decay x
+      activation frequency) but never instantiates (model_offload.py:83).  Victim = resident expert with the largest
+      expected time to its next use: layers until its layer runs again + L * (1/f - 1), f = moving average (alpha) of
+      "activated in a step", float32 arithmetic, layer-major scan, first maximum wins; physical slots are the budget.
   prefetch          core/prefetch/task_scheduler.h:66-79 (ReplaceCacheCandidates: new protected set, queued
       prefetches dropped), task_scheduler.cpp:82-118 (dedupe), :236-317 (evict-to-fit, skipping protected
       candidates and nodes in use).
@@ -29,12 +34,17 @@ from __future__ import annotations
 
 from typing import Iterable, List, Optional, Sequence, Set, Tuple
 
+import numpy as np
+
 
 class CacheOracle:
     def __init__(self, num_layers: int, num_experts: int, num_slots: int, policy: str = "reference"):
         self.L, self.E, self.nslots = num_layers, num_experts, num_slots
         self.policy = policy
         self.budget = num_slots            # cache_sizes_[gpu] in expert units (expert_dispatcher.cpp:52-54)
+        self.alpha = np.float32(0.25)
+        self.freq = np.full(num_layers * num_experts, 0.5, dtype=np.float32)
+        self.cur_layer = 0
         n = num_layers * num_experts
         self.resident = [False] * n
         self.visits = [0] * n
@@ -48,7 +58,26 @@ class CacheOracle:
     def _id(self, layer, expert):
         return layer * self.E + expert
 
+    def _score(self, i: int) -> np.float32:
+        l = i // self.E
+        d = (l - self.cur_layer) % self.L
+        if d <= 0:
+            d += self.L
+        f = max(self.freq[i], np.float32(0.02))
+        return np.float32(d) + np.float32(self.L) * (np.float32(1.0) / f - np.float32(1.0))
+
     def _victim(self, in_use: Sequence[int], allow_protected: bool) -> int:
+        if self.policy == "activation_aware":
+            best, best_s = -1, np.float32(-1.0)
+            for i in range(self.L * self.E):       # layer-major, strict '>'
+                if not self.resident[i] or i in in_use:
+                    continue
+                if not allow_protected and i in self.protected:
+                    continue
+                s = self._score(i)
+                if s > best_s:
+                    best, best_s = i, s
+            return best
         best, best_v = -1, 1 << 60
         for e in range(self.E):            # expert-major scan, strict '<'
             for l in range(self.L):
@@ -100,6 +129,11 @@ class CacheOracle:
         a wave takes every still-to-run expert that is resident or can get a slot without evicting another
         still-to-run expert; finished waves become evictable."""
         active = [self._id(layer, e) for e in sorted(set(experts))]
+        self.cur_layer = layer
+        act_set = set(experts)
+        for e in range(self.E):            # activation average of this layer's experts (api.cu: before the residency pass)
+            i = self._id(layer, e)
+            self.freq[i] = (np.float32(1.0) - self.alpha) * self.freq[i] + (self.alpha if e in act_set else np.float32(0.0))
         out = []
         remaining = list(active)
         wave: List[int] = []

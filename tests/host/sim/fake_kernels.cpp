@@ -114,6 +114,24 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
   return cudaSuccess;
 }
 
+cudaError_t launch_lookahead_counts(const RouteParams& p, int* counts_out, cudaStream_t) {
+  for (int t = 0; t < p.T; ++t) {
+    std::vector<float> s(p.E);
+    for (int e = 0; e < p.E; ++e) {
+      double acc = 0;
+      for (int h = 0; h < p.H; ++h)
+        acc += (double)as_float(p.x, (size_t)t * p.H + h, p.dtype) * as_float(p.gate_w, (size_t)e * p.H + h, p.gate_dtype);
+      s[e] = (float)acc;
+    }
+    std::vector<int> order(p.E);
+    for (int e = 0; e < p.E; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s[a] > s[b]; });
+    for (int j = 0; j < p.k; ++j) counts_out[order[j]] += 1;
+  }
+  logf("lookahead T=%d counts=%s", p.T, ints(counts_out, p.E).c_str());
+  return cudaSuccess;
+}
+
 cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cudaStream_t) {
   for (int t = 0; t < p.T; ++t) {
     int j = 0, nset = 0;

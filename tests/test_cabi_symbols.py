@@ -30,8 +30,8 @@ def test_header_symbols_exported_and_bound(lib_built):
 
 def test_config_struct_layout_matches_header(lib_built):
     from moe_infinity_b200 import _lib
-    # 18 int32 + float + int32 (80 B) + double + 4 int32 = 104 bytes with natural alignment
-    assert C.sizeof(_lib.Config) == 104
+    # 18 int32 + float + int32 (80 B) + double + 5 int32 + float = 112 bytes with natural alignment
+    assert C.sizeof(_lib.Config) == 112
     assert _lib.Config.device_memory_ratio.offset % 8 == 0
 
 

@@ -186,6 +186,85 @@ def test_reference_budget_charges_hits_on_cpu(sim):
         c.close()
 
 
+def test_activation_aware_policy_matches_oracle_on_cpu(sim):
+    """B2M_CACHE_ACTIVATION_AWARE: victim = largest expected time to next use (layer distance + L*(1/f - 1)); api.cu and
+    oracle/policy_oracle.py (policy 'activation_aware') agree on every hit flag and resident set of a seeded decode trace
+    in which layers are visited in order."""
+    for nslots, seed in ((10, 12), (13, 13)):
+        c = Ctx(sim, L_=4, E=8, num_slots=nslots, cache_policy=L.CACHE_ACTIVATION_AWARE)
+        assert c.rc == 0, c.err()
+        c.register_all(seed)
+        orc = CacheOracle(c.L, c.E, nslots, policy="activation_aware")
+        rng = np.random.default_rng(seed)
+        bias = rng.standard_normal((c.L, c.E)).astype(np.float32) * 1.5        # per-layer popular experts
+        for step in range(14):
+            for l in range(c.L):
+                lg = rng.standard_normal((5, c.E)).astype(np.float32) + bias[l]
+                before = {e: c.resident(l, e) for e in range(c.E)}
+                assert c.forward(l, lg) == 0, c.err()
+                cnt = c.counts()
+                active = [e for e in range(c.E) if cnt[e] > 0]
+                assert [(e, before[e]) for e in active] == orc.dispatch(l, active), (nslots, step, l)
+                for ll in range(c.L):
+                    for e in range(c.E):
+                        assert c.resident(ll, e) == orc.resident[ll * c.E + e], (nslots, step, l, ll, e)
+        s = c.stats()
+        assert s["evictions"] == orc.stats["evictions"] > 0 and s["misses"] == orc.stats["misses"]
+        c.close()
+
+
+def test_lookahead_prefetch_stages_next_layers_experts_on_cpu(sim):
+    """cfg.lookahead_prefetch: the routing call also applies the NEXT layer's router weight to this layer's input; the
+    predicted experts come back with the counts (no extra synchronisation), are protected from eviction and staged on the
+    prefetch stream; a correctly predicted expert is a hit (prefetch_useful) when its layer runs."""
+    Ln, E, H = 3, 8, 128
+    c = Ctx(sim, L_=Ln, E=E, H=H, num_slots=20, cache_policy=L.CACHE_ACTIVATION_AWARE, lookahead_prefetch=1,
+            max_inflight_prefetch=16)
+    assert c.rc == 0, c.err()
+    c.register_all(3)
+    rng = np.random.default_rng(3)
+    # router weights (bf16) per layer: expert e of layer l likes direction e + l (so the prediction is checkable)
+    gates = []
+    for l in range(Ln):
+        g = np.zeros((E, H), dtype=np.float32)
+        for e in range(E):
+            g[e, (e + l) % E] = 4.0
+        gb = (g.view(np.uint32) >> 16).astype(np.uint16)            # exact in bf16
+        gates.append(gb)
+        assert sim.b2m_set_gate(c.h, l, gb.ctypes.data) == 0
+    T = 4
+    syncs0 = c.stats()["host_syncs"]
+    for step in range(3):
+        for l in range(Ln):
+            xf = np.zeros((T, H), dtype=np.float32)
+            for t in range(T):
+                xf[t, (t + step) % E] = 3.0
+                xf[t, (t + step + 3) % E] = 2.0
+            x = (xf.view(np.uint32) >> 16).astype(np.uint16)
+            out = np.zeros((T, H), dtype=np.uint16)
+            take_log(sim)
+            rc = sim.b2m_moe_forward(c.h, l, x.ctypes.data, None, 0, 0, T, 0, out.ctypes.data, None)
+            assert rc == 0, c.err()
+            look = (C.c_int32 * E)()
+            assert sim.b2m_last_lookahead(c.h, look) == 0, c.err()
+            nxt = (l + 1) % Ln
+            want = np.zeros(E, dtype=int)
+            for t in range(T):                                       # top-2 of the next layer's logits on this input
+                lg = xf[t] @ (gates[nxt].astype(np.uint32) << 16).view(np.float32).T
+                for e in np.argsort(-lg, kind="stable")[:2]:
+                    want[e] += 1
+            assert list(look) == want.tolist()
+            assert sim.b2m_prefetch_drain(c.h) == 0
+            for e in range(E):
+                if want[e] > 0:
+                    assert c.resident(nxt, e), (step, l, e)           # staged ahead of its layer
+    s = c.stats()
+    assert s["host_syncs"] - syncs0 == 3 * Ln                        # still one read-back per layer call
+    assert s["prefetch_issued"] > 0 and s["prefetch_useful"] > 0
+    assert s["prefetch_useful"] >= 0.8 * (s["prefetch_issued"] - 4)   # same inputs feed every layer here: predictions hold
+    c.close()
+
+
 def test_all_resident_mode_never_syncs_on_cpu(sim):
     c = Ctx(sim, num_slots=24)                 # L*E slots: every expert fits
     c.register_all(4)
