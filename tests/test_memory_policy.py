@@ -164,13 +164,19 @@ def test_priority_score_matches_literal_reference(current_layer):
 
 # ---------------------------------------------------------------- cache policy oracle: the stated rules
 def test_cache_oracle_lfu_eviction_and_tie_order():
-    c = CacheOracle(num_layers=2, num_experts=4, num_slots=3)
+    c = CacheOracle(num_layers=2, num_experts=4, num_slots=3, policy="slots")
     assert c.dispatch(0, [0, 1]) == [(0, False), (1, False)]
     assert c.dispatch(0, [0]) == [(0, True)]                 # visits: (0,0)=2, (0,1)=1
     assert c.dispatch(1, [2]) == [(2, False)]                # third slot
     assert c.dispatch(1, [3]) == [(3, False)]                # evicts min visits, ties -> expert-major scan
     assert c.evicted_log == [(0, 1)]                         # (0,1) and (1,2) both have 1 visit; expert 1 scanned first
     assert c.stats["misses"] == 4 and c.stats["hits"] == 1
+    # the reference's byte budget is charged for hits too (expert_dispatcher.cpp:266): after 2 misses + 1 hit the budget
+    # of 3 experts is used up, so the third miss already evicts although a slot is physically free
+    # (behaviour confirmed on the reference's real engine: tests/golden/policy_ref_trace.json never holds 9 of its 9 experts)
+    r = CacheOracle(num_layers=2, num_experts=4, num_slots=3, policy="reference")
+    r.dispatch(0, [0, 1]); r.dispatch(0, [0]); r.dispatch(1, [2]); r.dispatch(1, [3])
+    assert r.evicted_log == [(0, 1), (1, 2)] and sum(r.resident) == 2
 
 
 def test_cache_oracle_waves_when_active_set_exceeds_slots():

@@ -301,12 +301,25 @@ def mode_timing(args):
         mask = mask.permute(0, 2, 1).sum(dim=-1).to(torch.bool)
         count = mask.sum(dim=0).cpu().numpy().flatten()                            # the reference's per-layer host sync
         active = [e for e in range(E) if count[e] > 0]
-        d.set_inputs(x, mask)
-        d.set_expected_queue(len(active))
-        for e in active:
-            d.enqueue_expert(l, e, 0, False)
         out = torch.zeros_like(x)
-        for y, _, e, hit in d.wait_expert():
+        if args.protocol == "batch":                                               # dispatch_local: all at once
+            d.set_inputs(x, mask)
+            d.set_expected_queue(len(active))
+            for e in active:
+                d.enqueue_expert(l, e, 0, False)
+            results = d.wait_expert()
+        else:
+            # one expert per enqueue/wait.  Needed whenever the engine evicts: GPUFetchFunc's victim scan try_locks EVERY
+            # node (expert_dispatcher.cpp:239-245) while the Python thread is still enqueueing the layer's other experts,
+            # whose own try_lock then fails -> DLOG_FATAL -> abort (:127-132).  Observed on a B200 with 352 MB experts
+            # (profiles/r02_ref_engine_offload_batch_abort.log); the single fetch thread serialises the copies anyway.
+            results = []
+            for e in active:
+                d.set_inputs(x, mask)
+                d.set_expected_queue(1)
+                d.enqueue_expert(l, e, 0, False)
+                results += d.wait_expert()
+        for y, _, e, hit in results:
             idx = mask[:, e]
             out[idx] += y.to(x.device) * wmask[idx, e][:, None]
             hits[1] += 1
@@ -331,7 +344,8 @@ def mode_timing(args):
            "hidden": H, "inter": I, "experts": E, "setup_s": setup_s, "budget_experts": args.budget_experts, "store_dir": store,
            "ms_per_step": ref_ms, "ms_per_step_median": sorted(per_step)[len(per_step) // 2], "ms_per_layer": ref_ms / L_,
            "tokens_per_s_32_layers": T / (ref_ms / L_ * 32 / 1e3), "hit_rate": hits[0] / max(hits[1], 1),
-           "resident_experts": len(ref.resident()), "threads": args.threads}
+           "resident_experts": len(ref.resident()), "threads": args.threads, "protocol": args.protocol,
+           "h2d_gb_per_step": (1.0 - hits[0] / max(hits[1], 1)) * hits[1] / max(args.steps, 1) * expert_bytes / 1e9}
 
     # ---- this repository's engine on the same weights and the reference's own router logits
     if args.compare:
@@ -390,6 +404,8 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--threads", type=int, default=8)
     ap.add_argument("--budget-experts", type=int, default=0, help="timing mode: derive --ratio from an HBM budget of N experts")
+    ap.add_argument("--protocol", choices=["batch", "sequential"], default="batch",
+                    help="timing mode: dispatch_local's all-at-once enqueue, or one expert per enqueue/wait (forced offload)")
     ap.add_argument("--compare", type=int, default=1, help="timing mode: also run this repo's engine and compare hidden states")
     args = ap.parse_args()
     if args.mode == "policy":
