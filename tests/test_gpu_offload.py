@@ -211,3 +211,44 @@ def test_cache_policy_matches_reference_engine_trace(lib_built):
         assert (rl, re_, int(hit)) == (l, e, rec["hit"]), rec
         res = sorted([ll, ee] for (ll, ee) in ids if d.engine.is_resident(ll, ee))
         assert res == rec["resident_after"], (rec["n"], l, e)
+
+
+def test_activation_aware_cache_with_lookahead_prefetch(lib_built):
+    """B2M_CACHE_ACTIVATION_AWARE + cfg.lookahead_prefetch on the GPU: outputs stay bit-identical to the all-resident run while
+    the next layer's experts are staged ahead from this layer's router-logit look-ahead; the look-ahead counts equal the
+    top-k of (x @ W_gate[next]^T); the eviction sequence equals oracle/policy_oracle.py (policy 'activation_aware')."""
+    from moe_infinity_b200 import MoEEngine, _lib as Lb
+    experts, gates = _model(11)
+    nslots = 14
+    full = _engine(experts, gates, L * E)
+    eng = _engine(experts, gates, nslots, cache_policy=Lb.CACHE_ACTIVATION_AWARE, lookahead_prefetch=True, max_inflight_prefetch=4)
+    plain = _engine(experts, gates, nslots, cache_policy=Lb.CACHE_ACTIVATION_AWARE)      # same policy, no prefetch: oracle-checkable
+    orc = CacheOracle(L, E, nslots, policy="activation_aware")
+    g = torch.Generator().manual_seed(2)
+    T = 6
+    for step in range(8):
+        for l in range(L):
+            x = torch.randn(T, H, generator=g).to(DT).cuda()
+            a = full.forward(l, x)
+            b = eng.forward(l, x)
+            before = {e: plain.is_resident(l, e) for e in range(E)}
+            c = plain.forward(l, x)
+            torch.cuda.synchronize()
+            assert torch.equal(a, b) and torch.equal(a, c), f"step {step} layer {l}"
+            cnt = plain.last_counts()
+            active = [e for e in range(E) if cnt[e] > 0]
+            assert [(e, before[e]) for e in active] == orc.dispatch(l, active), (step, l)
+            # look-ahead = top-k of the next layer's logits on this input (bf16 logits like the Mixtral router; skip near ties)
+            look = eng.last_lookahead()
+            lg = torch.nn.functional.linear(x.float(), gates[(l + 1) % L].float().cuda())
+            top = lg.topk(K + 1, dim=-1).values
+            clear = (top[:, K - 1] - top[:, K]) > 0.05 * lg.abs().max()
+            if bool(clear.all()):
+                want = torch.bincount(lg.topk(K, dim=-1).indices.flatten().cpu(), minlength=E).tolist()
+                assert look == want, (step, l)
+    st = eng.stats()
+    assert st["prefetch_issued"] > 0 and st["prefetch_useful"] > 0
+    assert st["host_syncs"] == 8 * L                       # the look-ahead rides on the per-layer count read-back
+    for ll in range(L):
+        for e in range(E):
+            assert plain.is_resident(ll, e) == orc.resident[ll * E + e]

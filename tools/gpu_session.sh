@@ -1,11 +1,10 @@
 #!/bin/bash
-# one gpurun call (session 2): GPU test-suite, the reference engine timed beside ours, both bench arms, DeepSeek / DYN_N baselines
+# session 3: look-ahead/activation-aware GPU test, reference engine under forced offload (sequential protocol), config 3 small then full
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s_pytest.log
-timeout 900 python tools/ref_engine_harness.py --mode timing --layers 4 --ratio 0.9 --steps 8 --out gpurun_out/ref_timing_resident.json > gpurun_out/s_timing_res.log 2>&1; echo "rc=$?" >> gpurun_out/s_timing_res.log
-timeout 900 python tools/ref_engine_harness.py --mode timing --layers 4 --budget-experts 15 --steps 4 --warmup 1 --compare 0 --out gpurun_out/ref_timing_offload.json > gpurun_out/s_timing_off.log 2>&1; echo "rc=$?" >> gpurun_out/s_timing_off.log
-timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/s_bench_ref.log 2>&1; echo "rc=$?" >> gpurun_out/s_bench_ref.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/s_bench.log 2>&1; echo "rc=$?" >> gpurun_out/s_bench.log
-timeout 600 python tools/bench_configs.py --what deepseek --out gpurun_out/s_deepseek_base.json > gpurun_out/s_deepseek_base.log 2>&1
-B2M_DYN_N=1 timeout 600 python tools/bench_configs.py --what deepseek --out gpurun_out/s_deepseek_dyn.json > gpurun_out/s_deepseek_dyn.log 2>&1
-tail -4 gpurun_out/s_pytest.log; tail -2 gpurun_out/s_timing_res.log; tail -2 gpurun_out/s_timing_off.log; tail -2 gpurun_out/s_bench_ref.log | cut -c1-600; tail -2 gpurun_out/s_bench.log | cut -c1-300; tail -2 gpurun_out/s_deepseek_base.log; tail -2 gpurun_out/s_deepseek_dyn.log
+timeout 600 python -m pytest tests/test_gpu_offload.py -m gpu -q --timeout 300 > gpurun_out/s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s_pytest.log
+timeout 900 python tools/ref_engine_harness.py --mode timing --layers 4 --budget-experts 15 --steps 4 --warmup 1 --compare 0 --protocol sequential --out gpurun_out/ref_timing_offload.json > gpurun_out/s_timing_off.log 2>&1; echo "rc=$?" >> gpurun_out/s_timing_off.log
+timeout 600 python bench.py --config offload --layers 8 --steps 6 --warmup 2 --prefill 2048 --ablate > gpurun_out/s_offload_small.log 2>&1; echo "rc=$?" >> gpurun_out/s_offload_small.log
+if tail -2 gpurun_out/s_offload_small.log | grep -q '"same_outputs": true'; then
+  timeout 1500 python bench.py --config offload --steps 32 --warmup 4 --ablate > gpurun_out/s_offload_full.log 2>&1; echo "rc=$?" >> gpurun_out/s_offload_full.log
+fi
+tail -4 gpurun_out/s_pytest.log; tail -2 gpurun_out/s_timing_off.log | cut -c1-900; tail -2 gpurun_out/s_offload_small.log | cut -c1-3000; tail -2 gpurun_out/s_offload_full.log | cut -c1-3000
