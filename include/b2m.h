@@ -261,6 +261,13 @@ int b2m_ep_p2p_collect(b2m_ctx* ctx, int T_local, void* stream);
 int b2m_ep_p2p_route(b2m_ctx* ctx, int layer, const void* x, const void* router_in, int router_in_kind,
                      int router_in_dtype, int T_local, void* stream);
 int b2m_ep_p2p_combine(b2m_ctx* ctx, int layer, const void* x, int T_local, void* out, void* stream);
+/* the whole expert-parallel layer in one call (T_local <= 256).  With <= 8 experts per rank it runs in FIVE kernels: the
+ * permute kernel stores rows + per-slot expert tags into the owners' receive areas, the owners' gate/up GEMM reads its
+ * token tile straight from that area (no regroup kernel; weights stream while the tokens are still in flight), the down
+ * GEMM's last CTA publishes "done", and the source's combine kernel reads the owners' fp32 outputs in place over NVLink
+ * (no return kernel).  Otherwise = b2m_ep_p2p_route -> regroup -> b2m_run_experts -> return -> b2m_ep_p2p_combine. */
+int b2m_ep_p2p_layer(b2m_ctx* ctx, int layer, const void* x, const void* router_in, int router_in_kind,
+                     int router_in_dtype, int T_local, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -139,6 +139,7 @@ struct b2m_ctx {
 
   int cur_ksplit = 1, cur_nt = 16, cur_nt_dn = 16, cur_T = 0;   // token-tile widths of the up (K3) and down (K4) GEMMs
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
+  bool ep_direct_next = false;   // the routing / combine call in progress belongs to b2m_ep_p2p_layer's direct mode
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
   struct P2P {
@@ -147,6 +148,8 @@ struct b2m_ctx {
     size_t area_bytes = 0;
     uint8_t* peer_base[16] = {nullptr};
     int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters
+    size_t tags_off = 0, y_off = 0;     // direct mode regions inside the allocation: tags[nranks*cap] (int), y[nranks*cap][H] (fp32)
+    CUtensorMap tm_recv[5];             // the receive area as the token operand of the gate/up GEMM: [nranks*cap rows][H]
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
@@ -822,6 +825,7 @@ int b2m_ws_ptr(b2m_ctx* c, int which, void** p) {
 
 // ------------------------------------------------------------------------------------
 static EpParams ep_p2p_params(b2m_ctx* c);
+static EpParams ep_p2p_params_direct(b2m_ctx* c);
 static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T,
                       int seq_len, void* stream, bool ep_dispatch);
 
@@ -867,8 +871,8 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   if (ep_dispatch) {
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;
-    p.ep = ep_p2p_params(c);
-    p.y_zero = nullptr;        // the regroup kernel clears the accumulator for the rows this rank will compute
+    p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
+    p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
   CK(c, launch_route(p, st));
   c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0);
@@ -1206,7 +1210,7 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   }
   if (ep_collect) {
     p.ep_collect = 1;
-    p.ep = ep_p2p_params(c);
+    p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
   }
   CK(c, launch_combine(p, st));
   c->stats.kernel_launches += 1;
@@ -1467,6 +1471,19 @@ static EpParams ep_p2p_params(b2m_ctx* c) {
   p.back_rows = q.base + q.area_bytes;
   p.epoch = q.local_ctr;
   p.done_ctr = q.local_ctr + 2;
+  for (int r = 0; r < q.nranks; ++r) {
+    p.peer_tags[r] = reinterpret_cast<int*>(q.peer_base[r] + q.tags_off);
+    p.peer_y[r] = reinterpret_cast<float*>(q.peer_base[r] + q.y_off);
+  }
+  p.local_tags = reinterpret_cast<int*>(q.base + q.tags_off);
+  p.local_y = reinterpret_cast<float*>(q.base + q.y_off);
+  return p;
+}
+// direct mode: [nranks][cap] receive slots without a counts row, per-slot tags, outputs read in place by the sources
+static EpParams ep_p2p_params_direct(b2m_ctx* c) {
+  EpParams p = ep_p2p_params(c);
+  p.inline_counts = 0;
+  p.direct = 1;
   return p;
 }
 
@@ -1479,9 +1496,16 @@ int b2m_ep_p2p_init(b2m_ctx* c, int nranks, int rank, int cap, void* ipc_handle_
   b2m_ctx::P2P& q = c->p2p;
   q.nranks = nranks; q.rank = rank; q.cap = cap;
   q.area_bytes = p2p_area_bytes(c, nranks, cap);
-  const size_t total = 2 * q.area_bytes + 32 * sizeof(int);
+  q.tags_off = (2 * q.area_bytes + 32 * sizeof(int) + 255) & ~(size_t)255;
+  q.y_off = (q.tags_off + (size_t)nranks * cap * sizeof(int) + 255) & ~(size_t)255;
+  const size_t total = q.y_off + (size_t)nranks * cap * c->cfg.hidden * sizeof(float);
   CK(c, cudaMalloc((void**)&q.base, total));
   CK(c, cudaMemset(q.base, 0, total));
+  CK(c, cudaMemset(q.base + q.tags_off, 0xff, (size_t)nranks * cap * sizeof(int)));   // every slot empty
+  for (int i = 0; i < 5; ++i) {
+    int rr = build_act_map(c, &q.tm_recv[i], q.base, c->cfg.hidden, nranks * cap, NT_LIST[i]);
+    if (rr) return rr;
+  }
   CK(c, cudaMalloc((void**)&q.local_ctr, 4 * sizeof(int)));
   CK(c, cudaMemset(q.local_ctr, 0, 4 * sizeof(int)));
   CK(c, cudaDeviceSynchronize());
@@ -1545,6 +1569,107 @@ int b2m_ep_p2p_combine(b2m_ctx* c, int layer, const void* x, int T_local, void* 
   if (r) return r;
   if (T_local < 0 || T_local * c->cfg.top_k > c->p2p.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, c->p2p.cap);
   return combine_impl(c, layer, x, T_local, out, stream, true);
+}
+
+// One expert-parallel MoE layer in FIVE kernels (was seven): gate/top-k -> permute that stores rows + slot tags into the
+// owners' receive areas -> gate/up GEMM reading its token tile straight from the receive area (weights stream from the
+// first cycle, only the token tiles wait for the peers' flags) -> down GEMM whose last CTA publishes "done" -> combine
+// that waits for the owners and reads their fp32 outputs in place over NVLink.  Falls back to the seven-kernel sequence
+// when a rank owns many experts (every local expert's GEMM spans all receive slots: fine for <= 8 experts per rank).
+int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in, int kind, int in_dtype, int T_local,
+                     void* out, void* stream) {
+  int r = p2p_ready(c);
+  if (r) return r;
+  r = check_layer(c, layer);
+  if (r) return r;
+  const b2m_ctx::P2P& q = c->p2p;
+  const b2m_config& f = c->cfg;
+  if (T_local < 1 || T_local * f.top_k > q.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, q.cap);
+  if (!out) return fail(c, B2M_EINVAL, "out is null");
+  const int El = f.num_experts / q.nranks, R = q.nranks * q.cap, T_total = q.nranks * T_local;
+  static const bool direct_on = !(getenv("B2M_EP_DIRECT") && getenv("B2M_EP_DIRECT")[0] == '0');
+  const bool direct = direct_on && El <= 8 && R <= 256 && T_local <= 256 && f.gemm_impl == 0 && f.shared_inter == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!direct) {
+    r = b2m_ep_p2p_route(c, layer, x, router_in, kind, in_dtype, T_local, stream);
+    if (!r) r = b2m_ep_p2p_regroup(c, T_total, stream);
+    if (!r) r = b2m_run_experts(c, layer, T_total, stream);
+    if (!r) r = b2m_ep_p2p_return(c, stream);
+    if (!r) r = b2m_ep_p2p_combine(c, layer, x, T_local, out, stream);
+    return r;
+  }
+  c->ep_direct_next = true;
+  r = route_impl(c, layer, x, router_in, kind, in_dtype, T_local, 0, stream, true);
+  c->ep_direct_next = false;
+  if (r) return r;
+  c->ep_mode = true;
+  c->ep_inline = 0;
+  for (int e = q.rank * El; e < (q.rank + 1) * El; ++e) {
+    const Expert& ex = c->experts[(size_t)layer * f.num_experts + e];
+    if (ex.state != ST_RESIDENT && ex.state != ST_LOADING)
+      return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", layer, e);
+  }
+  r = upload_row_if_dirty(c, layer, st);
+  if (r) return r;
+  // ---- plan: one token tile spanning all receive slots
+  int nt = 16;
+  while (nt < R) nt *= 2;
+  c->cur_T = T_total;
+  c->cur_nt = c->cur_nt_dn = nt;
+  const ExpertShape& s = c->arena.shape;
+  int ks = 1;
+  if (!s.has_bias) {
+    const int kblocks = (s.I + 63) / 64;
+    const long long tiles = (long long)El * ((s.H + 127) / 128);
+    ks = (int)std::min<long long>(8, (6LL * c->num_sms + tiles - 1) / tiles);
+    ks = std::max(1, std::min(ks, kblocks / 4 > 0 ? kblocks / 4 : 1));
+  }
+  c->cur_ksplit = ks;
+  EpParams ep = ep_p2p_params_direct(c);
+  GemmParams base;
+  memset(&base, 0, sizeof base);
+  base.slot_of = c->d_slot_of + (size_t)layer * f.num_experts;
+  base.E = f.num_experts;
+  base.single_n = -1;
+  base.ep_rows = R;
+  base.ep_first = q.rank * El;
+  base.ep_el = El;
+  base.ep_tags = ep.local_tags;
+  base.ep_nranks = q.nranks;
+  base.ep_rank = q.rank;
+  base.ep_flag = ep.local_recv_flag;
+  base.ep_epoch = ep.epoch;
+  GemmParams up = base;
+  up.M = s.I; up.K = s.H; up.ksplit = 1; up.epi = EPI_ACT16; up.act = s.act;
+  up.mimic = f.numerics == B2M_NUMERICS_REFERENCE; up.out = c->d_hmid; up.ld_out = s.I;
+  up.ep_wait = 1;
+  up.ep_zero = ks > 1 ? ep.local_y : nullptr;
+  up.ep_zero_elems = (size_t)R * s.H;
+  GemmParams dn = base;
+  dn.M = s.H; dn.K = s.I; dn.ksplit = ks; dn.epi = EPI_LINEAR_F32; dn.act = ACT_NONE; dn.mimic = 0;
+  dn.out = ep.local_y; dn.ld_out = s.H;
+  dn.stream_k = ks > 1 ? 1 : 0;
+  dn.early_a = pdl_enabled() ? 0 : 1;        // weights of the down projection are prefetched under the gate/up GEMM's tail
+  dn.ep_signal = 1;
+  dn.ep_done_ctr = ep.done_ctr + 1;
+  dn.ep_done_epoch = ep.epoch + 1;
+  for (int p2 = 0; p2 < q.nranks; ++p2) dn.ep_peer_done_flag[p2] = ep.peer_back_flag[p2];
+  if (s.has_bias) {
+    up.bias_base = dn.bias_base = c->arena.base;
+    up.bias_slot_elems = dn.bias_slot_elems = c->arena.slot_bytes / 2;
+    up.bias_off = s.off_bias1 / 2;
+    dn.bias_off = s.off_bias2 / 2;
+    dn.mimic = up.mimic;
+  }
+  const int ni = nt_index(nt);
+  CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, c->num_sms, st));
+  CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, c->tm_hmid[ni], dn, c->num_sms, st));
+  c->stats.kernel_launches += 2;
+  // ---- combine at the source: wait for the owners' "done", read their outputs in place
+  c->ep_direct_next = true;
+  r = combine_impl(c, layer, x, T_local, out, stream, true);
+  c->ep_direct_next = false;
+  return r;
 }
 
 int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {

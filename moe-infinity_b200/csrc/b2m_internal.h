@@ -51,6 +51,25 @@ struct GemmParams {
   const void* bias_base;
   size_t bias_slot_elems;
   size_t bias_off;
+  // ---- expert-parallel "direct" mode (ep_rows > 0; csrc/ep.cu header): the token operand is this rank's peer-written receive
+  // area itself, ALL ep_rows = nranks*cap slots as one shared row range for every local expert (no regroup kernel, static tile
+  // list -> weights stream from the first cycle); ep_tags[slot] = local expert index of the row in that slot or -1, and an
+  // epilogue only stores the slots whose tag names its expert.
+  int ep_rows;               // 0 = off
+  int ep_first;              // first global expert id owned by this rank
+  int ep_el;                 // experts per rank
+  const int* ep_tags;        // [ep_rows] written by the source ranks' dispatch kernels (peer stores)
+  int ep_nranks;
+  int ep_wait;               // 1: the token operand / tags arrive from the peers: wait for their epoch flags (gate/up GEMM)
+  const int* ep_flag;        // [nranks] this rank's receive flags
+  const int* ep_epoch;       // local epoch word the flags must reach
+  float* ep_zero;            // fp32 accumulator of the down projection, cleared once the flags have been seen
+  size_t ep_zero_elems;
+  int ep_signal;             // 1: when the whole grid has finished, publish *ep_done_epoch + 1 to every peer (down GEMM)
+  int* ep_done_ctr;          // CTA arrival counter (0 between launches)
+  int* ep_done_epoch;        // local epoch word of the return direction
+  int* ep_peer_done_flag[16];  // peer r's done_flag[nranks] (this rank writes entry [rank])
+  int ep_rank;
 };
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
@@ -93,6 +112,13 @@ struct EpParams {
   int* local_back_flag;
   int* epoch;                 // local: [0] dispatches issued, [1] returns issued
   int* done_ctr;              // local: [0] CTAs finished in dispatch kernel, [1] in return kernel
+  // ---- direct mode (direct = 1): receive slots are [nranks][cap] rows (no counts row); every slot carries a tag; the owners'
+  // fp32 outputs are read in place by the source ranks' combine kernels (peer loads), no return kernel
+  int direct;
+  int* peer_tags[16];         // peer r's tags[nranks*cap]
+  int* local_tags;
+  float* peer_y[16];          // peer r's fp32 outputs y[nranks*cap][H]
+  float* local_y;
 };
 cudaError_t launch_ep_pack(const EpParams& p, int max_rows, cudaStream_t st);
 cudaError_t launch_ep_regroup(const EpParams& p, cudaStream_t st);

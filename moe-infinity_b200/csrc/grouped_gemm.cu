@@ -16,6 +16,7 @@
 //           (down projection), optionally split-K with fp32 red.add.
 #include "b2m_common.cuh"
 #include "b2m_internal.h"
+#include "ep_device.cuh"
 #include "tile_walker.cuh"
 
 namespace b2m {
@@ -69,6 +70,15 @@ __device__ __forceinline__ float silu_mufu(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
+}
+
+// expert-parallel direct mode: wait (one thread) until every source rank has published this layer's epoch, i.e. its rows
+// and tags have landed in this rank's receive area.  Called by every thread that goes on to read peer-written data with
+// ordinary loads (the acquire orders that thread's own later reads); the TMA producer adds a generic->async proxy fence.
+__device__ __forceinline__ void ep_gemm_wait(const GemmParams& p) {
+  const int want = *reinterpret_cast<const volatile int*>(p.ep_epoch);
+  for (int r = 0; r < p.ep_nranks; ++r)
+    while (ld_acquire_sys(p.ep_flag + r) < want) __nanosleep(32);
 }
 
 template <int NT, bool DUAL, int DT, int MC>
@@ -127,6 +137,14 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (!p.early_a) pdl_wait();
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
+  } else if (p.ep_rows > 0) {
+    // direct mode: a static tile list -- every local expert spans all receive slots; nothing here depends on the peers
+    for (int i = threadIdx.x; i <= E; i += Cfg::THREADS) {
+      int le = i - p.ep_first;
+      le = le < 0 ? 0 : (le > p.ep_el ? p.ep_el : le);
+      offs[i] = le * p.ep_rows;
+    }
+    for (int i = threadIdx.x; i < E; i += Cfg::THREADS) slots[i] = p.slot_of[i];
   } else {
     for (int i = threadIdx.x; i <= E; i += Cfg::THREADS) offs[i] = p.offsets[i];
     for (int i = threadIdx.x; i < E; i += Cfg::THREADS) slots[i] = p.slot_of[i];
@@ -148,7 +166,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   if (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast targets them
 
-  TileWalker walker{tile_start, offs, slots, E, NT, p.stream_k ? 1 : p.ksplit, kblocks, 0, m_step, MC, crank, 0, 0, 0};
+  TileWalker walker{tile_start, offs, slots, E, NT, p.stream_k ? 1 : p.ksplit, kblocks, 0, m_step, MC, crank, 0, 0, 0,
+                    p.ep_rows > 0 ? 1 : 0};
   if (MC == 1 && p.stream_k) {
     const long long units = (long long)tile_start[E] * kblocks;
     walker.stream = 1;
@@ -163,7 +182,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      bool waited = !p.early_a;
+      bool waited = !(p.early_a || p.ep_wait);   // ep_wait: token tiles come from the peers, weights do not
       int npend = 0, pend_stage[Cfg::STAGES], pend_kb[Cfg::STAGES], pend_row[Cfg::STAGES];
       for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
@@ -194,7 +213,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             // tiles follow once it has
             pend_stage[npend] = stage; pend_kb[npend] = kb; pend_row[npend] = t.row0;
             if (++npend == Cfg::STAGES) {
-              pdl_wait();
+              if (p.early_a) pdl_wait();
+              if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); }
               for (int i = 0; i < npend; ++i)
                 tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                             pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -207,7 +227,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         }
       }
       if (!waited) {   // fewer work items than pipeline stages
-        pdl_wait();
+        if (p.early_a) pdl_wait();
+        if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); }
         for (int i = 0; i < npend; ++i)
           tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                       pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -260,6 +281,18 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     if (p.early_a) pdl_wait();
+    if (p.ep_rows > 0 && p.ep_flag) {
+      ep_gemm_wait(p);                   // this thread reads the peers' tags below (immediate when the flags are already up)
+      if (p.ep_zero) {
+        // clear the down projection's accumulator: safe now -- a source rank publishes this layer's flag only after its
+        // combine of the previous layer has finished reading the previous outputs
+        float4* z = reinterpret_cast<float4*>(p.ep_zero);
+        const size_t n4 = p.ep_zero_elems / 4;
+        const int et = Cfg::EPI_WARPS * 32;
+        for (size_t i = (size_t)blockIdx.x * et + (threadIdx.x - 128); i < n4; i += (size_t)gridDim.x * et)
+          z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int cgrp = (warp - 4) >> 2;    // with 8 epilogue warps two warps share a quadrant and alternate 16-column chunks
     const int r = q * 32 + lane;         // weight row inside the tile
@@ -277,16 +310,24 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         if (row_ok) bias0 = Half16<DT>::to_f(bp[m]);
         if (DUAL && m + BLOCK_M < p.M) bias1 = Half16<DT>::to_f(bp[m + BLOCK_M]);
       }
+      const int ep_le = t.e - p.ep_first;   // direct mode: only the slots tagged with this expert are stored
       for (int c0 = cgrp * 16; c0 < t.ncols; c0 += 16 * (Cfg::EPI_WARPS / 4)) {   // warp-uniform trip count
         uint32_t vg[16], vu[16];
         tmem_ld_x16(taddr + c0, vg);
         if (DUAL) tmem_ld_x16(taddr + NT + c0, vu);
+        uint32_t keep = 0xffffu;
+        if (p.ep_rows > 0) {
+          keep = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < t.ncols && __ldcg(p.ep_tags + t.row0 + c0 + j) == ep_le) keep |= 1u << j;
+        }
         tmem_ld_wait();
         if (p.epi == EPI_LINEAR_F32) {
           float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (c0 + j < t.ncols) {
+            if (c0 + j < t.ncols && ((keep >> j) & 1u)) {
               float* dst = out + (size_t)(t.row0 + c0 + j) * p.ld_out + m;
               if (row_ok) {
                 float v = __uint_as_float(vg[j]);
@@ -304,7 +345,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (row_ok && c0 + j < t.ncols) {
+            if (row_ok && c0 + j < t.ncols && ((keep >> j) & 1u)) {
               float g = __uint_as_float(vg[j]);
               float h;
               if (DUAL) {
@@ -335,8 +376,21 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   }
 
   // ---- teardown ---------------------------------------------------------------------
+  if (p.ep_signal) __threadfence_system();   // this thread's output stores / reductions before the grid-wide "done" below
   tc_fence_before();
   __syncthreads();
+  if (p.ep_signal && threadIdx.x == 0) {
+    // last CTA of the grid: every output of this rank for this layer is in memory -> tell the source ranks, whose combine
+    // kernels read the rows in place over NVLink
+    if (atomicAdd(p.ep_done_ctr, 1) == (int)gridDim.x - 1) {
+      __threadfence_system();
+      *p.ep_done_ctr = 0;
+      const int e = *p.ep_done_epoch + 1;
+      *p.ep_done_epoch = e;
+      __threadfence_system();
+      for (int r = 0; r < p.ep_nranks; ++r) st_release_sys(p.ep_peer_done_flag[r] + p.ep_rank, e);
+    }
+  }
   if (MC > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast / commit into its shared memory
   if (warp == 2) {
     tc_fence_after();

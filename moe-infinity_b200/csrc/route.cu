@@ -872,11 +872,27 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
       if (p.ep_dispatch) p.ep.offsets_src[e] = s_off[e];
     }
   }
-  if (p.ep_dispatch && blockIdx.x == 0) {
+  if (p.ep_dispatch && blockIdx.x == 0 && p.ep.inline_counts) {
     // counts ride in the extra last row of every peer segment
     for (int i = threadIdx.x; i < p.ep.nranks * p.E; i += RT_THREADS) {
       const int r = i / p.E, e = i - r * p.E;
       reinterpret_cast<int*>(ep_send_row(p.ep, r, p.ep.cap))[e] = s_tot[e];
+    }
+  }
+  if (p.ep_dispatch && blockIdx.x == 0 && p.ep.direct) {
+    // direct mode: every receive slot of this rank's segment at every owner gets a tag -- the local expert index of the row
+    // stored there, or -1 for an unused slot (the owner's GEMM epilogues store only the slots tagged with their expert)
+    const int El = p.E / p.ep.nranks;
+    for (int i = threadIdx.x; i < p.ep.nranks * p.ep.cap; i += RT_THREADS) {
+      const int r = i / p.ep.cap, pos = i - r * p.ep.cap;
+      const int row = s_off[r * El] + pos;
+      int tag = -1;
+      if (row < s_off[(r + 1) * El]) {
+        int e = r * El;
+        while (row >= s_off[e + 1]) ++e;
+        tag = e - r * El;
+      }
+      p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = tag;
     }
   }
   if (warp < nchunks) {
@@ -1055,14 +1071,19 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   int rows[MAX_K];
   float ws[MAX_K];
   const uint16_t* src16[MAX_K];
+  const float* srcf[MAX_K];
+  int my_owner = 0;
   if (p.ep_collect) {
-    if (p.ep.p2p) p2p_wait(p.ep, 1);     // return rows of every owner rank have landed
+    if (p.ep.p2p) p2p_wait(p.ep, 1);     // return rows of every owner rank have landed (direct mode: the owners' GEMMs are done)
     if (lane < k && my_row >= 0) {
       // permuted row -> (owner rank, position in that rank's segment of this rank's return area)
       const int El = p.ep.E / p.ep.nranks;
       const int r = my_e / El;
       const int stride = p.ep.inline_counts ? p.ep.cap + 1 : p.ep.cap;
-      my_row = r * stride + (my_row - p.ep.offsets_src[r * El]);
+      const int pos = my_row - p.ep.offsets_src[r * El];
+      my_owner = r;
+      my_row = p.ep.direct ? p.ep.rank * p.ep.cap + pos     // slot of the row in the OWNER's receive / output area
+                           : r * stride + pos;
     }
   }
 #pragma unroll
@@ -1070,13 +1091,17 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
     rows[r] = -1;
     ws[r] = 0.f;
     src16[r] = nullptr;
+    srcf[r] = nullptr;
     if (r < k) {
       const uint32_t who = __ballot_sync(0xffffffffu, lane < k && rank == r);
       const int src = __ffs(who) - 1;
       rows[r] = __shfl_sync(0xffffffffu, my_row, src);
       ws[r] = __shfl_sync(0xffffffffu, my_w, src);
-      if (p.ep_collect && rows[r] >= 0)
-        src16[r] = reinterpret_cast<const uint16_t*>(p.ep.back_rows) + (size_t)rows[r] * p.H;
+      const int owner = __shfl_sync(0xffffffffu, my_owner, src);
+      if (p.ep_collect && rows[r] >= 0) {
+        if (p.ep.direct) srcf[r] = p.ep.peer_y[owner] + (size_t)rows[r] * p.H;   // the owner's fp32 outputs, read over NVLink
+        else src16[r] = reinterpret_cast<const uint16_t*>(p.ep.back_rows) + (size_t)rows[r] * p.H;
+      }
     }
   }
   const int H = p.H;
@@ -1096,7 +1121,12 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
         const int r = r0 + q;
         if (r < k) {
           const bool ok = rows[r] >= 0;
-          if (p.ep_collect) {
+          if (p.ep_collect && p.ep.direct) {
+            const float4* src = reinterpret_cast<const float4*>((ok ? srcf[r] : p.ep.local_y) + h);
+            const float4 a = src[0], b = src[1];
+            yk[q][0] = a.x; yk[q][1] = a.y; yk[q][2] = a.z; yk[q][3] = a.w;
+            yk[q][4] = b.x; yk[q][5] = b.y; yk[q][6] = b.z; yk[q][7] = b.w;
+          } else if (p.ep_collect) {
             const uint16_t* sp = ok ? src16[r] : reinterpret_cast<const uint16_t*>(p.ep.back_rows);
             const uint4 v = *reinterpret_cast<const uint4*>(sp + h);
             const uint16_t* vs = reinterpret_cast<const uint16_t*>(&v);

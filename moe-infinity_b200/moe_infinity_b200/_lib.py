@@ -87,6 +87,7 @@ SYMBOLS = [
     ("b2m_ep_p2p_collect", _I, [_VP, _I, _VP]),
     ("b2m_ep_p2p_route", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     ("b2m_ep_p2p_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
+    ("b2m_ep_p2p_layer", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
 ]
 
 _lib = None

@@ -99,6 +99,18 @@ class _EngineOps:
                                        C.c_void_p(out.data_ptr()), self._s()))
         return out
 
+    def p2p_layer(self, layer, x, out, router_logits=None):
+        """The whole expert-parallel layer in one C call (b2m_ep_p2p_layer): five kernels when a rank owns <= 8 experts."""
+        e = self.eng
+        x2 = e._check_x(x)
+        if out is None:
+            out = torch.empty_like(x2)
+        rin, kind, rdt = e._router_args(router_logits, None)
+        e._ck(e.lib.b2m_ep_p2p_layer(e._h, layer, C.c_void_p(x2.data_ptr()),
+                                     C.c_void_p(rin.data_ptr() if rin is not None else 0), kind, rdt, x2.shape[0],
+                                     C.c_void_p(out.data_ptr()), self._s()))
+        return out
+
     def p2p_dispatch(self, T):
         e = self.eng
         e._ck(e.lib.b2m_ep_p2p_dispatch(e._h, T, self._s()))
@@ -152,6 +164,8 @@ class EPMoE:
             raise ValueError(f"EPMoE was sized for T_local={self.T}, got {T}")
         w, r, cap = self.world, self.rank, self.cap
         if self.p2p and T <= 256 and self.fused:
+            if hasattr(self.ops, "p2p_layer"):
+                return self.ops.p2p_layer(layer, x, out, router_logits)   # one C call; 5 kernels (direct mode) or the 7 below
             self.ops.p2p_route(layer, x, router_logits)          # gate/top-k + permute-and-dispatch (2 kernels)
             self.ops.p2p_regroup(self.T_total)
             self.ops.run_experts(layer, self.T_total)
@@ -315,8 +329,9 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                                    f"({el} experts/GPU/layer), decode batch {batch} per GPU (global {world*batch}), "
                                    f"{L} layers, bf16 random-init, all local experts HBM-resident",
                        "global_batch": world * batch, "layers": L, "parallelism": f"ep{world}",
-                       "exchange": ("fused peer-to-peer: dispatch/return kernels store rows into the owners' buffers over NVLink, "
-                                    "st.release.sys/ld.acquire.sys epoch flags, no collective call") if use_p2p else
+                       "exchange": ("fused peer-to-peer, 5 kernels/layer: the permute kernel stores rows + slot tags into the owners' "
+                                    "receive areas over NVLink, the owners' GEMMs read them in place, the sources' combine reads the "
+                                    "owners' fp32 outputs in place; st.release.sys/ld.acquire.sys epoch flags, no collective call") if use_p2p else
                                    "one fixed-capacity all_to_all_single (NCCL) each way; counts ride in the row buffer",
                        "l2": "inputs larger than L2 (each rank streams %.1f GB of weights per step)" % (bytes_rank / 1e9),
                        "timed_region": timed + ", max over ranks"},

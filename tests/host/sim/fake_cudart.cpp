@@ -96,9 +96,22 @@ cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }          // everything "submitted" has already run
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+// CUDA IPC: off by default (the real failure mode of a locked-down container); b2m_sim_enable_ipc(1) turns on an
+// in-process emulation -- a handle is the pointer itself -- so that several "ranks" can live in one test process
+static int g_ipc_on = 0;
+extern "C" void b2m_sim_enable_ipc(int on) { g_ipc_on = on; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  if (!g_ipc_on) return cudaErrorNotSupported;
+  std::memset(h, 0, sizeof *h);
+  std::memcpy(h, &p, sizeof p);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  if (!g_ipc_on) return cudaErrorNotSupported;
+  std::memcpy(p, &h, sizeof *p);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return g_ipc_on ? cudaSuccess : cudaErrorNotSupported; }
 
 cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
   if (std::strcmp(name, "cuTensorMapEncodeTiled") == 0) {

@@ -109,8 +109,8 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
     }
   }
   finish_routing(p);
-  logf("route T=%d offsets_early=%d rows_by_gate=%d ep_dispatch=%d counts=%s", p.T, p.offsets_early, p.rows_by_gate,
-       p.ep_dispatch, ints(p.counts, p.E).c_str());
+  logf("route T=%d offsets_early=%d rows_by_gate=%d ep_dispatch=%d ep_direct=%d counts=%s", p.T, p.offsets_early, p.rows_by_gate,
+       p.ep_dispatch, p.ep_dispatch ? p.ep.direct : 0, ints(p.counts, p.E).c_str());
   return cudaSuccess;
 }
 
@@ -148,10 +148,11 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
 
 static cudaError_t log_gemm(const char* kind, int nt, bool dual, const GemmParams& p) {
   logf("gemm impl=%s nt=%d dual=%d M=%d K=%d ksplit=%d stream_k=%d epi=%d act=%d mimic=%d early_a=%d dual_m=%d bias=%d "
-       "single_n=%d single_slot=%d slot_of=%s offsets=%s",
+       "single_n=%d single_slot=%d ep_rows=%d ep_first=%d ep_el=%d ep_wait=%d ep_zero=%d ep_signal=%d slot_of=%s offsets=%s",
        kind, nt, (int)dual, p.M, p.K, p.ksplit, p.stream_k, p.epi, p.act, p.mimic, p.early_a, p.dual_m,
-       p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.single_n >= 0 ? "[]" : ints(p.slot_of, p.E).c_str(),
-       p.single_n >= 0 ? "[]" : ints(p.offsets, p.E + 1).c_str());
+       p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.ep_rows, p.ep_first, p.ep_el, p.ep_wait, p.ep_zero ? 1 : 0, p.ep_signal,
+       p.single_n >= 0 ? "[]" : ints(p.slot_of, p.E).c_str(),
+       (p.single_n >= 0 || p.ep_rows > 0) ? "[]" : ints(p.offsets, p.E + 1).c_str());
   return cudaSuccess;
 }
 cudaError_t launch_grouped_gemm_tc(int, int nt, bool dual, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
@@ -169,7 +170,8 @@ cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t) {
 int gemm_tc_smem_bytes(int, bool) { return 200 * 1024; }
 
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t) {
-  logf("combine T=%d mode=%d shared=%d ep_collect=%d dtype=%d", p.T, p.mode, p.y_shared ? 1 : 0, p.ep_collect, p.dtype);
+  logf("combine T=%d mode=%d shared=%d ep_collect=%d dtype=%d%s", p.T, p.mode, p.y_shared ? 1 : 0, p.ep_collect, p.dtype,
+       (p.ep_collect && p.ep.direct) ? " ep_direct=1" : "");
   return cudaSuccess;
 }
 cudaError_t launch_cast_rows(const float*, void*, size_t n, int, cudaStream_t) { logf("cast_rows n=%zu", n); return cudaSuccess; }
