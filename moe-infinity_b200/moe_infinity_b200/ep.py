@@ -207,9 +207,17 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     eng = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype,
                     max_tokens=max(world * T, 16), num_slots=L * len(mine), device=local)
     torch.manual_seed(1000 + rank)
+
+    def init_expert(view, l, e):
+        # layer 0 is reproducible on every rank (per-expert generator) so that each rank can rebuild the whole layer for
+        # the bit-equality check against the single-GPU engine below; deeper layers only need realistic values
+        if l == 0:
+            view.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7000 + e))
+        else:
+            view.normal_(0.0, 0.02)
     for l in range(L):
         for e in mine:
-            eng.load_expert(l, e).normal_(0.0, 0.02)
+            init_expert(eng.load_expert(l, e), l, e)
     g = torch.Generator(device=dev).manual_seed(0)           # gates are replicated: same seed on every rank
     for l in range(L):
         eng.set_gate(l, torch.randn(E, H, device=dev, generator=g) * 0.02)
@@ -234,6 +242,33 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     def step():
         for l in range(L):
             ep.forward(l, x_dev[l], out=out_dev[l])
+
+    # ---- parity at full size: this rank's tokens through the expert-parallel layer 0 vs a single-GPU engine that holds all E
+    # experts of layer 0.  Same kernels, same rounding chain, experts combined in expert order; the only freedom is the
+    # order of the split-K fp32 reductions of the down projection (atomics: not even the single-GPU engine repeats itself
+    # bit for bit there, tests/test_gpu_fullsize.py), so: within 1 bf16 ulp everywhere and >= 97 % of the elements identical
+    full0 = MoEEngine(num_layers=1, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype, max_tokens=max(T, 16),
+                      num_slots=E, device=local)
+    for e in range(E):
+        init_expert(full0.load_expert(0, e), 0, e)
+    full0.set_gate(0, eng._gates[0])
+    par = torch.ones(2, device=dev)
+    eps = torch.finfo(dtype).eps
+    for it in range(2):
+        xq = torch.randn(T, H, device=dev, generator=torch.Generator(device=dev).manual_seed(90 + 10 * rank + it)).to(dtype)
+        a = full0.forward(0, xq).float()
+        b = ep.forward(0, xq).float()
+        torch.cuda.synchronize()
+        ok = bool(((a - b).abs() <= eps * a.abs() + eps * a.pow(2).mean().sqrt()).all())
+        frac = float((a == b).float().mean())
+        par[0] = min(float(par[0]), 1.0 if (ok and frac >= 0.97) else 0.0)
+        par[1] = min(float(par[1]), frac)
+    dist.all_reduce(par, op=dist.ReduceOp.MIN)
+    ep_parity = bool(par[0].item() == 1)
+    ep_parity_frac = float(par[1].item())
+    full0.close()
+    del full0
+    torch.cuda.empty_cache()
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -343,7 +378,7 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                     "h2d_bytes_per_step": x_host.numel() * 2 * world, "d2h_bytes_per_step": out_host.numel() * 2 * world,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps * world), "launches_per_step": int(launches_per_step),
-            "clocks": clocks,
+            "clocks": clocks, "ep_parity": ep_parity, "ep_parity_frac_bit_identical": ep_parity_frac,
         }
         print(json.dumps(line), flush=True)
     # teardown: a captured graph holds NCCL work; destroying the process group under it can hang, so drop the graph,
