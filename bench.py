@@ -599,12 +599,12 @@ def run_offload(args):
 
     sampler = ClockSampler(0)
     sampler.start()
-    ref = run(L_.CACHE_REFERENCE, False, "reference (on-demand, evict min incache_visit_count; prefetch off)")
-    ours = run(L_.CACHE_ACTIVATION_AWARE, True, "activation-aware cache + router-logit look-ahead prefetch")
+    ref = run(L_.CACHE_REFERENCE, 0, "reference (on-demand, evict min incache_visit_count; prefetch off)")
+    ours = run(L_.CACHE_ACTIVATION_AWARE, 1, "activation-aware cache + router-logit look-ahead prefetch into idle link time")
     extra = {}
     if args.ablate:
-        extra["activation_aware_no_prefetch"] = run(L_.CACHE_ACTIVATION_AWARE, False, "activation-aware cache, prefetch off")
-        extra["reference_policy_with_lookahead"] = run(L_.CACHE_REFERENCE, True, "reference eviction + look-ahead prefetch")
+        extra["activation_aware_no_prefetch"] = run(L_.CACHE_ACTIVATION_AWARE, 0, "activation-aware cache, prefetch off")
+        extra["activation_aware_prefetch_always"] = run(L_.CACHE_ACTIVATION_AWARE, 2, "activation-aware cache + unconditional look-ahead prefetch")
     clocks = sampler.stop()
     line = {
         "metric": METRIC, "value": ours["tokens_per_s"], "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warm,

@@ -101,12 +101,13 @@ typedef struct b2m_config {
   int32_t h2d_chunk_bytes;  /* H2D copy granularity in bytes (0 = whole expert in one cudaMemcpyAsync) */
   int32_t gemm_impl;        /* 0 = tcgen05 (product); 1 = CUDA-core cross-check kernel (bring-up only) */
   int32_t cache_policy;     /* B2M_CACHE_* : on-demand budget accounting */
-  int32_t lookahead_prefetch; /* 1 (offload mode, T <= 256): every routing call also applies the NEXT layer's router weight
+  int32_t lookahead_prefetch; /* 1 | 2 (offload mode, T <= 256): every routing call also applies the NEXT layer's router weight
                                (b2m_set_gate) to this layer's input and reads the predicted expert counts back with this
                                layer's own counts (same synchronisation); predicted experts that are not resident are staged
                                on the prefetch stream while this layer computes -- the router-logit driven prefetch of the
                                north star; replaces expert_predictor.predict + prefetch_experts (expert_prefetcher.py:42-59)
-                               for callers that do not supply their own hints */
+                               for callers that do not supply their own hints.  1 = only from layers that staged nothing
+                               on demand (the link is idle); 2 = always (costs bandwidth when the link is saturated) */
   float freq_alpha;         /* B2M_CACHE_ACTIVATION_AWARE: weight of the newest step in the activation average (0 = 0.25) */
 } b2m_config;
 

@@ -1052,6 +1052,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
       return fail(c, B2M_ESTATE, "expert (%d,%d) was never registered", id / E, id % E);
   std::vector<int> remaining = active, wave;
   int waves = 0;
+  int demand_copies = 0;   // experts this call had to stage on demand
   while (!remaining.empty()) {
     wave.clear();
     for (int id : remaining) {
@@ -1064,6 +1065,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
         const int slot = on_demand ? acquire_slot_on_demand(c, remaining) : acquire_slot(c, remaining, false);
         if (slot < 0) continue;                               // no room in this wave: stays in `remaining`
         if (on_demand) c->stats.misses++;
+        ++demand_copies;
         r = issue_copy(c, id, slot, c->fetch_stream, true);
         if (r) return r;
       } else if (on_demand) {
@@ -1118,7 +1120,12 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
                     remaining.end());
   }
   c->last_active = wave;   // experts of the last wave are still being read by kernels in flight
-  if (on_demand && c->last_look_valid) {
+  // Measured on a B200 (profiles/r02_offload_config3.json): when the host->device link is saturated by on-demand copies a
+  // prefetch cannot save time, only bytes -- and a wrong prediction costs a whole expert (6.4 ms for Mixtral): with ~80 %
+  // accurate predictions unconditional prefetching LOST 12 % against the same cache without it.  So (lookahead_prefetch = 1)
+  // predictions are staged only from layers that staged nothing on demand, i.e. into link time that is otherwise idle;
+  // lookahead_prefetch = 2 prefetches unconditionally (sparse-miss regimes, ablations).
+  if (on_demand && c->last_look_valid && (demand_copies == 0 || c->cfg.lookahead_prefetch >= 2)) {
     // stage the next layer's predicted experts while this layer computes: most-wanted first; a prediction only displaces
     // an expert whose own next use is expected at least a few layer visits later than the next layer
     const int nxt = (layer + 1) % c->cfg.num_layers;

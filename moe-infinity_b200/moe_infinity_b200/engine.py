@@ -76,7 +76,7 @@ class MoEEngine:
         cfg.h2d_chunk_bytes = h2d_chunk_bytes
         cfg.gemm_impl = gemm_impl
         cfg.cache_policy = cache_policy
-        cfg.lookahead_prefetch = int(bool(lookahead_prefetch))
+        cfg.lookahead_prefetch = int(lookahead_prefetch)
         cfg.freq_alpha = freq_alpha
         self.cfg = cfg
         self.max_tokens = max_tokens

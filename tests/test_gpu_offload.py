@@ -221,7 +221,7 @@ def test_activation_aware_cache_with_lookahead_prefetch(lib_built):
     experts, gates = _model(11)
     nslots = 14
     full = _engine(experts, gates, L * E)
-    eng = _engine(experts, gates, nslots, cache_policy=Lb.CACHE_ACTIVATION_AWARE, lookahead_prefetch=True, max_inflight_prefetch=4)
+    eng = _engine(experts, gates, nslots, cache_policy=Lb.CACHE_ACTIVATION_AWARE, lookahead_prefetch=2, max_inflight_prefetch=4)
     plain = _engine(experts, gates, nslots, cache_policy=Lb.CACHE_ACTIVATION_AWARE)      # same policy, no prefetch: oracle-checkable
     orc = CacheOracle(L, E, nslots, policy="activation_aware")
     g = torch.Generator().manual_seed(2)

@@ -218,7 +218,7 @@ def test_lookahead_prefetch_stages_next_layers_experts_on_cpu(sim):
     predicted experts come back with the counts (no extra synchronisation), are protected from eviction and staged on the
     prefetch stream; a correctly predicted expert is a hit (prefetch_useful) when its layer runs."""
     Ln, E, H = 3, 8, 128
-    c = Ctx(sim, L_=Ln, E=E, H=H, num_slots=20, cache_policy=L.CACHE_ACTIVATION_AWARE, lookahead_prefetch=1,
+    c = Ctx(sim, L_=Ln, E=E, H=H, num_slots=20, cache_policy=L.CACHE_ACTIVATION_AWARE, lookahead_prefetch=2,
             max_inflight_prefetch=16)
     assert c.rc == 0, c.err()
     c.register_all(3)
