@@ -1,10 +1,8 @@
 #!/bin/bash
-# session 3: look-ahead/activation-aware GPU test, reference engine under forced offload (sequential protocol), config 3 small then full
+# session 4 (2 GPUs): expert-parallel parity test, then the N=2 bench with the five-kernel layer and with the seven-kernel one
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_offload.py -m gpu -q --timeout 300 > gpurun_out/s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s_pytest.log
-timeout 900 python tools/ref_engine_harness.py --mode timing --layers 4 --budget-experts 15 --steps 4 --warmup 1 --compare 0 --protocol sequential --out gpurun_out/ref_timing_offload.json > gpurun_out/s_timing_off.log 2>&1; echo "rc=$?" >> gpurun_out/s_timing_off.log
-timeout 600 python bench.py --config offload --layers 8 --steps 6 --warmup 2 --prefill 2048 --ablate > gpurun_out/s_offload_small.log 2>&1; echo "rc=$?" >> gpurun_out/s_offload_small.log
-if tail -2 gpurun_out/s_offload_small.log | grep -q '"same_outputs": true'; then
-  timeout 1500 python bench.py --config offload --steps 32 --warmup 4 --ablate > gpurun_out/s_offload_full.log 2>&1; echo "rc=$?" >> gpurun_out/s_offload_full.log
-fi
-tail -4 gpurun_out/s_pytest.log; tail -2 gpurun_out/s_timing_off.log | cut -c1-900; tail -2 gpurun_out/s_offload_small.log | cut -c1-3000; tail -2 gpurun_out/s_offload_full.log | cut -c1-3000
+timeout -k 10 400 python -m pytest tests/test_gpu_ep.py -m gpu -q --timeout 380 > gpurun_out/s_pytest_ep.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s_pytest_ep.log
+tail -30 gpurun_out/s_pytest_ep.log
+timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/s_ep2_direct.log 2>&1; echo "rc=$?" >> gpurun_out/s_ep2_direct.log
+B2M_EP_DIRECT=0 timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/s_ep2_v1.log 2>&1; echo "rc=$?" >> gpurun_out/s_ep2_v1.log
+tail -3 gpurun_out/s_ep2_direct.log | cut -c1-1500; tail -3 gpurun_out/s_ep2_v1.log | cut -c1-1500
