@@ -270,6 +270,12 @@ int b2m_ep_p2p_combine(b2m_ctx* ctx, int layer, const void* x, int T_local, void
 int b2m_ep_p2p_layer(b2m_ctx* ctx, int layer, const void* x, const void* router_in, int router_in_kind,
                      int router_in_dtype, int T_local, void* out, void* stream);
 
+/* diagnostics (B2M_TIMELINE=1 in the environment): device-side nanosecond timestamps of the kernels of b2m_ep_p2p_layer's
+ * direct mode, 16 words per layer: [0,1] gate/top-k first start / last end, [2,3] permute+dispatch, [4,5,6] gate/up GEMM
+ * start / peers' flags seen / end, [8,10] down GEMM start / end (after "done" is published), [12,13,14] combine start /
+ * owners' flags seen / end.  Synchronises the device. */
+int b2m_timeline_read(b2m_ctx* ctx, unsigned long long* host_out, int n_layers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,8 @@ struct b2m_ctx {
 
   int cur_ksplit = 1, cur_nt = 16, cur_nt_dn = 16, cur_T = 0;   // token-tile widths of the up (K3) and down (K4) GEMMs
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
+  unsigned long long* tl_next = nullptr;   // timeline slots of the layer call in progress
+  unsigned long long* d_tl = nullptr;   // B2M_TIMELINE=1: [L][16] device timestamps of the expert-parallel layer's kernels
   bool ep_direct_next = false;   // the routing / combine call in progress belongs to b2m_ep_p2p_layer's direct mode
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
@@ -692,7 +694,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_look, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_look, c->d_tl, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
@@ -871,6 +873,7 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   if (ep_dispatch) {
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;
+    p.tl = c->tl_next;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
@@ -1218,6 +1221,7 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   if (ep_collect) {
     p.ep_collect = 1;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
+    if (c->tl_next) p.tl = c->tl_next + 12;
   }
   CK(c, launch_combine(p, st));
   c->stats.kernel_launches += 1;
@@ -1605,10 +1609,25 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
     if (!r) r = b2m_ep_p2p_combine(c, layer, x, T_local, out, stream);
     return r;
   }
+  static const bool timeline = getenv("B2M_TIMELINE") && getenv("B2M_TIMELINE")[0] == '1';
+  unsigned long long* tl = nullptr;
+  if (timeline) {
+    if (!c->d_tl) {
+      // [L][16] slots + one more row holding the reset pattern (device-to-device copies are capturable in a CUDA graph);
+      // starts are atomicMin'ed (-> all ones), ends atomicMax'ed (-> zero): slots 0, 2, 4, 8, 12 are starts
+      CK(c, cudaMalloc((void**)&c->d_tl, sizeof(unsigned long long) * 16 * (f.num_layers + 1)));
+      CK(c, cudaMemset(c->d_tl, 0, sizeof(unsigned long long) * 16 * (f.num_layers + 1)));
+      static const unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, 0, 0, ~0ull, 0, 0, 0, ~0ull, 0, 0, 0};
+      CK(c, cudaMemcpy(c->d_tl + (size_t)16 * f.num_layers, init, sizeof init, cudaMemcpyHostToDevice));
+    }
+    tl = c->d_tl + (size_t)layer * 16;
+    CK(c, cudaMemcpyAsync(tl, c->d_tl + (size_t)16 * f.num_layers, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+  }
+  c->tl_next = tl;
   c->ep_direct_next = true;
   r = route_impl(c, layer, x, router_in, kind, in_dtype, T_local, 0, stream, true);
   c->ep_direct_next = false;
-  if (r) return r;
+  if (r) { c->tl_next = nullptr; return r; }
   c->ep_mode = true;
   c->ep_inline = 0;
   for (int e = q.rank * El; e < (q.rank + 1) * El; ++e) {
@@ -1669,6 +1688,7 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
     dn.mimic = up.mimic;
   }
   const int ni = nt_index(nt);
+  if (tl) { up.tl = tl + 4; dn.tl = tl + 8; }
   CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, c->num_sms, st));
   CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, c->tm_hmid[ni], dn, c->num_sms, st));
   c->stats.kernel_launches += 2;
@@ -1676,7 +1696,17 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   c->ep_direct_next = true;
   r = combine_impl(c, layer, x, T_local, out, stream, true);
   c->ep_direct_next = false;
+  c->tl_next = nullptr;
   return r;
+}
+
+int b2m_timeline_read(b2m_ctx* c, unsigned long long* host_out, int n_layers) {
+  if (!c || !host_out) return B2M_EINVAL;
+  if (!c->d_tl) return fail(c, B2M_ESTATE, "no timeline recorded (B2M_TIMELINE=1 and b2m_ep_p2p_layer)");
+  if (n_layers < 1 || n_layers > c->cfg.num_layers) return fail(c, B2M_EINVAL, "n_layers out of range");
+  CK(c, cudaDeviceSynchronize());
+  CK(c, cudaMemcpy(host_out, c->d_tl, sizeof(unsigned long long) * 16 * n_layers, cudaMemcpyDeviceToHost));
+  return B2M_OK;
 }
 
 int b2m_ep_p2p_regroup(b2m_ctx* c, int T_total, void* stream) {

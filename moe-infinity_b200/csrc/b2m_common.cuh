@@ -36,6 +36,15 @@ template <int DT> __device__ __forceinline__ float round_dt(float f) { return Ha
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// device timeline (B2M_TIMELINE=1): nanosecond timestamps written by the kernels themselves, readable after a graph replay
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_min(unsigned long long* slot) { if (slot) atomicMin(slot, global_ns()); }
+__device__ __forceinline__ void tl_max(unsigned long long* slot) { if (slot) atomicMax(slot, global_ns()); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -70,6 +70,7 @@ struct GemmParams {
   int* ep_done_epoch;        // local epoch word of the return direction
   int* ep_peer_done_flag[16];  // peer r's done_flag[nranks] (this rank writes entry [rank])
   int ep_rank;
+  unsigned long long* tl;    // optional timeline slots of this launch: [0] first CTA start, [1] peers' flags seen, [2] last CTA end (ns)
 };
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
@@ -161,6 +162,7 @@ struct RouteParams {
                              // start fetching weights while the permute kernel is still gathering rows)
   int ep_dispatch;           // 1 (T <= 256 only): gathered rows go straight to the owning ranks' buffers (ep)
   EpParams ep;
+  unsigned long long* tl;    // optional timeline slots: [0] gate/top-k start, [1] its end, [2] permute start, [3] permute end
 };
 cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
 // look-ahead: top-k of the NEXT layer's router (p.gate_w = its weight) on this layer's input p.x -> counts_out[E] += 1 per
@@ -181,6 +183,7 @@ struct CombineParams {
   int T, H, k, dtype, mode;
   int ep_collect;          // 1: expert outputs are read from the peer-written return area (model dtype rows)
   EpParams ep;
+  unsigned long long* tl;  // optional timeline slots: [0] start, [1] owners' flags seen, [2] end
 };
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
 cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t st);

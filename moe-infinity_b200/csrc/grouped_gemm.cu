@@ -110,6 +110,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int m_tiles = (p.M + m_step - 1) / m_step;
 
   // ---- one-time setup -------------------------------------------------------------
+  if (p.tl && threadIdx.x == 0) tl_min(p.tl);
   pdl_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -214,7 +215,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             pend_stage[npend] = stage; pend_kb[npend] = kb; pend_row[npend] = t.row0;
             if (++npend == Cfg::STAGES) {
               if (p.early_a) pdl_wait();
-              if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); }
+              if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); if (p.tl) tl_max(p.tl + 1); }
               for (int i = 0; i < npend; ++i)
                 tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                             pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -379,6 +380,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (p.ep_signal) __threadfence_system();   // this thread's output stores / reductions before the grid-wide "done" below
   tc_fence_before();
   __syncthreads();
+  if (p.tl && threadIdx.x == 0) tl_max(p.tl + 2);
   if (p.ep_signal && threadIdx.x == 0) {
     // last CTA of the grid: every output of this rank for this layer is in memory -> tell the source ranks, whose combine
     // kernels read the rows in place over NVLink

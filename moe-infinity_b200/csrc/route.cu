@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   const int t = blockIdx.x;
   pdl_launch();
   pdl_wait();
+  if (p.tl && threadIdx.x == 0) tl_min(p.tl);
   bool scores_in = false;
   if (p.logits) {
     for (int e = threadIdx.x; e < p.E; e += RT_THREADS) s_logits[e] = load_as_float(p.logits, (size_t)t * p.E + e, p.logits_dtype);
@@ -709,6 +710,7 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
       }
     }
     route_token_warp(p, t, s_logits, scores_in, s_scr, p.topk_idx + (size_t)t * p.k, p.topk_w + (size_t)t * p.k);
+    if (p.tl && lane == 0) tl_max(p.tl + 1);
   }
   if (!p.offsets_early) return;
   // ---- the last CTA to finish publishes counts[E] / offsets[E+1] for the whole batch: the grouped GEMM only needs these
@@ -784,6 +786,7 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
   const int npairs = p.T * p.k;
   pdl_launch();
   pdl_wait();
+  if (p.tl && threadIdx.x == 0) tl_min(p.tl + 2);
   if (p.rows_by_gate) {
     // the gate/top-k kernel already published counts, offsets and the row maps: this kernel is a pure row copy
     const size_t rb = row_bytes(p);
@@ -922,6 +925,7 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
     for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
   }
   if (p.ep_dispatch && p.ep.p2p) p2p_signal(p.ep, 0);
+  if (p.tl && threadIdx.x == 0) tl_max(p.tl + 3);
   if (p.y_zero) {
     float4* z = reinterpret_cast<float4*>(p.y_zero);
     const size_t n4 = p.y_zero_elems / 4;
@@ -1054,6 +1058,7 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   const int k = p.k;
   pdl_launch();
   pdl_wait();
+  if (p.tl && threadIdx.x == 0) tl_min(p.tl);
   // each warp loads the token's routing list into lanes 0..k-1 and sorts it by expert id via shuffles
   int my_e = 0x7fffffff, my_row = -1;
   float my_w = 0.f;
@@ -1075,6 +1080,7 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   int my_owner = 0;
   if (p.ep_collect) {
     if (p.ep.p2p) p2p_wait(p.ep, 1);     // return rows of every owner rank have landed (direct mode: the owners' GEMMs are done)
+    if (p.tl && threadIdx.x == 0) tl_max(p.tl + 1);
     if (lane < k && my_row >= 0) {
       // permuted row -> (owner rank, position in that rank's segment of this rank's return area)
       const int El = p.ep.E / p.ep.nranks;
@@ -1193,6 +1199,7 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
     for (int i = 0; i < 8; ++i) os[i] = Half16<DT>::from_f(acc[i]);
     *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)t * H + h) = o;
   }
+  if (p.tl && threadIdx.x == 0) tl_max(p.tl + 2);
 }
 
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t st) {

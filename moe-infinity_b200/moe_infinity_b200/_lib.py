@@ -88,6 +88,7 @@ SYMBOLS = [
     ("b2m_ep_p2p_route", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     ("b2m_ep_p2p_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
     ("b2m_ep_p2p_layer", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    ("b2m_timeline_read", _I, [_VP, C.POINTER(C.c_uint64), _I]),
 ]
 
 _lib = None

@@ -325,6 +325,23 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     p50 = sorted(a.elapsed_time(b) for a, b in step_ms)[len(step_ms) // 2]
     clocks = sampler.stop() if rank == 0 else None
 
+    timeline = None
+    if os.environ.get("B2M_TIMELINE") == "1" and use_p2p:
+        # device timestamps of the last replayed step: per layer, microseconds relative to the layer's first kernel
+        buf = (C.c_uint64 * (16 * L))()
+        try:
+            eng._ck(eng.lib.b2m_timeline_read(eng._h, buf, L))
+            rows = []
+            for l in range(L):
+                v = [int(buf[16 * l + i]) for i in range(16)]
+                t0 = v[0]
+                names = {"gate_end": 1, "permute_start": 2, "permute_end": 3, "k3_start": 4, "k3_flags": 5, "k3_end": 6,
+                         "k4_start": 8, "k4_end": 10, "combine_start": 12, "combine_flags": 13, "combine_end": 14}
+                rows.append({n: round((v[i] - t0) / 1e3, 2) for n, i in names.items()})
+                rows[-1]["t0_ns"] = t0
+            timeline = rows
+        except Exception as ex:  # pragma: no cover
+            timeline = f"unavailable: {ex}"
     # e2e: host buffers, copies inside the timed region
     x_host = x_dev.cpu().pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
@@ -349,6 +366,8 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     dist.all_reduce(wall, op=dist.ReduceOp.MAX)
     e2e_ms = float(wall.item()) * 1e3
 
+    gathered = [None] * world
+    dist.all_gather_object(gathered, timeline)
     if rank == 0:
         peak, peak_src = load_peaks()
         ms_per_step = total_ms / args.steps
@@ -379,6 +398,7 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps * world), "launches_per_step": int(launches_per_step),
             "clocks": clocks, "ep_parity": ep_parity, "ep_parity_frac_bit_identical": ep_parity_frac,
+            "timeline_us": gathered if any(g is not None for g in gathered) else None,
         }
         print(json.dumps(line), flush=True)
     # teardown: a captured graph holds NCCL work; destroying the process group under it can hang, so drop the graph,
