@@ -644,8 +644,8 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_offsets, sizeof(int) * (E + 1)));
   CKC(cudaMemset(c->d_offsets, 0, sizeof(int) * (E + 1)));
   CKC(cudaMalloc((void**)&c->d_offsets_src, sizeof(int) * (E + 1)));
-  CKC(cudaMalloc((void**)&c->d_ticket, sizeof(int)));
-  CKC(cudaMemset(c->d_ticket, 0, sizeof(int)));
+  CKC(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(int)));       // [0] CTA arrival counter, [1] "row maps published" word (ep_fused)
+  CKC(cudaMemset(c->d_ticket, 0, 2 * sizeof(int)));
   CKC(cudaMalloc((void**)&c->d_err, sizeof(int)));
   CKC(cudaMemset(c->d_err, 0, sizeof(int)));
   CKC(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
@@ -874,11 +874,18 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;
     p.tl = c->tl_next;
+    static const bool fuse_on = !(getenv("B2M_EP_FUSE_ROUTE") && getenv("B2M_EP_FUSE_ROUTE")[0] == '0');
+    if (c->ep_direct_next && fuse_on && T <= c->num_sms && c->cfg.router != B2M_ROUTER_SWITCH_TOP1) {
+      p.ep_fused = 1;            // one launch: gate/top-k + rank + permute + dispatch (every CTA of the grid is resident)
+      p.offsets_early = 1;
+      p.rows_by_gate = 1;
+      p.ready = c->d_ticket + 1;
+    }
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
   CK(c, launch_route(p, st));
-  c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0);
+  c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0) - (p.ep_fused ? 1 : 0);
   c->last_counts_valid = false;
   // router-logit driven prefetch: the next layer's router applied to THIS layer's input predicts which experts the next
   // layer will want; the counts ride back with this layer's own counts (b2m_run_experts reads both in one synchronisation)
@@ -1689,7 +1696,13 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   }
   const int ni = nt_index(nt);
   if (tl) { up.tl = tl + 4; dn.tl = tl + 8; }
-  CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, c->num_sms, st));
+  // The tile list is static here, so the grid can be sized to it: with 448 tiles (4 experts x 112) on 148 CTAs the last 4
+  // tiles run alone and are limited by what one SM can ingest (~120 GB/s; measured 17 us of a 162 us kernel,
+  // profiles/r02_ep2_timeline_before.log); 112 CTAs x 4 tiles each finish together at the full HBM rate.
+  const int up_tiles = El * ((s.I + 127) / 128);
+  const int up_rounds = (up_tiles + c->num_sms - 1) / c->num_sms;
+  const int up_grid = std::max(1, std::min(c->num_sms, (up_tiles + up_rounds - 1) / up_rounds));
+  CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
   CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, c->tm_hmid[ni], dn, c->num_sms, st));
   c->stats.kernel_launches += 2;
   // ---- combine at the source: wait for the owners' "done", read their outputs in place

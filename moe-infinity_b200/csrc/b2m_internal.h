@@ -160,6 +160,8 @@ struct RouteParams {
                              // kernel only copies rows (no redundant ranking in each of its CTAs)
   int offsets_early;         // small-T path: the last gate/top-k CTA already publishes counts/offsets (so the gate/up GEMM can
                              // start fetching weights while the permute kernel is still gathering rows)
+  int ep_fused;              // ep_dispatch in direct mode with T <= #SMs: the gate/top-k kernel also permutes + dispatches (one launch)
+  int* ready;                // ep_fused: word the last gate/top-k CTA releases (value = local dispatch epoch + 1) once the row maps are out
   int ep_dispatch;           // 1 (T <= 256 only): gathered rows go straight to the owning ranks' buffers (ep)
   EpParams ep;
   unsigned long long* tl;    // optional timeline slots: [0] gate/top-k start, [1] its end, [2] permute start, [3] permute end

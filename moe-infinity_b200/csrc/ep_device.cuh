@@ -16,9 +16,11 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 // Every CTA calls this after its last store to peer memory; the last CTA to arrive publishes epoch to all peers.
 __device__ __forceinline__ void p2p_signal(const EpParams& p, int which /*0 dispatch, 1 return*/) {
   __shared__ int s_last;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(p.done_ctr + which, 1) == (int)gridDim.x - 1);
+  __syncthreads();                 // every thread's peer stores are ordered before thread 0's fence (CTA-scope barrier) ...
+  if (threadIdx.x == 0) {
+    __threadfence_system();        // ... which makes them visible system-wide (fences are cumulative): one fence per CTA, not per thread
+    s_last = (atomicAdd(p.done_ctr + which, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();

@@ -716,63 +716,118 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   // ---- the last CTA to finish publishes counts[E] / offsets[E+1] for the whole batch: the grouped GEMM only needs these
   // (not the gathered rows) to start streaming weights, so it can overlap the permute kernel
   __shared__ int s_last;
+  __shared__ int s_want;
   __shared__ int s_idx2[FUSED_MAX_T * MAX_K];
   __shared__ int s_cnt2[RT_WARPS][MAX_PL * 32];
   __shared__ int s_tot2[MAX_PL * 32];
+  __shared__ int s_off2[MAX_PL * 32 + 1];
+  // ep_fused (expert parallel, direct mode, T <= #SMs so that every CTA of this grid is resident): this kernel is also the
+  // permute + dispatch kernel -- once the last CTA has published the row maps every CTA stores its own token's rows into the
+  // owners' receive areas and the grid signals the peers.  One launch and one redundant ranking pass less per layer.
+  const bool fuse = p.ep_fused != 0;
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (fuse) s_want = *reinterpret_cast<volatile int*>(p.ep.epoch) + 1;   // epoch[0] moves only after every CTA has arrived in p2p_signal
     __threadfence();
     s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
+  if (!s_last && !fuse) return;
   const int npairs = p.T * p.k;
-  const int nchunks = (p.T + CHUNK - 1) / CHUNK;
-  for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx2[i] = __ldcg(p.topk_idx + i);   // other CTAs' results: L2
-  __syncthreads();
-  for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS)   // (chunk, expert subset) tasks over all warps
-    chunk_count_strided(s_idx2, (task / RT_WARPS) * CHUNK, p.T, p.k, p.E, s_cnt2[task / RT_WARPS], task % RT_WARPS, RT_WARPS);
-  __syncthreads();
-  if (threadIdx.x < p.E) {
-    int run = 0;
-    for (int c = 0; c < nchunks; ++c) { const int v = s_cnt2[c][threadIdx.x]; s_cnt2[c][threadIdx.x] = run; run += v; }   // -> exclusive chunk bases
-    s_tot2[threadIdx.x] = run;
-    p.counts[threadIdx.x] = run;
-  }
-  __shared__ int s_off2[MAX_PL * 32 + 1];
-  __syncthreads();
-  if (warp == 0) {
-    int v[MAX_PL], run = 0;
-#pragma unroll
-    for (int i = 0; i < MAX_PL; ++i) {
-      const int e = lane * MAX_PL + i;
-      v[i] = e < p.E ? s_tot2[e] : 0;
-      run += v[i];
+  if (s_last) {
+    __threadfence();
+    const int nchunks = (p.T + CHUNK - 1) / CHUNK;
+    for (int i = threadIdx.x; i < npairs; i += RT_THREADS) s_idx2[i] = __ldcg(p.topk_idx + i);   // other CTAs' results: L2
+    __syncthreads();
+    for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS)   // (chunk, expert subset) tasks over all warps
+      chunk_count_strided(s_idx2, (task / RT_WARPS) * CHUNK, p.T, p.k, p.E, s_cnt2[task / RT_WARPS], task % RT_WARPS, RT_WARPS);
+    __syncthreads();
+    if (threadIdx.x < p.E) {
+      int run = 0;
+      for (int c = 0; c < nchunks; ++c) { const int v = s_cnt2[c][threadIdx.x]; s_cnt2[c][threadIdx.x] = run; run += v; }   // -> exclusive chunk bases
+      s_tot2[threadIdx.x] = run;
+      p.counts[threadIdx.x] = run;
     }
-    int incl = run;
+    __syncthreads();
+    if (warp == 0) {
+      int v[MAX_PL], run = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    int base = incl - run;
+      for (int i = 0; i < MAX_PL; ++i) {
+        const int e = lane * MAX_PL + i;
+        v[i] = e < p.E ? s_tot2[e] : 0;
+        run += v[i];
+      }
+      int incl = run;
 #pragma unroll
-    for (int i = 0; i < MAX_PL; ++i) {
-      const int e = lane * MAX_PL + i;
-      if (e < p.E) { p.offsets[e] = base; s_off2[e] = base; }
-      base += v[i];
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      int base = incl - run;
+#pragma unroll
+      for (int i = 0; i < MAX_PL; ++i) {
+        const int e = lane * MAX_PL + i;
+        if (e < p.E) { p.offsets[e] = base; s_off2[e] = base; }
+        base += v[i];
+      }
+      if (lane == 31) { p.offsets[p.E] = incl; s_off2[p.E] = incl; }
+      if (lane == 0) *p.ticket = 0;
     }
-    if (lane == 31) { p.offsets[p.E] = incl; s_off2[p.E] = incl; }
-    if (lane == 0) *p.ticket = 0;
+    if (p.rows_by_gate) {
+      // publish the row maps as well (stable ascending-token order inside each expert): the permute kernel then only copies
+      __syncthreads();
+      for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS) {
+        const int* cb = s_cnt2[task / RT_WARPS];
+        chunk_rank_strided(p, (task / RT_WARPS) * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, s_idx2, task % RT_WARPS, RT_WARPS);
+      }
+    }
+    if (fuse) {
+      __syncthreads();
+      const int El = p.E / p.ep.nranks;
+      for (int e = threadIdx.x; e <= p.E; e += RT_THREADS) p.ep.offsets_src[e] = s_off2[e];
+      // one tag per receive slot of this rank's segment at every owner: local expert index of the row stored there, or -1
+      for (int i = threadIdx.x; i < p.ep.nranks * p.ep.cap; i += RT_THREADS) {
+        const int r = i / p.ep.cap, pos = i - r * p.ep.cap;
+        const int row = s_off2[r * El] + pos;
+        int tag = -1;
+        if (row < s_off2[(r + 1) * El]) {
+          int e = r * El;
+          while (row >= s_off2[e + 1]) ++e;
+          tag = e - r * El;
+        }
+        p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = tag;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.ready), "r"(s_want) : "memory");
+    }
   }
-  if (!p.rows_by_gate) return;
-  // publish the row maps as well (stable ascending-token order inside each expert): the permute kernel then only copies
+  if (!fuse) return;
+  // ---- every CTA: wait for the row maps, then store this token's rows into the owners' receive areas (NVLink stores)
+  if (threadIdx.x == 0) {
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ready) : "memory");
+      if (v != s_want) __nanosleep(20);
+    } while (v != s_want);
+  }
   __syncthreads();
-  for (int task = warp; task < nchunks * RT_WARPS; task += RT_WARPS) {
-    const int* cb = s_cnt2[task / RT_WARPS];
-    chunk_rank_strided(p, (task / RT_WARPS) * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, s_idx2, task % RT_WARPS, RT_WARPS);
+  {
+    const int El = p.E / p.ep.nranks;
+    const int vec_per_row = p.H / 8;
+    for (int j = 0; j < p.k; ++j) {
+      const int row = __ldcg(p.row_of + (size_t)t * p.k + j);
+      const int e = __ldcg(p.topk_idx + (size_t)t * p.k + j);
+      if (row < 0 || e < 0) continue;
+      const int r = e / El;
+      const int pos = row - __ldcg(p.ep.offsets_src + r * El);
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
+      uint4* dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, r, pos));
+      for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
+    }
   }
+  p2p_signal(p.ep, 0);
+  if (p.tl && threadIdx.x == 0) tl_max(p.tl + 3);
 }
 
 __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RouteParams p) {
@@ -989,7 +1044,7 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
     cudaError_t e = launch_pdl(gate_topk_small_kernel, dim3(p.T), dim3(RT_THREADS), 0, st, p);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || p.ep_fused) return e;      // ep_fused: that kernel also permuted and dispatched the rows
     return launch_pdl(permute_small_kernel, dim3(small_permute_grid(p)), dim3(RT_THREADS), 0, st, p);
   }
   const int nblocks = (p.T + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;

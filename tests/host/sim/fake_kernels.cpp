@@ -146,17 +146,17 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
   return cudaSuccess;
 }
 
-static cudaError_t log_gemm(const char* kind, int nt, bool dual, const GemmParams& p) {
-  logf("gemm impl=%s nt=%d dual=%d M=%d K=%d ksplit=%d stream_k=%d epi=%d act=%d mimic=%d early_a=%d dual_m=%d bias=%d "
+static cudaError_t log_gemm(const char* kind, int nt, bool dual, const GemmParams& p, int grid = -1) {
+  logf("gemm impl=%s grid=%d nt=%d dual=%d M=%d K=%d ksplit=%d stream_k=%d epi=%d act=%d mimic=%d early_a=%d dual_m=%d bias=%d "
        "single_n=%d single_slot=%d ep_rows=%d ep_first=%d ep_el=%d ep_wait=%d ep_zero=%d ep_signal=%d slot_of=%s offsets=%s",
-       kind, nt, (int)dual, p.M, p.K, p.ksplit, p.stream_k, p.epi, p.act, p.mimic, p.early_a, p.dual_m,
+       kind, grid, nt, (int)dual, p.M, p.K, p.ksplit, p.stream_k, p.epi, p.act, p.mimic, p.early_a, p.dual_m,
        p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.ep_rows, p.ep_first, p.ep_el, p.ep_wait, p.ep_zero ? 1 : 0, p.ep_signal,
        p.single_n >= 0 ? "[]" : ints(p.slot_of, p.E).c_str(),
        (p.single_n >= 0 || p.ep_rows > 0) ? "[]" : ints(p.offsets, p.E + 1).c_str());
   return cudaSuccess;
 }
 cudaError_t launch_grouped_gemm_tc(int, int nt, bool dual, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
-                                   const GemmParams& p, int, cudaStream_t) { return log_gemm("tc", nt, dual, p); }
+                                   const GemmParams& p, int grid, cudaStream_t) { return log_gemm("tc", nt, dual, p, grid); }
 cudaError_t launch_grouped_gemm_tc_mc2(int, bool dual, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
                                        const GemmParams& p, int, cudaStream_t) { return log_gemm("tc_mc2", 128, dual, p); }
 cudaError_t launch_grouped_gemm_simt(int, const void*, size_t, size_t, size_t, const void*, int, const GemmParams& p,

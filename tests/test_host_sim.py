@@ -651,6 +651,7 @@ def test_expert_parallel_direct_layer_on_cpu(sim):
             assert up["ep_rows"] == dn["ep_rows"] == str(R) and up["ep_first"] == str(rank * 4) and up["ep_el"] == "4"
             assert (up["ep_wait"], up["ep_signal"], dn["ep_wait"], dn["ep_signal"]) == ("1", "0", "0", "1")
             assert up["nt"] == dn["nt"] == "32" and up["dual"] == "1" and dn["epi"] == "1"
+            assert up["grid"] == "4" and dn["grid"] == "148"      # 4 experts x 1 weight-row tile: the gate/up grid is sized to its static tile list
             assert (dn["ksplit"] == "1") == (up["ep_zero"] == "0")          # the accumulator is cleared iff the down GEMM splits K
             assert "ep_direct=1" in lines[3] and _kv(lines[3])["ep_collect"] == "1"
             assert sim.b2m_ep_p2p_layer(c.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T + 1, out.ctypes.data, None) != 0
