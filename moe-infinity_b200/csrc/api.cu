@@ -142,6 +142,7 @@ struct b2m_ctx {
   unsigned long long* tl_next = nullptr;   // timeline slots of the layer call in progress
   unsigned long long* d_tl = nullptr;   // B2M_TIMELINE=1: [L][16] device timestamps of the expert-parallel layer's kernels
   bool ep_direct_next = false;   // the routing / combine call in progress belongs to b2m_ep_p2p_layer's direct mode
+  bool ep_fused_last = false;    // ... and its routing call used the fused dispatch (slots claimed with atomics, epoch tags)
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
   struct P2P {
@@ -149,7 +150,7 @@ struct b2m_ctx {
     uint8_t* base = nullptr;            // own allocation: [recv area][back area][flags]
     size_t area_bytes = 0;
     uint8_t* peer_base[16] = {nullptr};
-    int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters
+    int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters, [4..19] slot counters of the fused dispatch
     size_t tags_off = 0, y_off = 0;     // direct mode regions inside the allocation: tags[nranks*cap] (int), y[nranks*cap][H] (fp32)
     CUtensorMap tm_recv[5];             // the receive area as the token operand of the gate/up GEMM: [nranks*cap rows][H]
   } p2p;
@@ -876,16 +877,15 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     p.tl = c->tl_next;
     static const bool fuse_on = !(getenv("B2M_EP_FUSE_ROUTE") && getenv("B2M_EP_FUSE_ROUTE")[0] == '0');
     if (c->ep_direct_next && fuse_on && T <= c->num_sms && c->cfg.router != B2M_ROUTER_SWITCH_TOP1) {
-      p.ep_fused = 1;            // one launch: gate/top-k + rank + permute + dispatch (every CTA of the grid is resident)
-      p.offsets_early = 1;
-      p.rows_by_gate = 1;
-      p.ready = c->d_ticket + 1;
+      p.ep_fused = 1;            // one launch: gate/top-k + slot claim + row stores + signal
+      p.ep.slot_ctr = c->p2p.local_ctr + 4;
     }
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
   CK(c, launch_route(p, st));
   c->stats.kernel_launches += route_launch_count(T, c->cfg.router, kind == 0) - (p.ep_fused ? 1 : 0);
+  c->ep_fused_last = p.ep_fused != 0;
   c->last_counts_valid = false;
   // router-logit driven prefetch: the next layer's router applied to THIS layer's input predicts which experts the next
   // layer will want; the counts ride back with this layer's own counts (b2m_run_experts reads both in one synchronisation)
@@ -1228,6 +1228,7 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   if (ep_collect) {
     p.ep_collect = 1;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
+    if (c->ep_direct_next && c->ep_fused_last) p.ep.slot_ctr = c->p2p.local_ctr + 4;   // row_of holds owner-segment slots
     if (c->tl_next) p.tl = c->tl_next + 12;
   }
   CK(c, launch_combine(p, st));
@@ -1524,8 +1525,8 @@ int b2m_ep_p2p_init(b2m_ctx* c, int nranks, int rank, int cap, void* ipc_handle_
     int rr = build_act_map(c, &q.tm_recv[i], q.base, c->cfg.hidden, nranks * cap, NT_LIST[i]);
     if (rr) return rr;
   }
-  CK(c, cudaMalloc((void**)&q.local_ctr, 4 * sizeof(int)));
-  CK(c, cudaMemset(q.local_ctr, 0, 4 * sizeof(int)));
+  CK(c, cudaMalloc((void**)&q.local_ctr, 20 * sizeof(int)));
+  CK(c, cudaMemset(q.local_ctr, 0, 20 * sizeof(int)));
   CK(c, cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   CK(c, cudaIpcGetMemHandle(&h, q.base));
@@ -1668,6 +1669,7 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   base.ep_first = q.rank * El;
   base.ep_el = El;
   base.ep_tags = ep.local_tags;
+  base.ep_tag_epoch = c->ep_fused_last ? 1 : 0;
   base.ep_nranks = q.nranks;
   base.ep_rank = q.rank;
   base.ep_flag = ep.local_recv_flag;

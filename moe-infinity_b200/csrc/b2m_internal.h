@@ -59,6 +59,7 @@ struct GemmParams {
   int ep_first;              // first global expert id owned by this rank
   int ep_el;                 // experts per rank
   const int* ep_tags;        // [ep_rows] written by the source ranks' dispatch kernels (peer stores)
+  int ep_tag_epoch;          // 1: tags are (dispatch epoch << 8) | local expert (fused dispatch); 0: plain local expert index or -1
   int ep_nranks;
   int ep_wait;               // 1: the token operand / tags arrive from the peers: wait for their epoch flags (gate/up GEMM)
   const int* ep_flag;        // [nranks] this rank's receive flags
@@ -116,7 +117,8 @@ struct EpParams {
   // ---- direct mode (direct = 1): receive slots are [nranks][cap] rows (no counts row); every slot carries a tag; the owners'
   // fp32 outputs are read in place by the source ranks' combine kernels (peer loads), no return kernel
   int direct;
-  int* peer_tags[16];         // peer r's tags[nranks*cap]
+  int* slot_ctr;              // [nranks] slots handed out so far in this rank's segment at each owner (fused dispatch, 0 between layers)
+  int* peer_tags[16];         // peer r's tags[nranks*cap]: (dispatch epoch << 8) | local expert index; stale epochs never match
   int* local_tags;
   float* peer_y[16];          // peer r's fp32 outputs y[nranks*cap][H]
   float* local_y;

@@ -26,6 +26,8 @@ __device__ __forceinline__ void p2p_signal(const EpParams& p, int which /*0 disp
   __threadfence_system();
   if (threadIdx.x == 0) {
     p.done_ctr[which] = 0;
+    if (which == 0 && p.slot_ctr)
+      for (int r = 0; r < p.nranks; ++r) p.slot_ctr[r] = 0;   // every CTA has taken its slots: ready for the next layer
     const int e = p.epoch[which] + 1;
     p.epoch[which] = e;
     __threadfence_system();

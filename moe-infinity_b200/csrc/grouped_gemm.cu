@@ -75,10 +75,11 @@ __device__ __forceinline__ float silu_mufu(float x) {
 // expert-parallel direct mode: wait (one thread) until every source rank has published this layer's epoch, i.e. its rows
 // and tags have landed in this rank's receive area.  Called by every thread that goes on to read peer-written data with
 // ordinary loads (the acquire orders that thread's own later reads); the TMA producer adds a generic->async proxy fence.
-__device__ __forceinline__ void ep_gemm_wait(const GemmParams& p) {
+__device__ __forceinline__ int ep_gemm_wait(const GemmParams& p) {
   const int want = *reinterpret_cast<const volatile int*>(p.ep_epoch);
   for (int r = 0; r < p.ep_nranks; ++r)
     while (ld_acquire_sys(p.ep_flag + r) < want) __nanosleep(32);
+  return want;
 }
 
 template <int NT, bool DUAL, int DT, int MC>
@@ -282,8 +283,9 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     if (p.early_a) pdl_wait();
+    int ep_want = 0;
     if (p.ep_rows > 0 && p.ep_flag) {
-      ep_gemm_wait(p);                   // this thread reads the peers' tags below (immediate when the flags are already up)
+      ep_want = ep_gemm_wait(p);         // this thread reads the peers' tags below (immediate when the flags are already up)
       if (p.ep_zero) {
         // clear the down projection's accumulator: safe now -- a source rank publishes this layer's flag only after its
         // combine of the previous layer has finished reading the previous outputs
@@ -311,7 +313,8 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         if (row_ok) bias0 = Half16<DT>::to_f(bp[m]);
         if (DUAL && m + BLOCK_M < p.M) bias1 = Half16<DT>::to_f(bp[m + BLOCK_M]);
       }
-      const int ep_le = t.e - p.ep_first;   // direct mode: only the slots tagged with this expert are stored
+      // direct mode: only the slots tagged with (this layer's dispatch epoch, this expert) are stored
+      const int ep_le = p.ep_tag_epoch ? ((ep_want << 8) | (t.e - p.ep_first)) : (t.e - p.ep_first);
       for (int c0 = cgrp * 16; c0 < t.ncols; c0 += 16 * (Cfg::EPI_WARPS / 4)) {   // warp-uniform trip count
         uint32_t vg[16], vu[16];
         tmem_ld_x16(taddr + c0, vg);

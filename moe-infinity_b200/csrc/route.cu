@@ -712,6 +712,41 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
     route_token_warp(p, t, s_logits, scores_in, s_scr, p.topk_idx + (size_t)t * p.k, p.topk_w + (size_t)t * p.k);
     if (p.tl && lane == 0) tl_max(p.tl + 1);
   }
+  if (p.ep_fused) {
+    // ---- expert parallel, direct mode: this kernel is also the permute + dispatch kernel.  Rows need no global ranking here
+    // (every row is processed independently by the owner and found again through row_of): each (token, choice) takes the
+    // next free slot of this rank's segment at the owner with an atomic, stores its row there and tags the slot with
+    // (dispatch epoch, local expert) -- tags of earlier layers carry an older epoch and never match, so nothing is reset.
+    __shared__ int s_dst_rank[MAX_K], s_dst_pos[MAX_K];
+    __syncthreads();
+    if (warp == 0) {
+      const int want = *reinterpret_cast<volatile int*>(p.ep.epoch) + 1;   // epoch[0] moves only after every CTA arrived in p2p_signal
+      const int El = p.E / p.ep.nranks;
+      if (lane < p.k) {
+        const int e = p.topk_idx[(size_t)t * p.k + lane];
+        int r = -1, pos = -1;
+        if (e >= 0) {
+          r = e / El;
+          pos = atomicAdd(p.ep.slot_ctr + r, 1);
+          p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = (want << 8) | (e - r * El);
+        }
+        p.row_of[(size_t)t * p.k + lane] = pos;          // slot inside this rank's segment at the owner (the combine's key)
+        s_dst_rank[lane] = r;
+        s_dst_pos[lane] = pos;
+      }
+    }
+    __syncthreads();
+    const int vec_per_row = p.H / 8;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
+    for (int j = 0; j < p.k; ++j) {
+      if (s_dst_rank[j] < 0) continue;
+      uint4* dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, s_dst_rank[j], s_dst_pos[j]));
+      for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
+    }
+    p2p_signal(p.ep, 0);
+    if (p.tl && threadIdx.x == 0) tl_max(p.tl + 3);
+    return;
+  }
   if (!p.offsets_early) return;
   // ---- the last CTA to finish publishes counts[E] / offsets[E+1] for the whole batch: the grouped GEMM only needs these
   // (not the gathered rows) to start streaming weights, so it can overlap the permute kernel
@@ -724,7 +759,7 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   // ep_fused (expert parallel, direct mode, T <= #SMs so that every CTA of this grid is resident): this kernel is also the
   // permute + dispatch kernel -- once the last CTA has published the row maps every CTA stores its own token's rows into the
   // owners' receive areas and the grid signals the peers.  One launch and one redundant ranking pass less per layer.
-  const bool fuse = p.ep_fused != 0;
+  const bool fuse = false;   // (the expert-parallel fused dispatch returned above)
   __syncthreads();
   if (threadIdx.x == 0) {
     if (fuse) s_want = *reinterpret_cast<volatile int*>(p.ep.epoch) + 1;   // epoch[0] moves only after every CTA has arrived in p2p_signal
@@ -1141,7 +1176,8 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
       const int El = p.ep.E / p.ep.nranks;
       const int r = my_e / El;
       const int stride = p.ep.inline_counts ? p.ep.cap + 1 : p.ep.cap;
-      const int pos = my_row - p.ep.offsets_src[r * El];
+      const int pos = p.ep.slot_ctr ? my_row                       // fused dispatch: row_of already holds the slot in the owner's segment
+                                    : my_row - p.ep.offsets_src[r * El];
       my_owner = r;
       my_row = p.ep.direct ? p.ep.rank * p.ep.cap + pos     // slot of the row in the OWNER's receive / output area
                            : r * stride + pos;
