@@ -876,11 +876,11 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     p.ep_dispatch = 1;
     p.tl = c->tl_next;
     static const bool fuse_on = !(getenv("B2M_EP_FUSE_ROUTE") && getenv("B2M_EP_FUSE_ROUTE")[0] == '0');
+    p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     if (c->ep_direct_next && fuse_on && T <= c->num_sms && c->cfg.router != B2M_ROUTER_SWITCH_TOP1) {
       p.ep_fused = 1;            // one launch: gate/top-k + slot claim + row stores + signal
       p.ep.slot_ctr = c->p2p.local_ctr + 4;
     }
-    p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
   CK(c, launch_route(p, st));

@@ -109,6 +109,7 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
     }
   }
   finish_routing(p);
+  if (p.ep_fused && (!p.ep.slot_ctr || !p.ep.epoch || !p.ep.peer_tags[p.ep.rank])) return cudaErrorInvalidValue;   // the real kernel would fault
   logf("route T=%d offsets_early=%d rows_by_gate=%d ep_dispatch=%d ep_direct=%d counts=%s", p.T, p.offsets_early, p.rows_by_gate,
        p.ep_dispatch, p.ep_dispatch ? p.ep.direct : 0, ints(p.counts, p.E).c_str());
   return cudaSuccess;
