@@ -270,6 +270,29 @@ int b2m_ep_p2p_combine(b2m_ctx* ctx, int layer, const void* x, int T_local, void
 int b2m_ep_p2p_layer(b2m_ctx* ctx, int layer, const void* x, const void* router_in, int router_in_kind,
                      int router_in_dtype, int T_local, void* out, void* stream);
 
+/* ---- device-side activation tracer / predictor.  Replaces ExpertTracer.update_entry / find_most_similar
+ * (moe_infinity/memory/expert_tracer.py:78-125: two device syncs per sequence per layer in the reference) and
+ * ExpertPredictor.predict (expert_predictor.py:17-35) with ONE kernel per layer call and no host round trip; the trace
+ * library (load_trace, :40-52) and the per-sequence matrices live on the device.
+ *   b2m_trace_init        capacity = library entries (ArcherConfig.trace_capacity), max_seqs = concurrent sequences
+ *   b2m_trace_load        load_trace: n entries [n][L][E] fp32 from the host (persistent entries, never replaced)
+ *   b2m_trace_reset_seq   create_entry: zero the sequence's matrix
+ *   b2m_trace_update_predict  after a routing call of num_seqs*seq_len tokens (sequence-major rows): update every sequence's
+ *                         matrix at `layer`, pick its nearest library trace, write the decayed prediction, and add it to the
+ *                         call's hint matrix [L][E] (the scores ExpertPrefetcher.prefetch_experts sorts).  Asynchronous.
+ *                         In offload mode the hint matrix rides back with the next per-layer count read-back and feeds
+ *                         the prefetch scheduler (b2m_prefetch_hint semantics) when auto_prefetch != 0.
+ *   b2m_trace_finish_seq  finish_entry (:61-76): store the sequence's matrix in the library
+ *   b2m_trace_read        what: 0 sequence matrix, 1 last prediction of a sequence, 2 hint matrix, 3 library entry (all [L][E]
+ *                         fp32), 4 access counts (int32 [capacity] written as-is), 5 winner index of a sequence (1 int32);
+ *                         synchronises the device (tests, get_trace / save_trace persistence) */
+int b2m_trace_init(b2m_ctx* ctx, int capacity, int max_seqs, int auto_prefetch);
+int b2m_trace_load(b2m_ctx* ctx, int n, const float* lib_host);
+int b2m_trace_reset_seq(b2m_ctx* ctx, int seq_slot, void* stream);
+int b2m_trace_update_predict(b2m_ctx* ctx, int layer, int seq_slot0, int num_seqs, int seq_len, void* stream);
+int b2m_trace_finish_seq(b2m_ctx* ctx, int seq_slot, void* stream);
+int b2m_trace_read(b2m_ctx* ctx, int what, int index, void* host_out);
+
 /* diagnostics (B2M_TIMELINE=1 in the environment): device-side nanosecond timestamps of the kernels of b2m_ep_p2p_layer's
  * direct mode, 16 words per layer: [0,1] gate/top-k first start / last end, [2,3] permute+dispatch, [4,5,6] gate/up GEMM
  * start / peers' flags seen / end, [8,10] down GEMM start / end (after "done" is published), [12,13,14] combine start /

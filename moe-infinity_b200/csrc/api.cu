@@ -139,6 +139,15 @@ struct b2m_ctx {
 
   int cur_ksplit = 1, cur_nt = 16, cur_nt_dn = 16, cur_T = 0;   // token-tile widths of the up (K3) and down (K4) GEMMs
   bool ep_mode = false;       // experts of other ranks are simply absent (never an error)
+  // device-side tracer / predictor (b2m_trace_*)
+  struct Trace {
+    int capacity = 0, max_seqs = 0, persistent = 0, auto_prefetch = 0;
+    float *seq = nullptr, *lib = nullptr, *pred = nullptr, *hint = nullptr;
+    int *access = nullptr, *winner = nullptr;
+    float* h_hint = nullptr;      // pinned [L][E]: the hint matrix rides back with the per-layer count read-back
+    bool hint_pending = false;
+    int hint_layer = 0;
+  } tr;
   unsigned long long* tl_next = nullptr;   // timeline slots of the layer call in progress
   unsigned long long* d_tl = nullptr;   // B2M_TIMELINE=1: [L][16] device timestamps of the expert-parallel layer's kernels
   bool ep_direct_next = false;   // the routing / combine call in progress belongs to b2m_ep_p2p_layer's direct mode
@@ -705,6 +714,11 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_err) cudaFreeHost(c->h_err);
   if (c->h_look) cudaFreeHost(c->h_look);
+  {
+    void* tb[] = {c->tr.seq, c->tr.lib, c->tr.pred, c->tr.hint, c->tr.access, c->tr.winner};
+    for (void* b : tb) if (b) cudaFree(b);
+    if (c->tr.h_hint) cudaFreeHost(c->tr.h_hint);
+  }
   for (auto& x : c->experts) if (x.ready) cudaEventDestroy(x.ready);
   if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
   if (c->prefetch_stream) cudaStreamDestroy(c->prefetch_stream);
@@ -1024,6 +1038,25 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
     c->last_look_valid = c->look_pending;
     c->look_pending = false;
     c->cur_layer = layer;
+    if (c->tr.hint_pending && c->tr.auto_prefetch) {
+      // the device predictor's score matrix arrived with this read-back: ExpertPrefetcher.prefetch_experts on the host side
+      // (expert_prefetcher.py:42-59: layers >= the predicting layer, score > 0, descending) -> protected set + prefetch queue
+      c->tr.hint_pending = false;
+      const int Ln = c->cfg.num_layers;
+      std::vector<int32_t> pairs;
+      std::vector<float> scores;
+      for (int l = c->tr.hint_layer; l < Ln; ++l)
+        for (int e = 0; e < E; ++e) {
+          const float sc = c->tr.h_hint[(size_t)l * E + e];
+          if (sc > 0.f && !(l == layer && c->h_counts[e] > 0)) { pairs.push_back(l); pairs.push_back(e); scores.push_back(sc); }
+        }
+      if (!scores.empty()) {
+        for (int e = 0; e < E; ++e)                    // this layer's activated experts are in use from now on: never a prefetch victim
+          if (c->h_counts[e] > 0) c->last_active.push_back(layer * E + e);
+        int rr = b2m_prefetch_hint(c, (int)scores.size(), pairs.data(), scores.data());
+        if (rr) return rr;
+      }
+    }
     const float alpha = c->cfg.freq_alpha > 0.f ? c->cfg.freq_alpha : 0.25f;
     for (int e = 0; e < E; ++e) {
       Expert& x = c->experts[(size_t)layer * E + e];
@@ -1713,6 +1746,115 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   c->ep_direct_next = false;
   c->tl_next = nullptr;
   return r;
+}
+
+// ------------------------------------------------------------------------------------ device-side tracer / predictor
+static TraceParams trace_params(b2m_ctx* c) {
+  TraceParams p;
+  memset(&p, 0, sizeof p);
+  p.L = c->cfg.num_layers; p.E = c->cfg.num_experts; p.k = c->cfg.top_k;
+  p.capacity = c->tr.capacity; p.persistent = c->tr.persistent;
+  p.topk_idx = c->d_topk_idx;
+  p.seq = c->tr.seq; p.lib = c->tr.lib; p.access = c->tr.access; p.pred = c->tr.pred; p.hint = c->tr.hint; p.winner = c->tr.winner;
+  return p;
+}
+
+int b2m_trace_init(b2m_ctx* c, int capacity, int max_seqs, int auto_prefetch) {
+  if (!c) return B2M_EINVAL;
+  if (c->tr.lib) return fail(c, B2M_ESTATE, "tracer already initialised");
+  const int L = c->cfg.num_layers, E = c->cfg.num_experts;
+  if (capacity < 1 || max_seqs < 1 || (long long)L * E > 8192) return fail(c, B2M_EINVAL, "bad tracer geometry (capacity=%d max_seqs=%d L*E=%d)", capacity, max_seqs, L * E);
+  const size_t m = (size_t)L * E * sizeof(float);
+  CK(c, cudaMalloc((void**)&c->tr.lib, m * capacity));
+  CK(c, cudaMemset(c->tr.lib, 0, m * capacity));
+  CK(c, cudaMalloc((void**)&c->tr.seq, m * max_seqs));
+  CK(c, cudaMemset(c->tr.seq, 0, m * max_seqs));
+  CK(c, cudaMalloc((void**)&c->tr.pred, m * max_seqs));
+  CK(c, cudaMemset(c->tr.pred, 0, m * max_seqs));
+  CK(c, cudaMalloc((void**)&c->tr.hint, m));
+  CK(c, cudaMemset(c->tr.hint, 0, m));
+  CK(c, cudaMalloc((void**)&c->tr.access, sizeof(int) * capacity));
+  CK(c, cudaMemset(c->tr.access, 0, sizeof(int) * capacity));
+  CK(c, cudaMalloc((void**)&c->tr.winner, sizeof(int) * max_seqs));
+  CK(c, cudaMemset(c->tr.winner, 0, sizeof(int) * max_seqs));
+  CK(c, cudaHostAlloc((void**)&c->tr.h_hint, m, cudaHostAllocDefault));
+  c->tr.capacity = capacity; c->tr.max_seqs = max_seqs; c->tr.auto_prefetch = auto_prefetch;
+  return B2M_OK;
+}
+
+int b2m_trace_load(b2m_ctx* c, int n, const float* lib_host) {
+  if (!c || !lib_host) return B2M_EINVAL;
+  if (!c->tr.lib) return fail(c, B2M_ESTATE, "call b2m_trace_init first");
+  if (n < 0 || n > c->tr.capacity) return fail(c, B2M_EINVAL, "loaded trace capacity %d must be less than or equal to capacity %d", n, c->tr.capacity);
+  CK(c, cudaMemcpy(c->tr.lib, lib_host, (size_t)n * c->cfg.num_layers * c->cfg.num_experts * sizeof(float), cudaMemcpyHostToDevice));
+  c->tr.persistent = n;
+  return B2M_OK;
+}
+
+int b2m_trace_reset_seq(b2m_ctx* c, int seq_slot, void* stream) {
+  if (!c) return B2M_EINVAL;
+  if (!c->tr.lib) return fail(c, B2M_ESTATE, "call b2m_trace_init first");
+  if (seq_slot < 0 || seq_slot >= c->tr.max_seqs) return fail(c, B2M_EINVAL, "sequence slot %d out of range", seq_slot);
+  const size_t m = (size_t)c->cfg.num_layers * c->cfg.num_experts;
+  CK(c, cudaMemsetAsync(c->tr.seq + m * seq_slot, 0, m * sizeof(float), (cudaStream_t)stream));
+  return B2M_OK;
+}
+
+int b2m_trace_update_predict(b2m_ctx* c, int layer, int seq_slot0, int num_seqs, int seq_len, void* stream) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (!c->tr.lib) return fail(c, B2M_ESTATE, "call b2m_trace_init first");
+  if (num_seqs < 1 || seq_len < 1 || seq_slot0 < 0 || seq_slot0 + num_seqs > c->tr.max_seqs)
+    return fail(c, B2M_EINVAL, "sequences [%d, %d) out of range (max_seqs=%d)", seq_slot0, seq_slot0 + num_seqs, c->tr.max_seqs);
+  if (num_seqs * seq_len != c->cur_T) return fail(c, B2M_ESTATE, "num_seqs*seq_len=%d does not match the last routing call (T=%d)", num_seqs * seq_len, c->cur_T);
+  cudaStream_t st = (cudaStream_t)stream;
+  TraceParams p = trace_params(c);
+  p.layer = layer; p.seq_len = seq_len; p.seq_slot0 = seq_slot0;
+  const size_t m = (size_t)c->cfg.num_layers * c->cfg.num_experts * sizeof(float);
+  CK(c, cudaMemsetAsync(c->tr.hint, 0, m, st));
+  CK(c, launch_trace_update_predict(p, num_seqs, st));
+  c->stats.kernel_launches += 1;
+  if (c->tr.auto_prefetch && c->offload && !c->ep_mode) {
+    CK(c, cudaMemcpyAsync(c->tr.h_hint, c->tr.hint, m, cudaMemcpyDeviceToHost, st));   // consumed after the next count read-back
+    c->tr.hint_pending = true;
+    c->tr.hint_layer = layer;
+  }
+  return B2M_OK;
+}
+
+int b2m_trace_finish_seq(b2m_ctx* c, int seq_slot, void* stream) {
+  if (!c) return B2M_EINVAL;
+  if (!c->tr.lib) return fail(c, B2M_ESTATE, "call b2m_trace_init first");
+  if (seq_slot < 0 || seq_slot >= c->tr.max_seqs) return fail(c, B2M_EINVAL, "sequence slot %d out of range", seq_slot);
+  TraceParams p = trace_params(c);
+  CK(c, launch_trace_finish(p, seq_slot, (cudaStream_t)stream));
+  c->stats.kernel_launches += 1;
+  return B2M_OK;
+}
+
+int b2m_trace_read(b2m_ctx* c, int what, int index, void* host_out) {
+  if (!c || !host_out) return B2M_EINVAL;
+  if (!c->tr.lib) return fail(c, B2M_ESTATE, "call b2m_trace_init first");
+  const size_t m = (size_t)c->cfg.num_layers * c->cfg.num_experts;
+  CK(c, cudaDeviceSynchronize());
+  switch (what) {
+    case 0: case 1:
+      if (index < 0 || index >= c->tr.max_seqs) return fail(c, B2M_EINVAL, "sequence slot %d out of range", index);
+      CK(c, cudaMemcpy(host_out, (what == 0 ? c->tr.seq : c->tr.pred) + m * index, m * sizeof(float), cudaMemcpyDeviceToHost));
+      break;
+    case 2: CK(c, cudaMemcpy(host_out, c->tr.hint, m * sizeof(float), cudaMemcpyDeviceToHost)); break;
+    case 3:
+      if (index < 0 || index >= c->tr.capacity) return fail(c, B2M_EINVAL, "library entry %d out of range", index);
+      CK(c, cudaMemcpy(host_out, c->tr.lib + m * index, m * sizeof(float), cudaMemcpyDeviceToHost));
+      break;
+    case 4: CK(c, cudaMemcpy(host_out, c->tr.access, sizeof(int) * c->tr.capacity, cudaMemcpyDeviceToHost)); break;
+    case 5:
+      if (index < 0 || index >= c->tr.max_seqs) return fail(c, B2M_EINVAL, "sequence slot %d out of range", index);
+      CK(c, cudaMemcpy(host_out, c->tr.winner + index, sizeof(int), cudaMemcpyDeviceToHost));
+      break;
+    default: return fail(c, B2M_EINVAL, "unknown trace item %d", what);
+  }
+  return B2M_OK;
 }
 
 int b2m_timeline_read(b2m_ctx* c, unsigned long long* host_out, int n_layers) {

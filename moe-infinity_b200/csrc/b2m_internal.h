@@ -192,6 +192,24 @@ struct CombineParams {
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t st);
 cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t st);
 
+// ---- device-side activation tracer / predictor (tracer.cu) ----------------------------------------------
+struct TraceParams {
+  int L, E, k;
+  int layer;
+  int seq_len;             // tokens per sequence in this call (rows b*seq_len .. of the routing result belong to sequence b)
+  int seq_slot0;           // first sequence slot of this call
+  int capacity, persistent;
+  const int* topk_idx;     // [num_seqs*seq_len, k] routing result of the call (workspace)
+  float* seq;              // [max_seqs][L][E] per-sequence trace matrices
+  float* lib;              // [capacity][L][E] trace library
+  int* access;             // [capacity]
+  float* pred;             // [max_seqs][L][E] decayed prediction of the last call
+  float* hint;             // [L][E] sum of the predictions of the call's sequences (zeroed by the caller)
+  int* winner;             // [max_seqs] library entry chosen for each sequence
+};
+cudaError_t launch_trace_update_predict(const TraceParams& p, int num_seqs, cudaStream_t st);
+cudaError_t launch_trace_finish(const TraceParams& p, int seq_slot, cudaStream_t st);
+
 // fp32 [rows,H] -> model dtype [rows,H] (compat path: per-expert outputs handed back to Python)
 cudaError_t launch_cast_rows(const float* y, void* out, size_t n, int dtype, cudaStream_t st);
 

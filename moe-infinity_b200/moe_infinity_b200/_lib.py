@@ -89,6 +89,12 @@ SYMBOLS = [
     ("b2m_ep_p2p_combine", _I, [_VP, _I, _VP, _I, _VP, _VP]),
     ("b2m_ep_p2p_layer", _I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
     ("b2m_timeline_read", _I, [_VP, C.POINTER(C.c_uint64), _I]),
+    ("b2m_trace_init", _I, [_VP, _I, _I, _I]),
+    ("b2m_trace_load", _I, [_VP, _I, _VP]),
+    ("b2m_trace_reset_seq", _I, [_VP, _I, _VP]),
+    ("b2m_trace_update_predict", _I, [_VP, _I, _I, _I, _I, _VP]),
+    ("b2m_trace_finish_seq", _I, [_VP, _I, _VP]),
+    ("b2m_trace_read", _I, [_VP, _I, _I, _VP]),
 ]
 
 _lib = None

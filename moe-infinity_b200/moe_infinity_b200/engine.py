@@ -337,3 +337,71 @@ class DecodeSession:
         if sync:
             torch.cuda.current_stream().synchronize()
         return self.out_host
+
+
+class DeviceExpertTracer:
+    """Device-side ExpertTracer + ExpertPredictor (moe_infinity/memory/expert_tracer.py:17-125, expert_predictor.py:7-35):
+    the trace library and the per-sequence matrices live in HBM and one kernel per layer call does update_entry,
+    find_most_similar and predict for every sequence of the batch -- no `.cpu()` in the layer (the reference pays two
+    device syncs per sequence per layer).  Sequences are slots 0..max_seqs-1; a call's tokens are sequence-major
+    (rows b*seq_len .. (b+1)*seq_len-1 belong to slot seq_slot0 + b; decode: seq_len = 1).
+    Readers (`entry`, `prediction`, `hint`, `library`, `save_trace`) synchronise and are meant for tests / persistence."""
+
+    def __init__(self, engine: MoEEngine, capacity: int, max_seqs: int, auto_prefetch: bool = False):
+        self.eng, self.capacity, self.max_seqs = engine, capacity, max_seqs
+        engine._ck(engine.lib.b2m_trace_init(engine._h, capacity, max_seqs, int(auto_prefetch)))
+
+    def load_trace(self, trace):                       # expert_tracer.py:40-52
+        import numpy as np
+        if isinstance(trace, (str, bytes)) or hasattr(trace, "__fspath__"):
+            trace = np.load(trace, allow_pickle=False)
+        arr = np.ascontiguousarray(trace, dtype=np.float32)
+        assert arr.shape[1:] == (self.eng.L, self.eng.E) and arr.shape[0] <= self.capacity
+        self.eng._ck(self.eng.lib.b2m_trace_load(self.eng._h, arr.shape[0], C.c_void_p(arr.ctypes.data)))
+
+    def create_entry(self, seq_slot: int):             # :54-59
+        self.eng._ck(self.eng.lib.b2m_trace_reset_seq(self.eng._h, seq_slot, C.c_void_p(_stream_ptr())))
+        return seq_slot
+
+    def finish_entry(self, seq_slot: int):             # :61-76
+        self.eng._ck(self.eng.lib.b2m_trace_finish_seq(self.eng._h, seq_slot, C.c_void_p(_stream_ptr())))
+
+    def update_predict(self, layer: int, num_seqs: int, seq_len: int = 1, seq_slot0: int = 0):
+        """update_entry + find_most_similar + predict for the routing call that just ran (asynchronous)."""
+        self.eng._ck(self.eng.lib.b2m_trace_update_predict(self.eng._h, layer, seq_slot0, num_seqs, seq_len,
+                                                           C.c_void_p(_stream_ptr())))
+
+    def _read(self, what: int, index: int, n: int, dtype):
+        import numpy as np
+        out = np.zeros(n, dtype=dtype)
+        self.eng._ck(self.eng.lib.b2m_trace_read(self.eng._h, what, index, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def entry(self, seq_slot: int):
+        import numpy as np
+        return self._read(0, seq_slot, self.eng.L * self.eng.E, np.float32).reshape(self.eng.L, self.eng.E)
+
+    def prediction(self, seq_slot: int):
+        import numpy as np
+        return self._read(1, seq_slot, self.eng.L * self.eng.E, np.float32).reshape(self.eng.L, self.eng.E)
+
+    def hint(self):
+        import numpy as np
+        return self._read(2, 0, self.eng.L * self.eng.E, np.float32).reshape(self.eng.L, self.eng.E)
+
+    def library(self, index: int):
+        import numpy as np
+        return self._read(3, index, self.eng.L * self.eng.E, np.float32).reshape(self.eng.L, self.eng.E)
+
+    def access_counts(self):
+        import numpy as np
+        return self._read(4, 0, self.capacity, np.int32)
+
+    def winner(self, seq_slot: int) -> int:
+        import numpy as np
+        return int(self._read(5, seq_slot, 1, np.int32)[0])
+
+    def save_trace(self, path):
+        """Persist the library (what `load_trace` reads back): np.save of [capacity][L][E] fp32."""
+        import numpy as np
+        np.save(path, np.stack([self.library(i) for i in range(self.capacity)]))

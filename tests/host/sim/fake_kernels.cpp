@@ -168,6 +168,11 @@ cudaError_t launch_combine_f32(const CombineParams& p, cudaStream_t) {
   logf("combine_f32 T=%d mode=%d", p.T, p.mode);
   return cudaSuccess;
 }
+cudaError_t launch_trace_update_predict(const TraceParams& p, int num_seqs, cudaStream_t) {
+  logf("trace_update_predict layer=%d seqs=%d seq_len=%d slot0=%d", p.layer, num_seqs, p.seq_len, p.seq_slot0);
+  return cudaSuccess;
+}
+cudaError_t launch_trace_finish(const TraceParams&, int seq_slot, cudaStream_t) { logf("trace_finish slot=%d", seq_slot); return cudaSuccess; }
 int gemm_tc_smem_bytes(int, bool) { return 200 * 1024; }
 
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t) {

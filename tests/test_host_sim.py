@@ -677,6 +677,37 @@ def test_expert_parallel_direct_layer_on_cpu(sim):
         sim.b2m_sim_enable_ipc(0)
 
 
+def test_device_tracer_call_wiring_on_cpu(sim):
+    """b2m_trace_*: argument / state checks, one predictor launch per call, and -- in offload mode with auto_prefetch --
+    the hint matrix riding back with the next per-layer count read-back into the prefetch scheduler (no extra sync)."""
+    c = Ctx(sim, L_=3, E=8, num_slots=10)
+    assert c.rc == 0, c.err()
+    c.register_all(1)
+    assert sim.b2m_trace_update_predict(c.h, 0, 0, 1, 1, None) == L.B2M_ESTATE            # not initialised
+    assert sim.b2m_trace_init(c.h, 16, 4, 1) == 0, c.err()
+    assert sim.b2m_trace_init(c.h, 16, 4, 1) == L.B2M_ESTATE
+    lib = np.ones((2, 3, 8), dtype=np.float32)
+    assert sim.b2m_trace_load(c.h, 17, lib.ctypes.data) != 0
+    assert sim.b2m_trace_load(c.h, 2, lib.ctypes.data) == 0, c.err()
+    back = np.zeros((3, 8), dtype=np.float32)
+    assert sim.b2m_trace_read(c.h, 3, 1, back.ctypes.data) == 0 and back.sum() == 24
+    assert sim.b2m_trace_reset_seq(c.h, 4, None) != 0 and sim.b2m_trace_reset_seq(c.h, 3, None) == 0
+    T = 4
+    lg = np.random.default_rng(0).standard_normal((T, 8)).astype(np.float32)
+    x = np.zeros((T, c.H), dtype=np.uint16)
+    assert sim.b2m_route(c.h, 1, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, None) == 0, c.err()
+    assert sim.b2m_trace_update_predict(c.h, 1, 0, 3, 1, None) == L.B2M_ESTATE            # 3 x 1 tokens != T
+    assert sim.b2m_trace_update_predict(c.h, 1, 2, 4, 1, None) != 0                       # slots 2..5 of 4
+    take_log(sim)
+    assert sim.b2m_trace_update_predict(c.h, 1, 0, 4, 1, None) == 0, c.err()
+    assert [ln.split()[0] for ln in take_log(sim)] == ["trace_update_predict"]
+    syncs = c.stats()["host_syncs"]
+    assert sim.b2m_run_experts(c.h, 1, T, None) == 0, c.err()                             # consumes the (all-zero) hint matrix
+    assert c.stats()["host_syncs"] == syncs + 1
+    assert sim.b2m_trace_finish_seq(c.h, 0, None) == 0 and sim.b2m_trace_finish_seq(c.h, 9, None) != 0
+    c.close()
+
+
 def test_random_call_sequences_never_crash_on_cpu(sim):
     """Stateful fuzz of the C ABI's host logic: random (often invalid) calls in random order.  Every call must return a
     status code (0 or < 0 with a message), the cache invariants must hold after every step, and a valid forward must keep
