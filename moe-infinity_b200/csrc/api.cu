@@ -1262,6 +1262,8 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
     p.ep_collect = 1;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
     if (c->ep_direct_next && c->ep_fused_last) p.ep.slot_ctr = c->p2p.local_ctr + 4;   // row_of holds owner-segment slots
+    static const bool early_combine = !(getenv("B2M_EP_EARLY_COMBINE") && getenv("B2M_EP_EARLY_COMBINE")[0] == '0');
+    p.ep_early = (c->ep_direct_next && early_combine && !pdl_enabled() && f.shared_inter == 0) ? 1 : 0;
     if (c->tl_next) p.tl = c->tl_next + 12;
   }
   CK(c, launch_combine(p, st));

@@ -186,6 +186,7 @@ struct CombineParams {
   void* out;               // [T,H] model dtype
   int T, H, k, dtype, mode;
   int ep_collect;          // 1: expert outputs are read from the peer-written return area (model dtype rows)
+  int ep_early;            // direct mode: programmatic edge behind the down GEMM, no grid-completion wait (flags guard the data)
   EpParams ep;
   unsigned long long* tl;  // optional timeline slots: [0] start, [1] owners' flags seen, [2] end
 };

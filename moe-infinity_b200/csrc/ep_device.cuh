@@ -15,29 +15,26 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 // Every CTA calls this after its last store to peer memory; the last CTA to arrive publishes epoch to all peers.
 __device__ __forceinline__ void p2p_signal(const EpParams& p, int which /*0 dispatch, 1 return*/) {
-  __shared__ int s_last;
   __syncthreads();                 // every thread's peer stores are ordered before thread 0's fence (CTA-scope barrier) ...
-  if (threadIdx.x == 0) {
-    __threadfence_system();        // ... which makes them visible system-wide (fences are cumulative): one fence per CTA, not per thread
-    s_last = (atomicAdd(p.done_ctr + which, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x == 0) {
-    p.done_ctr[which] = 0;
-    if (which == 0 && p.slot_ctr)
-      for (int r = 0; r < p.nranks; ++r) p.slot_ctr[r] = 0;   // every CTA has taken its slots: ready for the next layer
-    const int e = p.epoch[which] + 1;
-    p.epoch[which] = e;
-    __threadfence_system();
-    for (int r = 0; r < p.nranks; ++r) st_release_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
-  }
+  if (threadIdx.x != 0) return;
+  __threadfence_system();          // ... which makes them visible system-wide (fences are cumulative): one fence per CTA
+  if (atomicAdd(p.done_ctr + which, 1) != (int)gridDim.x - 1) return;
+  __threadfence_system();          // last arriver: the other CTAs' (fenced) stores happen-before everything below
+  p.done_ctr[which] = 0;
+  if (which == 0 && p.slot_ctr)
+    for (int r = 0; r < p.nranks; ++r) p.slot_ctr[r] = 0;   // every CTA has taken its slots: ready for the next layer
+  const int e = p.epoch[which] + 1;
+  p.epoch[which] = e;
+  for (int r = 0; r < p.nranks; ++r)                          // st.release orders the stores above before the flag
+    st_release_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
 }
 // Wait until every source rank's flag reached this rank's own epoch (all ranks issue the same number of exchanges).
-__device__ __forceinline__ void p2p_wait(const EpParams& p, int which) {
+__device__ __forceinline__ void p2p_wait(const EpParams& p, int which, int epoch_word = -1) {
   if (threadIdx.x < p.nranks) {
-    const int want = p.epoch[which];
+    // epoch_word: which local epoch the flags must reach.  Direct mode's combine starts before this rank's own down GEMM has
+    // bumped epoch[1], so it compares the "done" flags with epoch[0] (this layer's dispatch count, final since the routing
+    // kernel finished): every layer call issues exactly one dispatch and one "done", so the two counters agree.
+    const int want = *reinterpret_cast<volatile int*>(p.epoch + (epoch_word < 0 ? which : epoch_word));
     const int* f = (which ? p.local_back_flag : p.local_recv_flag) + threadIdx.x;
     while (ld_acquire_sys(f) < want) __nanosleep(64);
   }

@@ -1147,7 +1147,10 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   const int lane = threadIdx.x & 31;
   const int k = p.k;
   pdl_launch();
-  pdl_wait();
+  // expert parallel, direct mode: launched with a programmatic edge behind the down GEMM and NOT waiting for that grid to
+  // drain -- everything it reads from earlier kernels is older than the GEMMs (routing tables) and the expert outputs are
+  // guarded by the owners' "done" flags (this rank's own included), so its CTAs are resident and polling when "done" lands
+  if (!(p.ep_collect && p.ep.direct && p.ep_early)) pdl_wait();
   if (p.tl && threadIdx.x == 0) tl_min(p.tl);
   // each warp loads the token's routing list into lanes 0..k-1 and sorts it by expert id via shuffles
   int my_e = 0x7fffffff, my_row = -1;
@@ -1169,7 +1172,7 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
   const float* srcf[MAX_K];
   int my_owner = 0;
   if (p.ep_collect) {
-    if (p.ep.p2p) p2p_wait(p.ep, 1);     // return rows of every owner rank have landed (direct mode: the owners' GEMMs are done)
+    if (p.ep.p2p) p2p_wait(p.ep, 1, (p.ep.direct && p.ep_early) ? 0 : -1);   // return rows landed (direct mode: the owners' GEMMs are done)
     if (p.tl && threadIdx.x == 0) tl_max(p.tl + 1);
     if (lane < k && my_row >= 0) {
       // permuted row -> (owner rank, position in that rank's segment of this rank's return area)
@@ -1299,8 +1302,9 @@ cudaError_t launch_combine(const CombineParams& p, cudaStream_t st) {
   int gy = (p.H + CB_THREADS * 8 - 1) / (CB_THREADS * 8);
   dim3 grid(p.T, gy);
   if (p.dtype == DT_F32) return launch_combine_f32(p, st);
-  if (p.dtype == DT_BF16) return launch_pdl(combine_kernel<DT_BF16>, grid, dim3(CB_THREADS), 0, st, p);
-  if (p.dtype == DT_F16) return launch_pdl(combine_kernel<DT_F16>, grid, dim3(CB_THREADS), 0, st, p);
+  const bool early = p.ep_collect && p.ep.direct && p.ep_early;
+  if (p.dtype == DT_BF16) return launch_cluster(combine_kernel<DT_BF16>, grid, dim3(CB_THREADS), 0, st, 1, early, p);
+  if (p.dtype == DT_F16) return launch_cluster(combine_kernel<DT_F16>, grid, dim3(CB_THREADS), 0, st, 1, early, p);
   return cudaErrorInvalidValue;
 }
 
