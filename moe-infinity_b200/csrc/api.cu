@@ -151,7 +151,7 @@ struct b2m_ctx {
   unsigned long long* tl_next = nullptr;   // timeline slots of the layer call in progress
   unsigned long long* d_tl = nullptr;   // B2M_TIMELINE=1: [L][16] device timestamps of the expert-parallel layer's kernels
   bool ep_direct_next = false;   // the routing / combine call in progress belongs to b2m_ep_p2p_layer's direct mode
-  bool ep_fused_last = false;    // ... and its routing call used the fused dispatch (slots claimed with atomics, epoch tags)
+  bool ep_fused_last = false;    // ... and its routing call was the fused gate/top-k + dispatch kernel
   int ep_inline = 0;          // exchange buffers carry the counts in an extra row per peer
   // peer-to-peer exchange (CUDA IPC mapped buffers of the other ranks)
   struct P2P {
@@ -160,8 +160,12 @@ struct b2m_ctx {
     size_t area_bytes = 0;
     uint8_t* peer_base[16] = {nullptr};
     int* local_ctr = nullptr;           // [0..1] epoch, [2..3] done counters, [4..19] slot counters of the fused dispatch
-    size_t tags_off = 0, y_off = 0;     // direct mode regions inside the allocation: tags[nranks*cap] (int), y[nranks*cap][H] (fp32)
-    CUtensorMap tm_recv[5];             // the receive area as the token operand of the gate/up GEMM: [nranks*cap rows][H]
+    // direct mode regions inside the allocation (after the two exchange areas and the flags): row counters cnt[E/nranks] (int),
+    // receive rows [E/nranks][nranks*cap][H] (model dtype), outputs y [E/nranks][nranks*cap][H] (fp32)
+    size_t cnt_off = 0, drecv_off = 0, y_off = 0;
+    CUtensorMap tm_recv[5];             // the direct receive area as the token operand of the gate/up GEMM: [E*cap rows][H]
+    void* d_hmid = nullptr;             // direct mode intermediate [E*cap rows][I] (local, same row indexing as the receive area)
+    CUtensorMap tm_hmid[5];
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
@@ -709,6 +713,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
   if (c->p2p.base) cudaFree(c->p2p.base);
+  if (c->p2p.d_hmid) cudaFree(c->p2p.d_hmid);
   if (c->p2p.local_ctr) cudaFree(c->p2p.local_ctr);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -889,12 +894,8 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
     p.ep_dispatch = 1;
     p.tl = c->tl_next;
-    static const bool fuse_on = !(getenv("B2M_EP_FUSE_ROUTE") && getenv("B2M_EP_FUSE_ROUTE")[0] == '0');
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
-    if (c->ep_direct_next && fuse_on && T <= c->num_sms && c->cfg.router != B2M_ROUTER_SWITCH_TOP1) {
-      p.ep_fused = 1;            // one launch: gate/top-k + slot claim + row stores + signal
-      p.ep.slot_ctr = c->p2p.local_ctr + 4;
-    }
+    if (c->ep_direct_next) p.ep_fused = 1;   // one launch: gate/top-k + row claim (remote atomics) + row stores + signal
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
   CK(c, launch_route(p, st));
@@ -1261,7 +1262,6 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   if (ep_collect) {
     p.ep_collect = 1;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
-    if (c->ep_direct_next && c->ep_fused_last) p.ep.slot_ctr = c->p2p.local_ctr + 4;   // row_of holds owner-segment slots
     static const bool early_combine = !(getenv("B2M_EP_EARLY_COMBINE") && getenv("B2M_EP_EARLY_COMBINE")[0] == '0');
     p.ep_early = (c->ep_direct_next && early_combine && !pdl_enabled() && f.shared_inter == 0) ? 1 : 0;
     if (c->tl_next) p.tl = c->tl_next + 12;
@@ -1526,11 +1526,12 @@ static EpParams ep_p2p_params(b2m_ctx* c) {
   p.epoch = q.local_ctr;
   p.done_ctr = q.local_ctr + 2;
   for (int r = 0; r < q.nranks; ++r) {
-    p.peer_tags[r] = reinterpret_cast<int*>(q.peer_base[r] + q.tags_off);
+    p.peer_cnt[r] = reinterpret_cast<int*>(q.peer_base[r] + q.cnt_off);
     p.peer_y[r] = reinterpret_cast<float*>(q.peer_base[r] + q.y_off);
   }
-  p.local_tags = reinterpret_cast<int*>(q.base + q.tags_off);
+  p.local_cnt = reinterpret_cast<int*>(q.base + q.cnt_off);
   p.local_y = reinterpret_cast<float*>(q.base + q.y_off);
+  p.region_rows = q.nranks * q.cap;
   return p;
 }
 // direct mode: [nranks][cap] receive slots without a counts row, per-slot tags, outputs read in place by the sources
@@ -1538,6 +1539,9 @@ static EpParams ep_p2p_params_direct(b2m_ctx* c) {
   EpParams p = ep_p2p_params(c);
   p.inline_counts = 0;
   p.direct = 1;
+  const b2m_ctx::P2P& q = c->p2p;
+  for (int r = 0; r < q.nranks; ++r) p.peer_recv[r] = q.peer_base[r] + q.drecv_off;   // per-expert regions, not per-source segments
+  p.recv_rows = q.base + q.drecv_off;
   return p;
 }
 
@@ -1550,14 +1554,18 @@ int b2m_ep_p2p_init(b2m_ctx* c, int nranks, int rank, int cap, void* ipc_handle_
   b2m_ctx::P2P& q = c->p2p;
   q.nranks = nranks; q.rank = rank; q.cap = cap;
   q.area_bytes = p2p_area_bytes(c, nranks, cap);
-  q.tags_off = (2 * q.area_bytes + 32 * sizeof(int) + 255) & ~(size_t)255;
-  q.y_off = (q.tags_off + (size_t)nranks * cap * sizeof(int) + 255) & ~(size_t)255;
-  const size_t total = q.y_off + (size_t)nranks * cap * c->cfg.hidden * sizeof(float);
+  const size_t drows = (size_t)(c->cfg.num_experts / nranks) * nranks * cap;   // = E*cap: one region of nranks*cap rows per local expert
+  q.cnt_off = (2 * q.area_bytes + 32 * sizeof(int) + 255) & ~(size_t)255;
+  q.drecv_off = (q.cnt_off + 256 * sizeof(int) + 255) & ~(size_t)255;
+  q.y_off = (q.drecv_off + drows * c->cfg.hidden * 2 + 255) & ~(size_t)255;
+  const size_t total = q.y_off + drows * c->cfg.hidden * sizeof(float);
   CK(c, cudaMalloc((void**)&q.base, total));
   CK(c, cudaMemset(q.base, 0, total));
-  CK(c, cudaMemset(q.base + q.tags_off, 0xff, (size_t)nranks * cap * sizeof(int)));   // every slot empty
+  CK(c, cudaMalloc(&q.d_hmid, drows * c->cfg.inter * 2));
+  CK(c, cudaMemset(q.d_hmid, 0, drows * c->cfg.inter * 2));
   for (int i = 0; i < 5; ++i) {
-    int rr = build_act_map(c, &q.tm_recv[i], q.base, c->cfg.hidden, nranks * cap, NT_LIST[i]);
+    int rr = build_act_map(c, &q.tm_recv[i], q.base + q.drecv_off, c->cfg.hidden, (int)drows, NT_LIST[i]);
+    if (!rr) rr = build_act_map(c, &q.tm_hmid[i], q.d_hmid, c->cfg.inter, (int)drows, NT_LIST[i]);
     if (rr) return rr;
   }
   CK(c, cudaMalloc((void**)&q.local_ctr, 20 * sizeof(int)));
@@ -1642,7 +1650,9 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   if (!out) return fail(c, B2M_EINVAL, "out is null");
   const int El = f.num_experts / q.nranks, R = q.nranks * q.cap, T_total = q.nranks * T_local;
   static const bool direct_on = !(getenv("B2M_EP_DIRECT") && getenv("B2M_EP_DIRECT")[0] == '0');
-  const bool direct = direct_on && El <= 8 && R <= 256 && T_local <= 256 && f.gemm_impl == 0 && f.shared_inter == 0;
+  // direct mode: the fused route+dispatch kernel needs every CTA resident (T_local <= #SMs)
+  const bool direct = direct_on && T_local <= c->num_sms && f.gemm_impl == 0 && f.shared_inter == 0 &&
+                      f.router != B2M_ROUTER_SWITCH_TOP1 && f.dtype != B2M_DTYPE_F32;
   cudaStream_t st = (cudaStream_t)stream;
   if (!direct) {
     r = b2m_ep_p2p_route(c, layer, x, router_in, kind, in_dtype, T_local, stream);
@@ -1680,16 +1690,16 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   }
   r = upload_row_if_dirty(c, layer, st);
   if (r) return r;
-  // ---- plan: one token tile spanning all receive slots
-  int nt = 16;
-  while (nt < R) nt *= 2;
+  // ---- plan: token tiles sized for the expected rows per expert (an expert with more rows simply takes several tiles: the
+  // tile list is built on the device from the row counters)
+  const int nt = pick_nt(std::max(1, (2 * T_total * f.top_k + f.num_experts - 1) / f.num_experts));
   c->cur_T = T_total;
   c->cur_nt = c->cur_nt_dn = nt;
   const ExpertShape& s = c->arena.shape;
   int ks = 1;
   if (!s.has_bias) {
     const int kblocks = (s.I + 63) / 64;
-    const long long tiles = (long long)El * ((s.H + 127) / 128);
+    const long long tiles = (long long)std::min(El, T_total * f.top_k) * ((s.H + 127) / 128);
     ks = (int)std::min<long long>(8, (6LL * c->num_sms + tiles - 1) / tiles);
     ks = std::max(1, std::min(ks, kblocks / 4 > 0 ? kblocks / 4 : 1));
   }
@@ -1703,18 +1713,17 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   base.ep_rows = R;
   base.ep_first = q.rank * El;
   base.ep_el = El;
-  base.ep_tags = ep.local_tags;
-  base.ep_tag_epoch = c->ep_fused_last ? 1 : 0;
+  base.ep_cnt = ep.local_cnt;
   base.ep_nranks = q.nranks;
   base.ep_rank = q.rank;
   base.ep_flag = ep.local_recv_flag;
   base.ep_epoch = ep.epoch;
   GemmParams up = base;
   up.M = s.I; up.K = s.H; up.ksplit = 1; up.epi = EPI_ACT16; up.act = s.act;
-  up.mimic = f.numerics == B2M_NUMERICS_REFERENCE; up.out = c->d_hmid; up.ld_out = s.I;
+  up.mimic = f.numerics == B2M_NUMERICS_REFERENCE; up.out = c->p2p.d_hmid; up.ld_out = s.I;
   up.ep_wait = 1;
   up.ep_zero = ks > 1 ? ep.local_y : nullptr;
-  up.ep_zero_elems = (size_t)R * s.H;
+  up.ep_zero_elems = (size_t)El * R * s.H;
   GemmParams dn = base;
   dn.M = s.H; dn.K = s.I; dn.ksplit = ks; dn.epi = EPI_LINEAR_F32; dn.act = ACT_NONE; dn.mimic = 0;
   dn.out = ep.local_y; dn.ld_out = s.H;
@@ -1736,11 +1745,11 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   // The tile list is static here, so the grid can be sized to it: with 448 tiles (4 experts x 112) on 148 CTAs the last 4
   // tiles run alone and are limited by what one SM can ingest (~120 GB/s; measured 17 us of a 162 us kernel,
   // profiles/r02_ep2_timeline_before.log); 112 CTAs x 4 tiles each finish together at the full HBM rate.
-  const int up_tiles = El * ((s.I + 127) / 128);
+  const int up_tiles = std::min(El, T_total * f.top_k) * ((s.I + 127) / 128);   // expected: every local expert active, one token tile
   const int up_rounds = (up_tiles + c->num_sms - 1) / c->num_sms;
   const int up_grid = std::max(1, std::min(c->num_sms, (up_tiles + up_rounds - 1) / up_rounds));
   CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
-  CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, c->tm_hmid[ni], dn, c->num_sms, st));
+  CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, q.tm_hmid[ni], dn, c->num_sms, st));
   c->stats.kernel_launches += 2;
   // ---- combine at the source: wait for the owners' "done", read their outputs in place
   c->ep_direct_next = true;

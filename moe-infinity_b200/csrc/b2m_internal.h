@@ -52,16 +52,15 @@ struct GemmParams {
   size_t bias_slot_elems;
   size_t bias_off;
   // ---- expert-parallel "direct" mode (ep_rows > 0; csrc/ep.cu header): the token operand is this rank's peer-written receive
-  // area itself, ALL ep_rows = nranks*cap slots as one shared row range for every local expert (no regroup kernel, static tile
-  // list -> weights stream from the first cycle); ep_tags[slot] = local expert index of the row in that slot or -1, and an
-  // epilogue only stores the slots whose tag names its expert.
-  int ep_rows;               // 0 = off
+  // area itself.  Every local expert owns a region of ep_rows = nranks*cap rows (its worst case); the source ranks claim rows
+  // in it from the front with (remote) atomics on ep_cnt[local expert], so the rows of an expert are contiguous and the tile
+  // width follows the actual count -- no regroup kernel, no host involvement.
+  int ep_rows;               // 0 = off; else rows per expert region
   int ep_first;              // first global expert id owned by this rank
   int ep_el;                 // experts per rank
-  const int* ep_tags;        // [ep_rows] written by the source ranks' dispatch kernels (peer stores)
-  int ep_tag_epoch;          // 1: tags are (dispatch epoch << 8) | local expert (fused dispatch); 0: plain local expert index or -1
+  int* ep_cnt;               // [ep_el] rows claimed in each local expert's region (cleared by the down GEMM's last CTA)
   int ep_nranks;
-  int ep_wait;               // 1: the token operand / tags arrive from the peers: wait for their epoch flags (gate/up GEMM)
+  int ep_wait;               // (kept for diagnostics) 1 = gate/up GEMM, the launch that actually has to wait for the peers
   const int* ep_flag;        // [nranks] this rank's receive flags
   const int* ep_epoch;       // local epoch word the flags must reach
   float* ep_zero;            // fp32 accumulator of the down projection, cleared once the flags have been seen
@@ -117,9 +116,9 @@ struct EpParams {
   // ---- direct mode (direct = 1): receive slots are [nranks][cap] rows (no counts row); every slot carries a tag; the owners'
   // fp32 outputs are read in place by the source ranks' combine kernels (peer loads), no return kernel
   int direct;
-  int* slot_ctr;              // [nranks] slots handed out so far in this rank's segment at each owner (fused dispatch, 0 between layers)
-  int* peer_tags[16];         // peer r's tags[nranks*cap]: (dispatch epoch << 8) | local expert index; stale epochs never match
-  int* local_tags;
+  int region_rows;            // direct mode: rows per expert region = nranks*cap
+  int* peer_cnt[16];          // peer r's row counters cnt[E/nranks] (direct mode: sources claim rows with remote atomics)
+  int* local_cnt;
   float* peer_y[16];          // peer r's fp32 outputs y[nranks*cap][H]
   float* local_y;
 };

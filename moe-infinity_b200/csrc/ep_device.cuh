@@ -21,8 +21,6 @@ __device__ __forceinline__ void p2p_signal(const EpParams& p, int which /*0 disp
   if (atomicAdd(p.done_ctr + which, 1) != (int)gridDim.x - 1) return;
   __threadfence_system();          // last arriver: the other CTAs' (fenced) stores happen-before everything below
   p.done_ctr[which] = 0;
-  if (which == 0 && p.slot_ctr)
-    for (int r = 0; r < p.nranks; ++r) p.slot_ctr[r] = 0;   // every CTA has taken its slots: ready for the next layer
   const int e = p.epoch[which] + 1;
   p.epoch[which] = e;
   for (int r = 0; r < p.nranks; ++r)                          // st.release orders the stores above before the flag

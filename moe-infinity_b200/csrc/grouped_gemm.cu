@@ -49,7 +49,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    (MAX_E + 1) * 4 * 2 /*tile_start, offsets*/ + MAX_E * 4 /*slots*/;
+                                    (MAX_E + 1) * 4 * 2 /*tile_start, offsets*/ + MAX_E * 4 * 2 /*slots, region counts*/;
   static_assert(TMEM_COLS_RAW <= 512, "TMEM overflow");
   static_assert(STAGES >= 2, "need >=2 stages");
 };
@@ -100,6 +100,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   int* tile_start = reinterpret_cast<int*>(tmem_ptr_smem + 2);
   int* offs = tile_start + (MAX_E + 1);
   int* slots = offs + (MAX_E + 1);
+  int* cnts = slots + MAX_E;           // direct mode: rows per expert region
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,13 +141,24 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
   } else if (p.ep_rows > 0) {
-    // direct mode: a static tile list -- every local expert spans all receive slots; nothing here depends on the peers
+    // direct mode: local expert le owns rows [le*ep_rows, le*ep_rows + cnt[le]) of the receive area; the counts are final
+    // once every source rank has published this layer's flag
+    if (threadIdx.x == 0) {
+      ep_gemm_wait(p);
+      fence_proxy_async_global();          // this thread is also the TMA producer: its later bulk loads read the peers' rows
+      if (p.tl && p.ep_wait) tl_max(p.tl + 1);
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i <= E; i += Cfg::THREADS) {
       int le = i - p.ep_first;
       le = le < 0 ? 0 : (le > p.ep_el ? p.ep_el : le);
       offs[i] = le * p.ep_rows;
     }
-    for (int i = threadIdx.x; i < E; i += Cfg::THREADS) slots[i] = p.slot_of[i];
+    for (int i = threadIdx.x; i < E; i += Cfg::THREADS) {
+      slots[i] = p.slot_of[i];
+      const int le = i - p.ep_first;
+      cnts[i] = (le >= 0 && le < p.ep_el) ? __ldcg(p.ep_cnt + le) : 0;
+    }
   } else {
     for (int i = threadIdx.x; i <= E; i += Cfg::THREADS) offs[i] = p.offsets[i];
     for (int i = threadIdx.x; i < E; i += Cfg::THREADS) slots[i] = p.slot_of[i];
@@ -156,7 +168,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     int acc = 0;
     for (int e = 0; e < E; ++e) {
       tile_start[e] = acc;
-      const int n_e = offs[e + 1] - offs[e];
+      const int n_e = p.ep_rows > 0 ? cnts[e] : offs[e + 1] - offs[e];
       if (n_e > 0 && slots[e] >= 0) acc += m_tiles * (((n_e + NT - 1) / NT + MC - 1) / MC) * (p.stream_k ? 1 : p.ksplit);
     }
     tile_start[E] = acc;
@@ -169,7 +181,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast targets them
 
   TileWalker walker{tile_start, offs, slots, E, NT, p.stream_k ? 1 : p.ksplit, kblocks, 0, m_step, MC, crank, 0, 0, 0,
-                    p.ep_rows > 0 ? 1 : 0};
+                    p.ep_rows > 0 ? cnts : nullptr};
   if (MC == 1 && p.stream_k) {
     const long long units = (long long)tile_start[E] * kblocks;
     walker.stream = 1;
@@ -184,7 +196,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      bool waited = !(p.early_a || p.ep_wait);   // ep_wait: token tiles come from the peers, weights do not
+      bool waited = !p.early_a;
       int npend = 0, pend_stage[Cfg::STAGES], pend_kb[Cfg::STAGES], pend_row[Cfg::STAGES];
       for (int tile = tile0; walker.get(tile, t); tile += tile_stride) {
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
@@ -195,7 +207,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           // decode: weights are streamed exactly once -> evict-first.  Several n-tiles per expert (prefill): the same
           // weight tile is re-read by every n-tile -> keep it in L2.  Tokens are re-read by every m-tile: keep.
-          const uint64_t wh = (offs[t.e + 1] - offs[t.e] <= NT) ? CACHE_EVICT_FIRST : CACHE_EVICT_NORMAL;
+          const uint64_t wh = ((p.ep_rows > 0 ? cnts[t.e] : offs[t.e + 1] - offs[t.e]) <= NT) ? CACHE_EVICT_FIRST : CACHE_EVICT_NORMAL;
           if (MC == 1) {
             tma_load_3d(&tmA0, &full_bar[stage], sA0, kb * BLOCK_K, t.m0, t.slot, wh);
             if (DUAL) tma_load_3d(&tmA1, &full_bar[stage], sA1, kb * BLOCK_K, t.m0 + (p.dual_m ? BLOCK_M : 0), t.slot, wh);
@@ -215,8 +227,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             // tiles follow once it has
             pend_stage[npend] = stage; pend_kb[npend] = kb; pend_row[npend] = t.row0;
             if (++npend == Cfg::STAGES) {
-              if (p.early_a) pdl_wait();
-              if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); if (p.tl) tl_max(p.tl + 1); }
+              pdl_wait();
               for (int i = 0; i < npend; ++i)
                 tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                             pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -229,8 +240,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         }
       }
       if (!waited) {   // fewer work items than pipeline stages
-        if (p.early_a) pdl_wait();
-        if (p.ep_wait) { ep_gemm_wait(p); fence_proxy_async_global(); }
+        pdl_wait();
         for (int i = 0; i < npend; ++i)
           tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                       pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -283,9 +293,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     if (p.early_a) pdl_wait();
-    int ep_want = 0;
-    if (p.ep_rows > 0 && p.ep_flag) {
-      ep_want = ep_gemm_wait(p);         // this thread reads the peers' tags below (immediate when the flags are already up)
+    if (p.ep_rows > 0) {
       if (p.ep_zero) {
         // clear the down projection's accumulator: safe now -- a source rank publishes this layer's flag only after its
         // combine of the previous layer has finished reading the previous outputs
@@ -313,25 +321,16 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         if (row_ok) bias0 = Half16<DT>::to_f(bp[m]);
         if (DUAL && m + BLOCK_M < p.M) bias1 = Half16<DT>::to_f(bp[m + BLOCK_M]);
       }
-      // direct mode: only the slots tagged with (this layer's dispatch epoch, this expert) are stored
-      const int ep_le = p.ep_tag_epoch ? ((ep_want << 8) | (t.e - p.ep_first)) : (t.e - p.ep_first);
       for (int c0 = cgrp * 16; c0 < t.ncols; c0 += 16 * (Cfg::EPI_WARPS / 4)) {   // warp-uniform trip count
         uint32_t vg[16], vu[16];
         tmem_ld_x16(taddr + c0, vg);
         if (DUAL) tmem_ld_x16(taddr + NT + c0, vu);
-        uint32_t keep = 0xffffu;
-        if (p.ep_rows > 0) {
-          keep = 0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < t.ncols && __ldcg(p.ep_tags + t.row0 + c0 + j) == ep_le) keep |= 1u << j;
-        }
         tmem_ld_wait();
         if (p.epi == EPI_LINEAR_F32) {
           float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (c0 + j < t.ncols && ((keep >> j) & 1u)) {
+            if (c0 + j < t.ncols) {
               float* dst = out + (size_t)(t.row0 + c0 + j) * p.ld_out + m;
               if (row_ok) {
                 float v = __uint_as_float(vg[j]);
@@ -349,7 +348,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (row_ok && c0 + j < t.ncols && ((keep >> j) & 1u)) {
+            if (row_ok && c0 + j < t.ncols) {
               float g = __uint_as_float(vg[j]);
               float h;
               if (DUAL) {
@@ -390,6 +389,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if (atomicAdd(p.ep_done_ctr, 1) == (int)gridDim.x - 1) {
       __threadfence_system();
       *p.ep_done_ctr = 0;
+      for (int le = 0; le < p.ep_el; ++le) p.ep_cnt[le] = 0;   // every CTA has read the counts: regions are free for the next layer
       const int e = *p.ep_done_epoch + 1;
       *p.ep_done_epoch = e;
       __threadfence_system();

@@ -713,34 +713,31 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
     if (p.tl && lane == 0) tl_max(p.tl + 1);
   }
   if (p.ep_fused) {
-    // ---- expert parallel, direct mode: this kernel is also the permute + dispatch kernel.  Rows need no global ranking here
-    // (every row is processed independently by the owner and found again through row_of): each (token, choice) takes the
-    // next free slot of this rank's segment at the owner with an atomic, stores its row there and tags the slot with
-    // (dispatch epoch, local expert) -- tags of earlier layers carry an older epoch and never match, so nothing is reset.
-    __shared__ int s_dst_rank[MAX_K], s_dst_pos[MAX_K];
+    // ---- expert parallel, direct mode: this kernel is also the permute + dispatch kernel.  Rows need no global ranking
+    // (every row is processed independently by the owner and found again through row_of): each (token, choice) claims the
+    // next free row of its expert's region at the owner with an atomic on the OWNER's counter (a remote atomic over NVLink
+    // for peers) and stores its row there -- the owner sees each expert's rows contiguous, exactly as many as there are.
+    __shared__ int s_dst_rank[MAX_K], s_dst_row[MAX_K];
     __syncthreads();
-    if (warp == 0) {
-      const int want = *reinterpret_cast<volatile int*>(p.ep.epoch) + 1;   // epoch[0] moves only after every CTA arrived in p2p_signal
+    if (warp == 0 && lane < p.k) {
       const int El = p.E / p.ep.nranks;
-      if (lane < p.k) {
-        const int e = p.topk_idx[(size_t)t * p.k + lane];
-        int r = -1, pos = -1;
-        if (e >= 0) {
-          r = e / El;
-          pos = atomicAdd(p.ep.slot_ctr + r, 1);
-          p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = (want << 8) | (e - r * El);
-        }
-        p.row_of[(size_t)t * p.k + lane] = pos;          // slot inside this rank's segment at the owner (the combine's key)
-        s_dst_rank[lane] = r;
-        s_dst_pos[lane] = pos;
+      const int e = p.topk_idx[(size_t)t * p.k + lane];
+      int r = -1, pos = -1, le = 0;
+      if (e >= 0) {
+        r = e / El;
+        le = e - r * El;
+        pos = atomicAdd(p.ep.peer_cnt[r] + le, 1);
       }
+      p.row_of[(size_t)t * p.k + lane] = pos;            // row inside the expert's region at the owner (the combine's key)
+      s_dst_rank[lane] = r;
+      s_dst_row[lane] = le * p.ep.region_rows + pos;
     }
     __syncthreads();
     const int vec_per_row = p.H / 8;
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
     for (int j = 0; j < p.k; ++j) {
       if (s_dst_rank[j] < 0) continue;
-      uint4* dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, s_dst_rank[j], s_dst_pos[j]));
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.ep.peer_recv[s_dst_rank[j]]) + (size_t)s_dst_row[j] * p.H);
       for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
     }
     p2p_signal(p.ep, 0);
@@ -751,23 +748,17 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
   // ---- the last CTA to finish publishes counts[E] / offsets[E+1] for the whole batch: the grouped GEMM only needs these
   // (not the gathered rows) to start streaming weights, so it can overlap the permute kernel
   __shared__ int s_last;
-  __shared__ int s_want;
   __shared__ int s_idx2[FUSED_MAX_T * MAX_K];
   __shared__ int s_cnt2[RT_WARPS][MAX_PL * 32];
   __shared__ int s_tot2[MAX_PL * 32];
   __shared__ int s_off2[MAX_PL * 32 + 1];
-  // ep_fused (expert parallel, direct mode, T <= #SMs so that every CTA of this grid is resident): this kernel is also the
-  // permute + dispatch kernel -- once the last CTA has published the row maps every CTA stores its own token's rows into the
-  // owners' receive areas and the grid signals the peers.  One launch and one redundant ranking pass less per layer.
-  const bool fuse = false;   // (the expert-parallel fused dispatch returned above)
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (fuse) s_want = *reinterpret_cast<volatile int*>(p.ep.epoch) + 1;   // epoch[0] moves only after every CTA has arrived in p2p_signal
     __threadfence();
     s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last && !fuse) return;
+  if (!s_last) return;
   const int npairs = p.T * p.k;
   if (s_last) {
     __threadfence();
@@ -816,53 +807,7 @@ __global__ void __launch_bounds__(RT_THREADS) gate_topk_small_kernel(const Route
         chunk_rank_strided(p, (task / RT_WARPS) * CHUNK, [&](int e) { return s_off2[e] + cb[e]; }, s_idx2, task % RT_WARPS, RT_WARPS);
       }
     }
-    if (fuse) {
-      __syncthreads();
-      const int El = p.E / p.ep.nranks;
-      for (int e = threadIdx.x; e <= p.E; e += RT_THREADS) p.ep.offsets_src[e] = s_off2[e];
-      // one tag per receive slot of this rank's segment at every owner: local expert index of the row stored there, or -1
-      for (int i = threadIdx.x; i < p.ep.nranks * p.ep.cap; i += RT_THREADS) {
-        const int r = i / p.ep.cap, pos = i - r * p.ep.cap;
-        const int row = s_off2[r * El] + pos;
-        int tag = -1;
-        if (row < s_off2[(r + 1) * El]) {
-          int e = r * El;
-          while (row >= s_off2[e + 1]) ++e;
-          tag = e - r * El;
-        }
-        p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = tag;
-      }
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.ready), "r"(s_want) : "memory");
-    }
   }
-  if (!fuse) return;
-  // ---- every CTA: wait for the row maps, then store this token's rows into the owners' receive areas (NVLink stores)
-  if (threadIdx.x == 0) {
-    int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ready) : "memory");
-      if (v != s_want) __nanosleep(20);
-    } while (v != s_want);
-  }
-  __syncthreads();
-  {
-    const int El = p.E / p.ep.nranks;
-    const int vec_per_row = p.H / 8;
-    for (int j = 0; j < p.k; ++j) {
-      const int row = __ldcg(p.row_of + (size_t)t * p.k + j);
-      const int e = __ldcg(p.topk_idx + (size_t)t * p.k + j);
-      if (row < 0 || e < 0) continue;
-      const int r = e / El;
-      const int pos = row - __ldcg(p.ep.offsets_src + r * El);
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + (size_t)t * p.H);
-      uint4* dst = reinterpret_cast<uint4*>(ep_send_row(p.ep, r, pos));
-      for (int v = threadIdx.x; v < vec_per_row; v += RT_THREADS) dst[v] = src[v];
-    }
-  }
-  p2p_signal(p.ep, 0);
-  if (p.tl && threadIdx.x == 0) tl_max(p.tl + 3);
 }
 
 __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RouteParams p) {
@@ -970,22 +915,6 @@ __global__ void __launch_bounds__(RT_THREADS) permute_small_kernel(const RoutePa
     for (int i = threadIdx.x; i < p.ep.nranks * p.E; i += RT_THREADS) {
       const int r = i / p.E, e = i - r * p.E;
       reinterpret_cast<int*>(ep_send_row(p.ep, r, p.ep.cap))[e] = s_tot[e];
-    }
-  }
-  if (p.ep_dispatch && blockIdx.x == 0 && p.ep.direct) {
-    // direct mode: every receive slot of this rank's segment at every owner gets a tag -- the local expert index of the row
-    // stored there, or -1 for an unused slot (the owner's GEMM epilogues store only the slots tagged with their expert)
-    const int El = p.E / p.ep.nranks;
-    for (int i = threadIdx.x; i < p.ep.nranks * p.ep.cap; i += RT_THREADS) {
-      const int r = i / p.ep.cap, pos = i - r * p.ep.cap;
-      const int row = s_off[r * El] + pos;
-      int tag = -1;
-      if (row < s_off[(r + 1) * El]) {
-        int e = r * El;
-        while (row >= s_off[e + 1]) ++e;
-        tag = e - r * El;
-      }
-      p.ep.peer_tags[r][p.ep.rank * p.ep.cap + pos] = tag;
     }
   }
   if (warp < nchunks) {
@@ -1179,11 +1108,9 @@ __global__ void __launch_bounds__(CB_THREADS) combine_kernel(const CombineParams
       const int El = p.ep.E / p.ep.nranks;
       const int r = my_e / El;
       const int stride = p.ep.inline_counts ? p.ep.cap + 1 : p.ep.cap;
-      const int pos = p.ep.slot_ctr ? my_row                       // fused dispatch: row_of already holds the slot in the owner's segment
-                                    : my_row - p.ep.offsets_src[r * El];
       my_owner = r;
-      my_row = p.ep.direct ? p.ep.rank * p.ep.cap + pos     // slot of the row in the OWNER's receive / output area
-                           : r * stride + pos;
+      my_row = p.ep.direct ? (my_e - r * El) * p.ep.region_rows + my_row     // row_of = row inside the expert's region at the owner
+                           : r * stride + (my_row - p.ep.offsets_src[r * El]);
     }
   }
 #pragma unroll

@@ -28,9 +28,9 @@ struct TileWalker {
   // get() then ignores `tile` and hands out the next segment (part of one tile) of that range
   int stream;
   int u_cur, u_end;
-  // expert-parallel direct mode: every expert with rows spans the SAME row range [0, n_e) (n_e = all receive slots);
-  // offs[] still carries the per-expert widths as a prefix so that tile counting is unchanged
-  int shared_rows;
+  // expert-parallel direct mode: every local expert owns a fixed-capacity row region that the source ranks fill from the
+  // front; offs[e] = first row of the region, cnts[e] = rows in it (null: rows are packed, n_e = offs[e+1] - offs[e])
+  const int* cnts;
   B2M_HD bool get(int tile, TileInfo& t) {
     int kb0 = 0, kb1 = 0;
     if (stream) {
@@ -44,7 +44,7 @@ struct TileWalker {
     }
     while (tile >= tile_start[e_cur + 1]) ++e_cur;
     const int e = e_cur;
-    const int n_e = offs[e + 1] - offs[e];
+    const int n_e = cnts ? cnts[e] : offs[e + 1] - offs[e];
     const int n_tiles = ((n_e + NTv - 1) / NTv + mc - 1) / mc;   // token-tile groups (one per cluster)
     int local = tile - tile_start[e];
     const int per_m = n_tiles * ksplit;
@@ -56,7 +56,7 @@ struct TileWalker {
     t.e = e;
     t.slot = slots[e];
     t.m0 = m * m_step;
-    t.row0 = (shared_rows ? 0 : offs[e]) + n * NTv;
+    t.row0 = offs[e] + n * NTv;
     t.ncols = tw_max(0, tw_min(NTv, n_e - n * NTv));   // 0: ghost tile of an odd group (loads + MMA still run in lock step)
     t.kb_begin = s * kb_per;
     t.kb_end = tw_min(kblocks, t.kb_begin + kb_per);

@@ -109,7 +109,8 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t) {
     }
   }
   finish_routing(p);
-  if (p.ep_fused && (!p.ep.slot_ctr || !p.ep.epoch || !p.ep.peer_tags[p.ep.rank])) return cudaErrorInvalidValue;   // the real kernel would fault
+  if (p.ep_fused && (!p.ep.epoch || !p.ep.peer_cnt[p.ep.rank] || !p.ep.peer_recv[p.ep.rank] || p.ep.region_rows < 1))
+    return cudaErrorInvalidValue;   // the real kernel would fault
   logf("route T=%d offsets_early=%d rows_by_gate=%d ep_dispatch=%d ep_direct=%d counts=%s", p.T, p.offsets_early, p.rows_by_gate,
        p.ep_dispatch, p.ep_dispatch ? p.ep.direct : 0, ints(p.counts, p.E).c_str());
   return cudaSuccess;
@@ -149,9 +150,9 @@ cudaError_t launch_route_from_mask(const RouteParams& p, const uint8_t* mask, cu
 
 static cudaError_t log_gemm(const char* kind, int nt, bool dual, const GemmParams& p, int grid = -1) {
   logf("gemm impl=%s grid=%d nt=%d dual=%d M=%d K=%d ksplit=%d stream_k=%d epi=%d act=%d mimic=%d early_a=%d dual_m=%d bias=%d "
-       "single_n=%d single_slot=%d ep_rows=%d ep_first=%d ep_el=%d ep_wait=%d ep_zero=%d ep_signal=%d slot_of=%s offsets=%s",
+       "single_n=%d single_slot=%d ep_rows=%d ep_first=%d ep_el=%d ep_wait=%d ep_zero=%d ep_signal=%d ep_cnt=%d slot_of=%s offsets=%s",
        kind, grid, nt, (int)dual, p.M, p.K, p.ksplit, p.stream_k, p.epi, p.act, p.mimic, p.early_a, p.dual_m,
-       p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.ep_rows, p.ep_first, p.ep_el, p.ep_wait, p.ep_zero ? 1 : 0, p.ep_signal,
+       p.bias_base ? 1 : 0, p.single_n, p.single_slot, p.ep_rows, p.ep_first, p.ep_el, p.ep_wait, p.ep_zero ? 1 : 0, p.ep_signal, p.ep_cnt ? 1 : 0,
        p.single_n >= 0 ? "[]" : ints(p.slot_of, p.E).c_str(),
        (p.single_n >= 0 || p.ep_rows > 0) ? "[]" : ints(p.offsets, p.E + 1).c_str());
   return cudaSuccess;

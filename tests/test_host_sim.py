@@ -611,11 +611,10 @@ def test_expert_parallel_call_sequence_and_errors_on_cpu(sim):
 
 
 def test_expert_parallel_direct_layer_on_cpu(sim):
-    """b2m_ep_p2p_layer, host side, two ranks in one process (the emulated CUDA IPC hands out plain pointers): with <= 8
-    experts per rank the layer is five launches -- gate/top-k + permute (one routing call, rows and slot tags go to the
-    owners), a gate/up GEMM over ALL receive slots that waits for the peers and clears the accumulator, a down GEMM that
-    signals, a combine that reads the owners' outputs in place -- and every buffer the kernels are handed lies inside the
-    IPC-mapped allocation; a rank owning many experts falls back to the seven-launch sequence."""
+    """b2m_ep_p2p_layer, host side, two ranks in one process (the emulated CUDA IPC hands out plain pointers): the layer is
+    four launches -- one routing call (gate/top-k that also claims rows in the owners' per-expert regions and stores them),
+    a gate/up GEMM that waits for the peers, reads the row counters and clears the accumulator, a down GEMM that signals and
+    resets the counters, a combine that reads the owners' outputs in place."""
     sim.b2m_sim_enable_ipc(1)
     try:
         nranks, T, E, H, I, k = 2, 6, 8, 128, 128, 2
@@ -647,31 +646,36 @@ def test_expert_parallel_direct_layer_on_cpu(sim):
             assert [ln.split()[0] for ln in lines] == ["route", "gemm", "gemm", "combine"]
             assert _kv(lines[0])["ep_dispatch"] == "1" and _kv(lines[0])["ep_direct"] == "1"
             up, dn = _kv(lines[1]), _kv(lines[2])
-            R = nranks * cap
+            R = nranks * cap                                       # rows of one expert region (its worst case)
             assert up["ep_rows"] == dn["ep_rows"] == str(R) and up["ep_first"] == str(rank * 4) and up["ep_el"] == "4"
             assert (up["ep_wait"], up["ep_signal"], dn["ep_wait"], dn["ep_signal"]) == ("1", "0", "0", "1")
-            assert up["nt"] == dn["nt"] == "32" and up["dual"] == "1" and dn["epi"] == "1"
-            assert up["grid"] == "4" and dn["grid"] == "148"      # 4 experts x 1 weight-row tile: the gate/up grid is sized to its static tile list
+            assert up["ep_cnt"] == dn["ep_cnt"] == "1"
+            assert up["nt"] == dn["nt"] == "16" and up["dual"] == "1" and dn["epi"] == "1"    # ~2*T_total*k/E = 6 rows per expert expected
+            assert up["grid"] == "4" and dn["grid"] == "148"      # 4 experts x 1 weight-row tile: the gate/up grid is sized to the expected tile list
             assert (dn["ksplit"] == "1") == (up["ep_zero"] == "0")          # the accumulator is cleared iff the down GEMM splits K
             assert "ep_direct=1" in lines[3] and _kv(lines[3])["ep_collect"] == "1"
             assert sim.b2m_ep_p2p_layer(c.h, 0, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T + 1, out.ctypes.data, None) != 0
         for c in ctxs:
             c.close()
-        # 32 experts per rank: the shared-row GEMMs would waste 32x the MMA work -> seven-launch sequence
-        c = Ctx(sim, L_=1, E=64, H=H, I=I, k=k, num_slots=32, max_tokens=nranks * T)
+        # DeepSeek shared experts are outside the direct mode -> the seven-launch sequence (six here: route is one call)
+        c = Ctx(sim, L_=1, E=64, H=H, I=I, k=k, num_slots=32, max_tokens=nranks * T, expert_type=L.EXPERT_DEEPSEEK,
+                router=L.ROUTER_DEEPSEEK_GREEDY, shared_inter=2 * I, gate_dtype=L.DTYPE_F32)
         assert c.rc == 0, c.err()
         for e in range(32):
             blob = rng.integers(0, 255, c.expert_bytes(), dtype=np.uint8)
             c.blobs[(0, e)] = blob
             assert sim.b2m_register_expert(c.h, 0, e, blob.ctypes.data, blob.nbytes) == 0, c.err()
             assert sim.b2m_make_resident(c.h, 0, e, 1, None) == 0, c.err()
+        shared = np.zeros(3 * H * 2 * I * 2, dtype=np.uint8)
+        assert sim.b2m_register_shared(c.h, 0, shared.ctypes.data, shared.nbytes) == 0, c.err()
         h = (C.c_char * 64)()
         assert sim.b2m_ep_p2p_init(c.h, nranks, 0, cap, h) == 0, c.err()
         assert sim.b2m_ep_p2p_open(c.h, 1, h) == 0, c.err()                 # loop-back "peer": enough for the call sequence
-        lg64 = rng.standard_normal((T, 64)).astype(np.float32)
+        sc64 = rng.random((T, 64)).astype(np.float32)
         take_log(sim)
-        assert sim.b2m_ep_p2p_layer(c.h, 0, x.ctypes.data, lg64.ctypes.data, 1, L.DTYPE_F32, T, out.ctypes.data, None) == 0, c.err()
-        assert [ln.split()[0] for ln in take_log(sim)] == ["route", "ep_regroup", "gemm", "gemm", "ep_ungroup", "combine"]
+        assert sim.b2m_ep_p2p_layer(c.h, 0, x.ctypes.data, sc64.ctypes.data, 2, L.DTYPE_F32, T, out.ctypes.data, None) == 0, c.err()
+        names = [ln.split()[0] for ln in take_log(sim)]
+        assert names[:2] == ["route", "ep_regroup"] and "ep_ungroup" in names and names[-1] == "combine"
         c.close()
     finally:
         sim.b2m_sim_enable_ipc(0)
