@@ -246,7 +246,9 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
     # ---- parity at full size: this rank's tokens through the expert-parallel layer 0 vs a single-GPU engine that holds all E
     # experts of layer 0.  Same kernels, same rounding chain, experts combined in expert order; the only freedom is the
     # order of the split-K fp32 reductions of the down projection (atomics: not even the single-GPU engine repeats itself
-    # bit for bit there, tests/test_gpu_fullsize.py), so: within 1 bf16 ulp everywhere and >= 97 % of the elements identical
+    # bit for bit there, tests/test_gpu_fullsize.py), so: the tests' hidden-state bound (2 ulp of the value + 2 ulp of the rms,
+    # tests/test_gpu_parity.py:hidden_close -- a one-ulp flip of one of the two summed expert outputs can exceed one ulp of
+    # their sum) everywhere and >= 97 % of the elements identical
     full0 = MoEEngine(num_layers=1, num_experts=E, hidden=H, inter=I, top_k=k, dtype=dtype, max_tokens=max(T, 16),
                       num_slots=E, device=local)
     for e in range(E):
@@ -259,7 +261,7 @@ def bench_ep(args, cfg, batch, metric, load_peaks, ClockSampler):
         a = full0.forward(0, xq).float()
         b = ep.forward(0, xq).float()
         torch.cuda.synchronize()
-        ok = bool(((a - b).abs() <= eps * a.abs() + eps * a.pow(2).mean().sqrt()).all())
+        ok = bool(((a - b).abs() <= 2 * eps * a.abs() + 2 * eps * a.pow(2).mean().sqrt()).all())
         frac = float((a == b).float().mean())
         par[0] = min(float(par[0]), 1.0 if (ok and frac >= 0.97) else 0.0)
         par[1] = min(float(par[1]), frac)
