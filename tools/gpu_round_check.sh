@@ -39,8 +39,18 @@ ls -la "$OUT/${TAG}_k3k4.ncu-rep" 2>/dev/null
 # optional: the reference's own native engine beside ours (REF_ENGINE=1; needs oracle/_ref/prefetch_op.so and an
 # O_DIRECT-capable directory; aborts on any DLOG_FATAL, hence last and in its own process)
 if [ "${REF_ENGINE:-0}" = 1 ]; then
-  run ref_engine 900 python tools/ref_engine_harness.py --layers 4 --tokens 8 --steps 16 --ratio 0.9 --dir "$OUT/ref_store"
+  run ref_engine 900 python tools/ref_engine_harness.py --mode timing --layers 4 --tokens 8 --steps 16 --ratio 0.9
   tail -2 "$OUT/${TAG}_ref_engine.log"
-  rm -rf "$OUT/ref_store"
+fi
+# the other BASELINE configs through bench.py's own driver-runnable lines
+if [ "${EXTRA:-0}" = 1 ]; then
+  run bench_reference 600 python bench.py --impl reference --steps 20 --warmup 5
+  tail -1 "$OUT/${TAG}_bench_reference.log" | cut -c1-400
+  run deepseek 600 python bench.py --config deepseek --steps 20
+  tail -1 "$OUT/${TAG}_deepseek.log" | cut -c1-600
+  run offload 1500 python bench.py --config offload --steps 32 --warmup 4 --ablate
+  tail -1 "$OUT/${TAG}_offload.log" | cut -c1-400
+  run offload_skew2 1500 python bench.py --config offload --steps 32 --warmup 4 --skew 2.0 --ablate
+  tail -1 "$OUT/${TAG}_offload_skew2.log" | cut -c1-400
 fi
 echo "done: $TAG"
