@@ -39,6 +39,33 @@ constexpr int STAGE_RING = 8;
 
 std::string g_create_error;
 
+// ---- run-time switches: read ONCE per process, here and nowhere else in this file.  Every default is the setting that
+// measured best on a B200 (DESIGN.md §6 has the A/B numbers); the others stay selectable for re-measurement.
+struct Switches {
+  bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, timeline;
+  long long nt256_min_avg;
+  static bool off(const char* n) { const char* v = getenv(n); return v && v[0] == '0'; }   // default on
+  static bool on(const char* n) { const char* v = getenv(n); return v && v[0] == '1'; }    // default off
+  Switches()
+      : nt256(!off("B2M_NT256")),                 // 256-token tiles in the tensor-bound regime
+        nt256_up(!off("B2M_NT256_UP")),           // ... for the gate/up GEMM too (B2M_NUMERICS_FP32 only)
+        pdl(on("B2M_PDL")),                       // programmatic dependent launch on every decode kernel: 2.5 % slower
+        early_k3(!off("B2M_EARLY_K3")),           // gate/up GEMM prefetches weights under the permute kernel
+        rows_by_gate(!off("B2M_ROWS_BY_GATE")),   // the last gate/top-k CTA publishes the row maps
+        pdl_k3(on("B2M_PDL_K3")),
+        dyn_n(on("B2M_DYN_N")),                   // per-tile MMA width: +1.5 % at DeepSeek prefill (profiles/r02a_deepseek_dyn_n.json), parity untested -> off
+        early_a(!off("B2M_EARLY_A")),             // down GEMM prefetches weights under the gate/up GEMM's tail
+        streamk(!off("B2M_STREAMK")),             // stream-K partition of the split-K down GEMM
+        ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
+        ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
+        timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
+        nt256_min_avg(getenv("B2M_NT256_MIN_AVG") ? atoll(getenv("B2M_NT256_MIN_AVG")) : 256) {}
+};
+const Switches& sw() {
+  static const Switches s;
+  return s;
+}
+
 struct ExpertShape {
   int H = 0, I = 0;
   bool dual = true;
@@ -292,10 +319,8 @@ int pick_nt(int T) {
 // The gate/up GEMM's two 256-column accumulators leave no second TMEM stage, so its SwiGLU epilogue serialises with the
 // MMAs: with the precise expf/div epilogue it got slower (7.2 -> 8.1 ms), with the MUFU epilogue faster (-> 6.6 ms).
 int pick_nt_model(const b2m_config& f, int T) {
-  static const bool on = !(getenv("B2M_NT256") && getenv("B2M_NT256")[0] == '0');
   const long long avg = (long long)T * f.top_k / f.num_experts;
-  static const long long min_avg = getenv("B2M_NT256_MIN_AVG") ? atoll(getenv("B2M_NT256_MIN_AVG")) : 256;   // DeepSeek-V2-Lite prefill (avg 384): 27.6 -> 25.1 ms
-  if (on && avg >= min_avg && f.hidden >= 256) return 256;
+  if (sw().nt256 && avg >= sw().nt256_min_avg && f.hidden >= 256) return 256;   // DeepSeek-V2-Lite prefill (avg 384): 27.6 -> 25.1 ms
   return pick_nt(T);
 }
 
@@ -517,7 +542,7 @@ void plan_gemm(b2m_ctx* c, int T) {
   c->cur_nt_dn = pick_nt_model(c->cfg, T);
   // gate/up GEMM: 256-token tiles too (single TMEM stage, MUFU SiLU epilogue): 7.37 -> 6.61 ms at T=16384
   // (profiles/r01f_prefill.txt); B2M_NT256_UP=0 keeps the 128-token double-buffered tiles
-  static const bool up256 = !(getenv("B2M_NT256_UP") && getenv("B2M_NT256_UP")[0] == '0');
+  const bool up256 = sw().nt256_up;
   // reference numerics keep the precise SiLU, with which the single-stage 256-token tile is slower than the double-buffered
   // 128-token tile (8.1 vs 7.2-7.4 ms): 256 for the gate/up GEMM only in B2M_NUMERICS_FP32 mode
   c->cur_nt = (up256 && c->cur_nt_dn == 256 && c->cfg.numerics == B2M_NUMERICS_FP32) ? 256 : pick_nt(T);
@@ -527,10 +552,8 @@ void plan_gemm(b2m_ctx* c, int T) {
 }
 
 // same switch as b2m_common.cuh:pdl_enabled() (that header is device code; this file also builds against the host emulation)
-bool pdl_enabled() {
-  static const bool on = getenv("B2M_PDL") && getenv("B2M_PDL")[0] == '1';
-  return on;
-}
+bool pdl_enabled() { return sw().pdl; }
+
 
 int route_launch_count(int T, int router, bool fused_gate) {
   if (T == 0) return 0;
@@ -881,14 +904,14 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
   if (c->cur_ksplit > 1) { p.y_zero = c->d_y; p.y_zero_elems = (size_t)T * c->cfg.top_k * c->cfg.hidden; }
   // small batches, all experts resident: let the last gate/top-k CTA publish the offsets so that the gate/up GEMM can be
   // launched with a programmatic edge behind the permute kernel and stream weights while rows are still being gathered
-  static const bool k3_early = !(getenv("B2M_EARLY_K3") && getenv("B2M_EARLY_K3")[0] == '0');
+  const bool k3_early = sw().early_k3;
   // Not with B2M_PDL=1: with a programmatic edge on EVERY kernel the permute kernel may start before the gate/top-k kernel
   // has finished, so a GEMM that reads offsets/slot_of before its own griddepcontrol.wait could see the previous layer's
   // tables.  Pre-wait reads may only touch data older than the predecessor's own launch.
   c->k3_early_ok = k3_early && !pdl_enabled() && T >= 1 && T <= 256 && c->cfg.router != B2M_ROUTER_SWITCH_TOP1 && !ep_dispatch &&
                    !c->offload && !c->ep_mode && c->cfg.gemm_impl == 0;
   p.offsets_early = c->k3_early_ok ? 1 : 0;
-  static const bool rows_by_gate = !(getenv("B2M_ROWS_BY_GATE") && getenv("B2M_ROWS_BY_GATE")[0] == '0');
+  const bool rows_by_gate = sw().rows_by_gate;
   p.rows_by_gate = (c->k3_early_ok && rows_by_gate) ? 1 : 0;
   if (ep_dispatch) {
     if (T > 256 || T < 1) return fail(c, B2M_EINVAL, "fused route+dispatch handles 1..256 tokens per rank (got %d)", T);
@@ -975,20 +998,27 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     if (phases & 2)
       CK(c, launch_grouped_gemm_simt(f.dtype, a.base, slot_elems, s.off_down / 2, s.off_down / 2, b_down, s.I, dn, false, st));
   } else {
-    // tensor-bound regime (several 128-token tiles per expert): 2-CTA clusters multicast the weight tiles (B2M_MC2=0 off)
-    // measured: no gain on B200 (L2 already de-duplicates the two CTAs' requests; the SM ingest port is the limit), so
-    // the variant is opt-in: B2M_MC2=1
+    // tensor-bound regime (several 128-token tiles per expert): a 2-CTA cluster variant that multicasts the weight tiles was
+    // measured to give no gain on B200 (L2 already de-duplicates the two CTAs' requests; the SM ingest port is the limit):
+    // compiled only with -DB2M_ENABLE_MC2 (then selected with B2M_MC2=1), not part of the default library
+#ifdef B2M_ENABLE_MC2
     static const bool mc2_on = getenv("B2M_MC2") && getenv("B2M_MC2")[0] == '1';
     const bool mc2 = mc2_on && nt == 128 && T_hint_large;
-    static const bool pdl_k3 = getenv("B2M_PDL_K3") && getenv("B2M_PDL_K3")[0] == '1';
+#else
+    const bool mc2 = false;
+#endif
+    const bool pdl_k3 = sw().pdl_k3;
     // experimental, default off and not yet measured: per-tile MMA width (ragged last token tiles of prefill-sized experts)
-    static const bool dyn_n = getenv("B2M_DYN_N") && getenv("B2M_DYN_N")[0] == '1';
+    const bool dyn_n = sw().dyn_n;
     up.dyn_n = dn.dyn_n = (dyn_n && T_hint_large && !mc2) ? 1 : 0;
     up.pdl_edge = (pdl_k3 && !T_hint_large) ? 1 : 0;
     up.early_a = (c->k3_early_ok && &a == &c->arena && phases == 3) ? 1 : 0;   // routed experts right behind the permute kernel
     if (phases & 1) {
+#ifdef B2M_ENABLE_MC2
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
-      else CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
+      else
+#endif
+      CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, a.tm_gate, a.tm_up, tm_b_up, up, c->num_sms, st));
     }
     if (phases & 2) {
       // prefill-sized token tiles: pair two m-tiles of the down matrix on one token tile (dual_m) -> 1.33x the
@@ -997,14 +1027,17 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       dn.dual_m = pair ? 1 : 0;
       // decode: let the down projection start under the tail of the gate/up GEMM and prefetch its first weight tiles
       // measured on B200 (profiles/r01g_pdl_edges.txt): 12.945 -> 12.855 ms/step; B2M_EARLY_A=0 disables
-      static const bool early_a = !(getenv("B2M_EARLY_A") && getenv("B2M_EARLY_A")[0] == '0');
+      const bool early_a = sw().early_a;
       dn.early_a = (early_a && !pdl_enabled() && (phases & 1) && f.gemm_impl == 0 && !T_hint_large) ? 1 : 0;
       // split-K at decode: equal contiguous shares of all (tile, k-block) units per CTA instead of a fixed factor, so no
       // SM is left with an extra slice in the last wave (B2M_STREAMK=0: fixed factor)
-      static const bool streamk = !(getenv("B2M_STREAMK") && getenv("B2M_STREAMK")[0] == '0');
+      const bool streamk = sw().streamk;
       dn.stream_k = (streamk && dn.ksplit > 1 && !(mc2 && nt_dn == 128)) ? 1 : 0;
+#ifdef B2M_ENABLE_MC2
       if (mc2 && nt_dn == 128) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, pair, a.tm_down_h, a.tm_down_h, tm_b_down, dn, c->num_sms, st));
-      else CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
+      else
+#endif
+      CK(c, launch_grouped_gemm_tc(f.dtype, nt_dn, pair, a.tm_down, a.tm_down, tm_b_down, dn, c->num_sms, st));
     }
   }
   c->stats.kernel_launches += ((phases & 1) ? 1 : 0) + ((phases & 2) ? 1 : 0);
@@ -1262,7 +1295,7 @@ static int combine_impl(b2m_ctx* c, int layer, const void* x, int T, void* out, 
   if (ep_collect) {
     p.ep_collect = 1;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
-    static const bool early_combine = !(getenv("B2M_EP_EARLY_COMBINE") && getenv("B2M_EP_EARLY_COMBINE")[0] == '0');
+    const bool early_combine = sw().ep_early_combine;
     p.ep_early = (c->ep_direct_next && early_combine && !pdl_enabled() && f.shared_inter == 0) ? 1 : 0;
     if (c->tl_next) p.tl = c->tl_next + 12;
   }
@@ -1649,7 +1682,7 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   if (T_local < 1 || T_local * f.top_k > q.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, q.cap);
   if (!out) return fail(c, B2M_EINVAL, "out is null");
   const int El = f.num_experts / q.nranks, R = q.nranks * q.cap, T_total = q.nranks * T_local;
-  static const bool direct_on = !(getenv("B2M_EP_DIRECT") && getenv("B2M_EP_DIRECT")[0] == '0');
+  const bool direct_on = sw().ep_direct;
   // direct mode: the fused route+dispatch kernel needs every CTA resident (T_local <= #SMs)
   const bool direct = direct_on && T_local <= c->num_sms && f.gemm_impl == 0 && f.shared_inter == 0 &&
                       f.router != B2M_ROUTER_SWITCH_TOP1 && f.dtype != B2M_DTYPE_F32;
@@ -1662,7 +1695,7 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
     if (!r) r = b2m_ep_p2p_combine(c, layer, x, T_local, out, stream);
     return r;
   }
-  static const bool timeline = getenv("B2M_TIMELINE") && getenv("B2M_TIMELINE")[0] == '1';
+  const bool timeline = sw().timeline;
   unsigned long long* tl = nullptr;
   if (timeline) {
     if (!c->d_tl) {

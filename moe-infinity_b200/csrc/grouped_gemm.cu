@@ -497,7 +497,9 @@ static cudaError_t dispatch_nt(int nt, bool dual, const CUtensorMap& a0, const C
 #undef B2M_CASE
 }
 
-// 2-CTA multicast variant (prefill: NT = 128, several token tiles per expert); a0/a1 must be the 64-row-box maps
+#ifdef B2M_ENABLE_MC2
+// 2-CTA multicast variant (prefill: NT = 128, several token tiles per expert); a0/a1 must be the 64-row-box maps.
+// Measured: no gain on B200 -> not instantiated in the default build (-DB2M_ENABLE_MC2 brings it back).
 cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& a0h, const CUtensorMap& a1h,
                                        const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st) {
   if (p.E > MAX_E) return cudaErrorInvalidValue;
@@ -507,6 +509,7 @@ cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& 
     return dual ? launch_tc<128, true, DT_F16, 2>(a0h, a1h, b, p, grid, st) : launch_tc<128, false, DT_F16, 2>(a0h, a1h, b, p, grid, st);
   return cudaErrorInvalidValue;
 }
+#endif
 
 cudaError_t launch_grouped_gemm_tc(int dtype, int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1,
                                    const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st) {
