@@ -27,7 +27,7 @@ def test_device_tracer_matches_host_classes(lib_built, L, E, k, B, S):
     from moe_infinity_b200.engine import DeviceExpertTracer
     T = B * S
     eng = _engine(L, E, k, T)
-    cap = 12
+    cap = 8          # capacity == loaded entries: an EMPTY library row has NaN distance and wins the argmin (checked below)
     dev = DeviceExpertTracer(eng, capacity=cap, max_seqs=B)
     rng = np.random.default_rng(L * 100 + E)
     # library: each entry prefers a different subset of experts per layer (clear nearest neighbours)
@@ -79,12 +79,33 @@ def test_device_tracer_matches_host_classes(lib_built, L, E, k, B, S):
                 np.testing.assert_allclose(dev.hint(), want_hint, rtol=1e-5, atol=1e-9)
     assert checked >= B * L                       # the comparison was not vacuous
     assert eng.stats()["host_syncs"] == syncs0    # nothing in the layer path synchronised with the host
-    # finish_entry: the sequence's matrix lands in the first empty library row (8 loaded -> row 8), access count 1
+    # finish_entry with a full library of persistent entries: nothing is replaced on either side
+    before = dev.library(7).copy()
     dev.finish_entry(0)
-    host.finish_entry(seqs[0])
-    np.testing.assert_array_equal(dev.library(8), host.trace_collection[8])
-    assert dev.access_counts()[8] == 1
+    np.testing.assert_array_equal(dev.library(7), before)
     eng.close()
+    # a library with empty rows: the reference's argmin returns the first NaN distance = the first empty row (Q8), on the
+    # host class and on the device alike; finish_entry then fills exactly that row
+    eng2 = _engine(L, E, k, T)
+    dev2 = DeviceExpertTracer(eng2, capacity=cap + 3, max_seqs=B)
+    dev2.load_trace(lib)
+    host2 = M.ExpertTracer(cap + 3, L, E)
+    host2.load_trace(lib)
+    pred2 = M.ExpertPredictor(L, E)
+    pred2.add_tracer(host2)
+    sid = host2.create_entry()
+    logits = torch.randn(T, E, generator=torch.Generator().manual_seed(5))
+    eng2.route(1, x, router_logits=logits.to(torch.bfloat16).cuda())
+    dev2.update_predict(1, num_seqs=B, seq_len=S)
+    idx = eng2.ws("topk_idx", T).cpu().numpy().reshape(B, S, k)
+    m = pred2.predict(sid, idx[0], 1)
+    assert dev2.winner(0) == cap
+    np.testing.assert_allclose(dev2.prediction(0), m, rtol=1e-6, atol=1e-12)
+    dev2.finish_entry(0)
+    host2.finish_entry(sid)
+    np.testing.assert_array_equal(dev2.library(cap), host2.trace_collection[cap])
+    assert dev2.access_counts()[cap] == 1
+    eng2.close()
 
 
 def _distances(tracer, matrix, layer_idx):

@@ -30,7 +30,7 @@ tail -4 "$OUT/${TAG}_configs.log"
 run microbench 300 python tools/route_microbench.py
 cat "$OUT/${TAG}_microbench.log"
 # ncu: launch list of two bench steps (the first ~260 launches are torch weight-init kernels), then a full capture
-run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:b2m -c 400 --csv \
+run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:grouped_gemm|gate_topk|permute_small|combine_kernel|route_' -c 400 --csv \
     --log-file "$OUT/${TAG}_launches.csv" python bench.py --steps 2 --warmup 1
 python tools/ncu_summarize.py launches "$OUT/${TAG}_launches.csv" "$OUT/${TAG}_launches.txt" > /dev/null 2>&1 && cat "$OUT/${TAG}_launches.txt"
 run ncu_full 600 ncu --set full --clock-control none --import-source on -k regex:grouped_gemm_tc_kernel -s 4 -c 2 \
