@@ -107,7 +107,9 @@ typedef struct b2m_config {
                                on the prefetch stream while this layer computes -- the router-logit driven prefetch of the
                                north star; replaces expert_predictor.predict + prefetch_experts (expert_prefetcher.py:42-59)
                                for callers that do not supply their own hints.  1 = only from layers that staged nothing
-                               on demand (the link is idle); 2 = always (costs bandwidth when the link is saturated) */
+                               on demand (the link is idle) and only while the scheduler's own measured accuracy (prefetched
+                               experts used before eviction) stays >= 90 % -- otherwise it suspends itself for 256 layer calls
+                               and probes again; 2 = always (costs bandwidth when the link is saturated) */
   float freq_alpha;         /* B2M_CACHE_ACTIVATION_AWARE: weight of the newest step in the activation average (0 = 0.25) */
 } b2m_config;
 

@@ -205,6 +205,10 @@ struct b2m_ctx {
   // on-demand eviction; a miss evicts exactly one victim iff budget < 1.  Physical slots remain the hard limit.
   long long budget_units = 0;
   int cur_layer = 0;             // layer of the dispatch in progress / last dispatched (next-use distance of the activation-aware policy)
+  // look-ahead prefetch governor: on a link-bound path a wrong prefetch costs a whole expert of bandwidth, so the scheduler
+  // watches its own accuracy (prefetched experts used before eviction vs evicted unused) and suspends itself when it is low
+  unsigned pf_win_useful = 0, pf_win_wasted = 0;
+  long long pf_suspended_until = 0;   // in on-demand layer calls (stats.host_syncs)
   int* d_look = nullptr;         // [E] look-ahead counts: next layer's router applied to this layer's input
   int* h_look = nullptr;         // pinned [E]
   bool look_pending = false;     // the last routing call launched the look-ahead kernel
@@ -403,6 +407,7 @@ void evict(b2m_ctx* c, int id) {
   const int slot = x.slot;
   x.state = ST_HOST;
   x.slot = -1;
+  if (x.prefetched_unused) c->pf_win_wasted++;
   x.prefetched_unused = false;
   c->slots[slot].owner = -1;
   c->h_slot_of[id] = -1;
@@ -1147,7 +1152,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
         if (r) return r;
       } else if (on_demand) {
         c->stats.hits++;
-        if (x.prefetched_unused) { c->stats.prefetch_useful++; x.prefetched_unused = false; }
+        if (x.prefetched_unused) { c->stats.prefetch_useful++; c->pf_win_useful++; x.prefetched_unused = false; }
       }
       if (on_demand) {
         c->stats.dispatches++;
@@ -1202,7 +1207,13 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
   // accurate predictions unconditional prefetching LOST 12 % against the same cache without it.  So (lookahead_prefetch = 1)
   // predictions are staged only from layers that staged nothing on demand, i.e. into link time that is otherwise idle;
   // lookahead_prefetch = 2 prefetches unconditionally (sparse-miss regimes, ablations).
-  if (on_demand && c->last_look_valid && (demand_copies == 0 || c->cfg.lookahead_prefetch >= 2)) {
+  if (c->cfg.lookahead_prefetch == 1 && c->pf_win_useful + c->pf_win_wasted >= 16) {
+    // governor (mode 1 only): below 90 % accuracy prefetching loses on a saturated link -> suspend for 256 layer calls, then probe again
+    if (c->pf_win_useful * 10 < (c->pf_win_useful + c->pf_win_wasted) * 9) c->pf_suspended_until = (long long)c->stats.host_syncs + 256;
+    c->pf_win_useful = c->pf_win_wasted = 0;
+  }
+  const bool pf_suspended = c->cfg.lookahead_prefetch == 1 && (long long)c->stats.host_syncs < c->pf_suspended_until;
+  if (on_demand && c->last_look_valid && !pf_suspended && (demand_copies == 0 || c->cfg.lookahead_prefetch >= 2)) {
     // stage the next layer's predicted experts while this layer computes: most-wanted first; a prediction only displaces
     // an expert whose own next use is expected at least a few layer visits later than the next layer
     const int nxt = (layer + 1) % c->cfg.num_layers;
