@@ -42,7 +42,7 @@ std::string g_create_error;
 // ---- run-time switches: read ONCE per process, here and nowhere else in this file.  Every default is the setting that
 // measured best on a B200 (DESIGN.md §6 has the A/B numbers); the others stay selectable for re-measurement.
 struct Switches {
-  bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, timeline;
+  bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, timeline, fused_ffn;
   long long nt256_min_avg;
   static bool off(const char* n) { const char* v = getenv(n); return v && v[0] == '0'; }   // default on
   static bool on(const char* n) { const char* v = getenv(n); return v && v[0] == '1'; }    // default off
@@ -59,6 +59,7 @@ struct Switches {
         ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
         ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
         timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
+        fused_ffn(!off("B2M_FUSED_FFN")),         // decode: gate/up + down GEMMs of the routed experts in one persistent kernel
         nt256_min_avg(getenv("B2M_NT256_MIN_AVG") ? atoll(getenv("B2M_NT256_MIN_AVG")) : 256) {}
 };
 const Switches& sw() {
@@ -196,6 +197,7 @@ struct b2m_ctx {
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
+  int* d_gbar = nullptr;         // [2] grid barrier of the fused expert-FFN kernel (arrival counter, generation)
   int* d_err = nullptr;          // sticky device error word (RouteParams::err_flag)
   int* h_err = nullptr;          // pinned readback of d_err
   bool k3_early_ok = false;      // offsets of the current routing were published before the permute kernel
@@ -688,6 +690,8 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaMalloc((void**)&c->d_offsets_src, sizeof(int) * (E + 1)));
   CKC(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(int)));       // [0] CTA arrival counter, [1] "row maps published" word (ep_fused)
   CKC(cudaMemset(c->d_ticket, 0, 2 * sizeof(int)));
+  CKC(cudaMalloc((void**)&c->d_gbar, 2 * sizeof(int)));
+  CKC(cudaMemset(c->d_gbar, 0, 2 * sizeof(int)));
   CKC(cudaMalloc((void**)&c->d_err, sizeof(int)));
   CKC(cudaMemset(c->d_err, 0, sizeof(int)));
   CKC(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
@@ -736,7 +740,7 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->arena.owned && c->arena.base) cudaFree(c->arena.base);
   if (c->shared_arena.owned && c->shared_arena.base) cudaFree(c->shared_arena.base);
   void* bufs[] = {c->d_slot_of, c->d_topk_idx, c->d_topk_w, c->d_row_of, c->d_perm_token, c->d_counts, c->d_offsets,
-                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_err, c->d_look, c->d_tl, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
+                  c->d_chunk_counts, c->d_offsets_src, c->d_ticket, c->d_gbar, c->d_err, c->d_look, c->d_tl, c->d_dest_of, c->d_scores, c->d_logits, c->d_xp, c->d_hmid, c->d_y, c->d_hmid_s, c->d_y_s};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int r = 0; r < c->p2p.nranks; ++r)
     if (c->p2p.peer_base[r] && r != c->p2p.rank) cudaIpcCloseMemHandle(c->p2p.peer_base[r]);
@@ -1018,6 +1022,18 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     up.dyn_n = dn.dyn_n = (dyn_n && T_hint_large && !mc2) ? 1 : 0;
     up.pdl_edge = (pdl_k3 && !T_hint_large) ? 1 : 0;
     up.early_a = (c->k3_early_ok && &a == &c->arena && phases == 3) ? 1 : 0;   // routed experts right behind the permute kernel
+    // decode regime, routed experts, both phases in one call: ONE persistent kernel (gate/up phase, grid barrier, down phase)
+    // -- the down GEMM's set-up and first pipeline fill no longer sit on the critical path between two kernels
+    if (sw().fused_ffn && phases == 3 && !T_hint_large && !mc2 && &a == &c->arena && s.dual && nt == nt_dn && nt <= 128 &&
+        !pdl_enabled()) {
+      dn.dual_m = 0;
+      dn.early_a = 1;
+      dn.stream_k = (sw().streamk && dn.ksplit > 1) ? 1 : 0;
+      CK(c, launch_fused_ffn(f.dtype, nt, a.tm_gate, a.tm_up, tm_b_up, a.tm_down, tm_b_down, up, dn, c->num_sms, c->num_sms,
+                             c->d_gbar, st));
+      c->stats.kernel_launches += 1;
+      return B2M_OK;
+    }
     if (phases & 1) {
 #ifdef B2M_ENABLE_MC2
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
@@ -1792,9 +1808,16 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   const int up_tiles = std::min(El, T_total * f.top_k) * ((s.I + 127) / 128);   // expected: every local expert active, one token tile
   const int up_rounds = (up_tiles + c->num_sms - 1) / c->num_sms;
   const int up_grid = std::max(1, std::min(c->num_sms, (up_tiles + up_rounds - 1) / up_rounds));
-  CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
-  CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, q.tm_hmid[ni], dn, c->num_sms, st));
-  c->stats.kernel_launches += 2;
+  if (sw().fused_ffn && s.dual && nt <= 128 && !pdl_enabled()) {
+    dn.early_a = 1;
+    CK(c, launch_fused_ffn(f.dtype, nt, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], c->arena.tm_down, q.tm_hmid[ni], up, dn,
+                           c->num_sms, up_grid, c->d_gbar, st));
+    c->stats.kernel_launches += 1;
+  } else {
+    CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
+    CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, q.tm_hmid[ni], dn, c->num_sms, st));
+    c->stats.kernel_launches += 2;
+  }
   // ---- combine at the source: wait for the owners' "done", read their outputs in place
   c->ep_direct_next = true;
   r = combine_impl(c, layer, x, T_local, out, stream, true);

@@ -79,6 +79,11 @@ cudaError_t launch_grouped_gemm_tc_mc2(int dtype, bool dual, const CUtensorMap& 
                                        const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t st);
 cudaError_t launch_grouped_gemm_simt(int dtype, const void* arena, size_t slot_elems, size_t offA0, size_t offA1,
                                      const void* B, int ldb, const GemmParams& p, bool dual, cudaStream_t st);
+// fused expert FFN (decode regime): gate/up + SwiGLU phase on the first `up_ctas` CTAs, grid barrier (gbar: 2 ints, zero
+// initialised), down phase on all `grid` CTAs.  `dn.early_a` must be 1 (its weights stream before the barrier).
+cudaError_t launch_fused_ffn(int dtype, int nt, const CUtensorMap& gate, const CUtensorMap& upm, const CUtensorMap& b_up,
+                             const CUtensorMap& down, const CUtensorMap& b_down, const GemmParams& up, const GemmParams& dn,
+                             int grid, int up_ctas, int* gbar, cudaStream_t st);
 int gemm_tc_smem_bytes(int nt, bool dual);
 // fp32 experts (dtype int 1): CUDA-core fp32 FMA kernel, f32_path.cu.  Offsets/slot sizes in fp32 elements.
 cudaError_t launch_grouped_gemm_f32(const void* arena, size_t slot_elems, size_t offA0, size_t offA1, const void* B,

@@ -82,14 +82,30 @@ __device__ __forceinline__ int ep_gemm_wait(const GemmParams& p) {
   return want;
 }
 
+// How a phase waits for the data its token operand depends on
+enum : int { DEP_PDL = 0,     // griddepcontrol.wait: the predecessor kernel in the stream (stand-alone launches)
+             DEP_GRID = 1 };  // fused gate/up + down kernel: every CTA of THIS grid has finished the gate/up phase
+struct GridBar {
+  int* word;   // [0] arrival counter, [1] generation (bumped by the last arriver)
+  int gen;     // generation observed at kernel start
+};
+__device__ __forceinline__ void grid_bar_wait(const GridBar& g) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(g.word + 1) : "memory");
+    if (v == g.gen) __nanosleep(20);
+  } while (v == g.gen);
+}
+
+// One grouped GEMM over the device-side tile list: TMA producer / MMA issuer / epilogue warps over a shared-memory ring.
+// Used as the whole body of grouped_gemm_tc_kernel and, twice, by fused_ffn_kernel (gate/up phase, grid barrier, down phase).
+// TMEM is allocated by the caller (tmem_base); `ctas` = how many CTAs of the grid take tiles of this phase.
 template <int NT, bool DUAL, int DT, int MC>
-__global__ void __launch_bounds__((GemmCfg<NT, DUAL>::THREADS), 1)
-grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                       const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB,
+                                          const GemmParams& p, uint8_t* smem, uint32_t tmem_base, int dep_mode,
+                                          const GridBar& gbar, int ctas) {
   using Cfg = GemmCfg<NT, DUAL>;
-  extern __shared__ uint8_t smem_raw[];
   // carve shared memory: [stages | barriers | tmem ptr | tile tables]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;
@@ -111,9 +127,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int m_step = (DUAL && p.dual_m) ? 2 * BLOCK_M : BLOCK_M;
   const int m_tiles = (p.M + m_step - 1) / m_step;
 
-  // ---- one-time setup -------------------------------------------------------------
-  if (p.tl && threadIdx.x == 0) tl_min(p.tl);
-  pdl_launch();
+  // ---- per-phase setup ------------------------------------------------------------
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     if (DUAL) tma_prefetch_desc(&tmA1);
@@ -130,14 +144,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
   // everything above is on-chip; from here on we touch memory earlier kernels produced.  In early_a mode (down projection
   // launched with a programmatic edge behind the gate/up GEMM) only the token-tile loads depend on the predecessor: the
   // producer prefetches weight tiles first and waits later; the routing tables read below are older than the predecessor.
-  if (!p.early_a) pdl_wait();
+  if (!p.early_a && dep_mode == DEP_PDL) pdl_wait();
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
   } else if (p.ep_rows > 0) {
@@ -176,7 +186,6 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   if (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast targets them
 
@@ -185,11 +194,13 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (MC == 1 && p.stream_k) {
     const long long units = (long long)tile_start[E] * kblocks;
     walker.stream = 1;
-    walker.u_cur = (int)(units * blockIdx.x / gridDim.x);
-    walker.u_end = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    walker.u_cur = (int)blockIdx.x < ctas ? (int)(units * blockIdx.x / ctas) : 0;
+    walker.u_end = (int)blockIdx.x < ctas ? (int)(units * (blockIdx.x + 1) / ctas) : 0;
   }
   TileInfo t;
-  const int tile0 = blockIdx.x / MC, tile_stride = gridDim.x / MC;   // tiles are dealt to clusters
+  // tiles are dealt to clusters; in the fused kernel a phase may use fewer CTAs than the grid has (ctas): the rest take none
+  const int tile_stride = ctas / MC;
+  const int tile0 = (int)blockIdx.x < ctas ? (int)blockIdx.x / MC : 0x3fffffff;
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -227,7 +238,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             // tiles follow once it has
             pend_stage[npend] = stage; pend_kb[npend] = kb; pend_row[npend] = t.row0;
             if (++npend == Cfg::STAGES) {
-              pdl_wait();
+              if (dep_mode == DEP_PDL) pdl_wait(); else { grid_bar_wait(gbar); fence_proxy_async_global(); }
               for (int i = 0; i < npend; ++i)
                 tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                             pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -240,7 +251,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         }
       }
       if (!waited) {   // fewer work items than pipeline stages
-        pdl_wait();
+        if (dep_mode == DEP_PDL) pdl_wait(); else { grid_bar_wait(gbar); fence_proxy_async_global(); }
         for (int i = 0; i < npend; ++i)
           tma_load_2d(&tmB, &full_bar[pend_stage[i]], stage_base + pend_stage[i] * Cfg::STAGE_BYTES + (DUAL ? 2 : 1) * A_TILE_BYTES,
                       pend_kb[i] * BLOCK_K, pend_row[i], CACHE_EVICT_LAST);
@@ -248,7 +259,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one lane) =====================
-    if (p.early_a) pdl_wait();
+    if (p.early_a && dep_mode == DEP_PDL) pdl_wait();
     constexpr uint32_t idesc = make_idesc_f16(DT, BLOCK_M, NT);
     int stage = 0;
     uint32_t phase = 0;
@@ -292,7 +303,7 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    if (p.early_a) pdl_wait();
+    if (p.early_a && dep_mode == DEP_PDL) pdl_wait();
     if (p.ep_rows > 0) {
       if (p.ep_zero) {
         // clear the down projection's accumulator: safe now -- a source rank publishes this layer's flag only after its
@@ -378,10 +389,16 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
   }
 
-  // ---- teardown ---------------------------------------------------------------------
-  if (p.ep_signal) __threadfence_system();   // this thread's output stores / reductions before the grid-wide "done" below
+  // ---- end of the phase: every role of this CTA is done with the ring, the barriers and the accumulators
+  if (p.ep_signal) __threadfence_system();   // this thread's output stores / reductions before the grid-wide "done" (gemm_finish)
   tc_fence_before();
   __syncthreads();
+}
+
+// after the last phase of a kernel: timeline, the expert-parallel "done" signal, TMEM release
+template <int MC>
+__device__ __forceinline__ void gemm_finish(const GemmParams& p, uint32_t tmem_base, int tmem_cols) {
+  const int warp = threadIdx.x >> 5;
   if (p.tl && threadIdx.x == 0) tl_max(p.tl + 2);
   if (p.ep_signal && threadIdx.x == 0) {
     // last CTA of the grid: every output of this rank for this layer is in memory -> tell the source ranks, whose combine
@@ -399,8 +416,79 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (MC > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast / commit into its shared memory
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+__device__ __forceinline__ uint8_t* smem_aligned(uint8_t* raw) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+}
+// allocate `cols` TMEM columns (warp 2) and hand the base address to every thread
+__device__ __forceinline__ uint32_t tmem_setup(uint32_t* slot, int cols) {
+  if ((threadIdx.x >> 5) == 2) {
+    tmem_alloc(slot, cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *slot;
+}
+
+template <int NT, bool DUAL, int DT, int MC>
+__global__ void __launch_bounds__((GemmCfg<NT, DUAL>::THREADS), 1)
+grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                       const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<NT, DUAL>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = smem_aligned(smem_raw);
+  if (p.tl && threadIdx.x == 0) tl_min(p.tl);
+  pdl_launch();
+  const uint32_t tmem_base = tmem_setup(&s_tmem, Cfg::TMEM_COLS);
+  GridBar nobar{nullptr, 0};
+  gemm_body<NT, DUAL, DT, MC>(tmA0, tmA1, tmB, p, smem, tmem_base, DEP_PDL, nobar, (int)gridDim.x);
+  gemm_finish<MC>(p, tmem_base, Cfg::TMEM_COLS);
+}
+
+// Fused expert FFN for the HBM-bound (decode) regime: gate/up GEMM + SwiGLU, grid-wide barrier, down GEMM in ONE persistent
+// kernel.  What it removes from every layer: a kernel boundary on the critical path -- the down GEMM's CTAs could only become
+// resident when the gate/up CTAs had left their SMs (both want all shared memory), so its TMEM/barrier set-up, tile tables and
+// first pipeline fill were exposed (measured ~15 us per layer at every N, profiles/r02_ep*_timeline_regions.log).  Here the
+// CTA keeps its resources, re-arms its barriers, starts streaming the down projection's weights at once and only its token
+// tiles wait for the grid barrier.  Needs every CTA resident (persistent grid <= #SMs, one CTA per SM: true by construction)
+// and no second barrier-kernel running beside it.
+template <int NT, int DT>
+__global__ void __launch_bounds__((GemmCfg<NT, true>::THREADS), 1)
+fused_ffn_kernel(const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ CUtensorMap tmUp,
+                 const __grid_constant__ CUtensorMap tmBup, const __grid_constant__ CUtensorMap tmDown,
+                 const __grid_constant__ CUtensorMap tmBdn, const GemmParams up, const GemmParams dn, int* gbar_word,
+                 int up_ctas) {
+  using CfgU = GemmCfg<NT, true>;
+  using CfgD = GemmCfg<NT, false>;
+  constexpr int TMEM_COLS = CfgU::TMEM_COLS > CfgD::TMEM_COLS ? CfgU::TMEM_COLS : CfgD::TMEM_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_gen;
+  uint8_t* smem = smem_aligned(smem_raw);
+  if (up.tl && threadIdx.x == 0) tl_min(up.tl);
+  pdl_launch();
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile int*>(gbar_word + 1);   // moves only after every CTA of this grid arrived
+  const uint32_t tmem_base = tmem_setup(&s_tmem, TMEM_COLS);
+  GridBar gb{gbar_word, s_gen};
+  gemm_body<NT, true, DT, 1>(tmGate, tmUp, tmBup, up, smem, tmem_base, DEP_PDL, gb, up_ctas);
+  if (threadIdx.x == 0) {
+    if (up.tl) tl_max(up.tl + 2);
+    if (dn.tl) tl_min(dn.tl);
+    __threadfence();                       // this CTA's intermediate rows (all threads, ordered by the barrier that ended the phase)
+    if (atomicAdd(gbar_word, 1) == (int)gridDim.x - 1) {
+      gbar_word[0] = 0;
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gbar_word + 1), "r"(gb.gen + 1) : "memory");
+    }
+  }
+  gemm_body<NT, false, DT, 1>(tmDown, tmDown, tmBdn, dn, smem, tmem_base, DEP_GRID, gb, (int)gridDim.x);
+  gemm_finish<1>(dn, tmem_base, TMEM_COLS);
 }
 
 // --------------------------------------------------------------------------------------
@@ -477,6 +565,45 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
   }
   if (MC > 1) grid -= grid % MC;
   return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, p.early_a != 0 || p.pdl_edge != 0, a0, a1, b, p);
+}
+
+template <int NT, int DT>
+static cudaError_t launch_fused(const CUtensorMap& g, const CUtensorMap& u, const CUtensorMap& bup, const CUtensorMap& d,
+                                const CUtensorMap& bdn, const GemmParams& up, const GemmParams& dn, int grid, int up_ctas,
+                                int* gbar, cudaStream_t st) {
+  using CfgU = GemmCfg<NT, true>;
+  using CfgD = GemmCfg<NT, false>;
+  constexpr int SMEM = CfgU::SMEM_BYTES > CfgD::SMEM_BYTES ? CfgU::SMEM_BYTES : CfgD::SMEM_BYTES;
+  auto kern = fused_ffn_kernel<NT, DT>;
+  static bool attr_done = false;   // per-instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_cluster(kern, dim3(grid), dim3(CfgU::THREADS), (size_t)SMEM, st, 1, up.early_a != 0 || up.pdl_edge != 0, g, u, bup, d,
+                        bdn, up, dn, gbar, up_ctas);
+}
+
+// gate/up + SwiGLU and down projection of the routed experts in one persistent kernel (decode regime: nt <= 128, dual gate/up)
+cudaError_t launch_fused_ffn(int dtype, int nt, const CUtensorMap& g, const CUtensorMap& u, const CUtensorMap& bup,
+                             const CUtensorMap& d, const CUtensorMap& bdn, const GemmParams& up, const GemmParams& dn, int grid,
+                             int up_ctas, int* gbar, cudaStream_t st) {
+  if (up.E > MAX_E || grid < 1 || up_ctas < 1 || up_ctas > grid || !gbar) return cudaErrorInvalidValue;
+#define B2M_FCASE(N)                                                                                         \
+  case N:                                                                                                    \
+    return dtype == DT_BF16 ? launch_fused<N, DT_BF16>(g, u, bup, d, bdn, up, dn, grid, up_ctas, gbar, st)   \
+                            : launch_fused<N, DT_F16>(g, u, bup, d, bdn, up, dn, grid, up_ctas, gbar, st);
+  if (dtype != DT_BF16 && dtype != DT_F16) return cudaErrorInvalidValue;
+  switch (nt) {
+    B2M_FCASE(16)
+    B2M_FCASE(32)
+    B2M_FCASE(64)
+    B2M_FCASE(128)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef B2M_FCASE
 }
 
 template <int DT>

@@ -174,6 +174,13 @@ cudaError_t launch_trace_update_predict(const TraceParams& p, int num_seqs, cuda
   return cudaSuccess;
 }
 cudaError_t launch_trace_finish(const TraceParams&, int seq_slot, cudaStream_t) { logf("trace_finish slot=%d", seq_slot); return cudaSuccess; }
+cudaError_t launch_fused_ffn(int, int nt, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                             const CUtensorMap&, const GemmParams& up, const GemmParams& dn, int grid, int up_ctas, int* gbar,
+                             cudaStream_t) {
+  if (!gbar || !dn.early_a) return cudaErrorInvalidValue;
+  log_gemm("fused", nt, true, up, up_ctas);     // one launch, two phases: logged as two gemm lines so the planning tests read both
+  return log_gemm("fused", nt, false, dn, grid);
+}
 int gemm_tc_smem_bytes(int, bool) { return 200 * 1024; }
 
 cudaError_t launch_combine(const CombineParams& p, cudaStream_t) {
