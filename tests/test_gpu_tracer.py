@@ -60,6 +60,7 @@ def test_device_tracer_matches_host_classes(lib_built, L, E, k, B, S):
             dev.update_predict(l, num_seqs=B, seq_len=S)
             idx = eng.ws("topk_idx", T).cpu().numpy().reshape(B, S, k)
             want_hint = np.zeros((L, E), dtype=np.float64)
+            hint_ok = True
             for b in range(B):
                 m = pred.predict(seqs[b], idx[b], l)                      # host: update_entry + find_most_similar + decay
                 np.testing.assert_array_equal(dev.entry(b), host.get_entry(seqs[b]).matrix.astype(np.float32))
@@ -73,9 +74,8 @@ def test_device_tracer_matches_host_classes(lib_built, L, E, k, B, S):
                     checked += 1
                     want_hint += m
                 else:
-                    want_hint = None
-                    break
-            if want_hint is not None:
+                    hint_ok = False          # near-tie between two library entries: the device may legitimately pick the other
+            if hint_ok:
                 np.testing.assert_allclose(dev.hint(), want_hint, rtol=1e-5, atol=1e-9)
     assert checked >= B * L                       # the comparison was not vacuous
     assert eng.stats()["host_syncs"] == syncs0    # nothing in the layer path synchronised with the host
