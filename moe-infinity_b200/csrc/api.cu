@@ -59,7 +59,7 @@ struct Switches {
         ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
         ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
         timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
-        fused_ffn(on("B2M_FUSED_FFN")),           // gate/up + down GEMMs of the routed experts in one persistent kernel: measured
+        fused_ffn(on("B2M_FUSED_FFN")),           // (only in -DB2M_ENABLE_FUSED_FFN builds) gate/up + down GEMMs in one persistent kernel: measured
                                                   // 12.89 vs 12.84 ms/step (Mixtral) and 5.04 vs 4.75 ms (DeepSeek: it keeps the
                                                   // side-stream shared-expert GEMMs off the SMs) -> opt-in
         nt256_min_avg(getenv("B2M_NT256_MIN_AVG") ? atoll(getenv("B2M_NT256_MIN_AVG")) : 256) {}
@@ -1026,6 +1026,7 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
     up.early_a = (c->k3_early_ok && &a == &c->arena && phases == 3) ? 1 : 0;   // routed experts right behind the permute kernel
     // decode regime, routed experts, both phases in one call: ONE persistent kernel (gate/up phase, grid barrier, down phase)
     // -- the down GEMM's set-up and first pipeline fill no longer sit on the critical path between two kernels
+#ifdef B2M_ENABLE_FUSED_FFN
     if (sw().fused_ffn && phases == 3 && !T_hint_large && !mc2 && &a == &c->arena && s.dual && nt == nt_dn && nt <= 128 &&
         !pdl_enabled()) {
       dn.dual_m = 0;
@@ -1036,6 +1037,7 @@ static int launch_expert_gemms(b2m_ctx* c, Arena& a, const GemmParams& base, con
       c->stats.kernel_launches += 1;
       return B2M_OK;
     }
+#endif
     if (phases & 1) {
 #ifdef B2M_ENABLE_MC2
       if (mc2) CK(c, launch_grouped_gemm_tc_mc2(f.dtype, s.dual, a.tm_gate_h, a.tm_up_h, tm_b_up, up, c->num_sms, st));
@@ -1810,12 +1812,15 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   const int up_tiles = std::min(El, T_total * f.top_k) * ((s.I + 127) / 128);   // expected: every local expert active, one token tile
   const int up_rounds = (up_tiles + c->num_sms - 1) / c->num_sms;
   const int up_grid = std::max(1, std::min(c->num_sms, (up_tiles + up_rounds - 1) / up_rounds));
+#ifdef B2M_ENABLE_FUSED_FFN
   if (sw().fused_ffn && s.dual && nt <= 128 && !pdl_enabled()) {
     dn.early_a = 1;
     CK(c, launch_fused_ffn(f.dtype, nt, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], c->arena.tm_down, q.tm_hmid[ni], up, dn,
                            c->num_sms, up_grid, c->d_gbar, st));
     c->stats.kernel_launches += 1;
-  } else {
+  } else
+#endif
+  {
     CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
     CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, q.tm_hmid[ni], dn, c->num_sms, st));
     c->stats.kernel_launches += 2;

@@ -390,7 +390,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtenso
   }
 
   // ---- end of the phase: every role of this CTA is done with the ring, the barriers and the accumulators
-  if (p.ep_signal) __threadfence_system();   // this thread's output stores / reductions before the grid-wide "done" (gemm_finish)
   tc_fence_before();
   __syncthreads();
 }
@@ -401,16 +400,17 @@ __device__ __forceinline__ void gemm_finish(const GemmParams& p, uint32_t tmem_b
   const int warp = threadIdx.x >> 5;
   if (p.tl && threadIdx.x == 0) tl_max(p.tl + 2);
   if (p.ep_signal && threadIdx.x == 0) {
-    // last CTA of the grid: every output of this rank for this layer is in memory -> tell the source ranks, whose combine
-    // kernels read the rows in place over NVLink
+    // the CTA's output stores / reductions (all threads, ordered before this point by the barrier that ended the phase) become
+    // visible system-wide with ONE fence (fences are cumulative); the last CTA of the grid then tells the source ranks, whose
+    // combine kernels read the rows in place over NVLink
+    __threadfence_system();
     if (atomicAdd(p.ep_done_ctr, 1) == (int)gridDim.x - 1) {
       __threadfence_system();
       *p.ep_done_ctr = 0;
       for (int le = 0; le < p.ep_el; ++le) p.ep_cnt[le] = 0;   // every CTA has read the counts: regions are free for the next layer
       const int e = *p.ep_done_epoch + 1;
       *p.ep_done_epoch = e;
-      __threadfence_system();
-      for (int r = 0; r < p.ep_nranks; ++r) st_release_sys(p.ep_peer_done_flag[r] + p.ep_rank, e);
+      for (int r = 0; r < p.ep_nranks; ++r) st_release_sys(p.ep_peer_done_flag[r] + p.ep_rank, e);   // release orders the stores above
     }
   }
   if (MC > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast / commit into its shared memory
@@ -451,6 +451,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   gemm_finish<MC>(p, tmem_base, Cfg::TMEM_COLS);
 }
 
+#ifdef B2M_ENABLE_FUSED_FFN
+// (Experiment, measured and NOT part of the default library: Mixtral decode 12.89 vs 12.84 ms/step, DeepSeek-V2-Lite decode
+// 5.04 vs 4.75 ms/step -- a persistent barrier kernel keeps the side-stream shared-expert GEMMs off the SMs --, expert
+// parallel N=2 8.51 vs 8.47 ms/step; profiles/r02c_*.json.  Build with -DB2M_ENABLE_FUSED_FFN and run with B2M_FUSED_FFN=1.)
 // Fused expert FFN for the HBM-bound (decode) regime: gate/up GEMM + SwiGLU, grid-wide barrier, down GEMM in ONE persistent
 // kernel.  What it removes from every layer: a kernel boundary on the critical path -- the down GEMM's CTAs could only become
 // resident when the gate/up CTAs had left their SMs (both want all shared memory), so its TMEM/barrier set-up, tile tables and
@@ -490,6 +494,8 @@ fused_ffn_kernel(const __grid_constant__ CUtensorMap tmGate, const __grid_consta
   gemm_body<NT, false, DT, 1>(tmDown, tmDown, tmBdn, dn, smem, tmem_base, DEP_GRID, gb, (int)gridDim.x);
   gemm_finish<1>(dn, tmem_base, TMEM_COLS);
 }
+
+#endif  // B2M_ENABLE_FUSED_FFN
 
 // --------------------------------------------------------------------------------------
 // Plain CUDA-core grouped GEMM with identical semantics (debug / bring-up cross-check only;
@@ -567,6 +573,7 @@ static cudaError_t launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const
   return launch_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, MC, p.early_a != 0 || p.pdl_edge != 0, a0, a1, b, p);
 }
 
+#ifdef B2M_ENABLE_FUSED_FFN
 template <int NT, int DT>
 static cudaError_t launch_fused(const CUtensorMap& g, const CUtensorMap& u, const CUtensorMap& bup, const CUtensorMap& d,
                                 const CUtensorMap& bdn, const GemmParams& up, const GemmParams& dn, int grid, int up_ctas,
@@ -605,6 +612,8 @@ cudaError_t launch_fused_ffn(int dtype, int nt, const CUtensorMap& g, const CUte
   }
 #undef B2M_FCASE
 }
+
+#endif  // B2M_ENABLE_FUSED_FFN
 
 template <int DT>
 static cudaError_t dispatch_nt(int nt, bool dual, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
