@@ -117,16 +117,27 @@ class prefetch_handle:  # noqa: N801  (reference spelling)
             return -1
         return self._dispatcher.engine.device.index if self._dispatcher.engine.is_resident(*le) else -1
 
-    # ---- dense-parameter path (begin/end hooks): weights simply live on the device
+    # ---- dense-parameter path (begin/end hooks, model_offload.py:904-991 -> archer_prefetch_handle.cpp:83-180): static
+    # placement -- a dense tensor is uploaded ONCE, on its first `begin`, and stays resident; later begins only find it already
+    # in place (the reference re-points .data on every begin and puts a 1-element placeholder back on every end)
     def begin(self, request_id: int, tensor: torch.Tensor):
-        tid = self._ptr2id.get(tensor.data_ptr())
-        if tid is not None and tid in self._tensors:
+        ptr = tensor.data_ptr()
+        tid = self._ptr2id.get(ptr)
+        if tid is None or tid not in self._tensors:
+            return
+        dev_t = self._dense_dev.get(tid) if hasattr(self, "_dense_dev") else None
+        if dev_t is None:
+            if not hasattr(self, "_dense_dev"):
+                self._dense_dev = {}
             dev = torch.device("cuda", self.get_node_default_device([tid]))
-            tensor.data = self._tensors[tid].to(dev)
-            self._ptr2id[tensor.data_ptr()] = tid
+            dev_t = self._tensors[tid].to(dev)
+            self._dense_dev[tid] = dev_t
+        if ptr != dev_t.data_ptr():
+            tensor.data = dev_t
+            self._ptr2id[dev_t.data_ptr()] = tid
 
     def end(self, request_id: int, tensor: torch.Tensor):
-        return None
+        return None          # stays resident: nothing to release
 
     def fetch_tensors(self, request_id: int, tensor_ids: Sequence[int]):
         return None

@@ -127,3 +127,24 @@ def test_switch_block_golden(lib_built):
     stable = (logits.cpu().reshape(-1, c["E"]) - fx["router_logits"].reshape(-1, c["E"])).abs().max(-1).values < 1e-4
     assert torch.equal(expert_index.cpu().flatten()[stable], fx["expert_index"].flatten()[stable])
     hidden_close(out, fx["out"], None, c["dtype"], "switch block")
+
+
+def test_dense_parameter_begin_is_static_placement(lib_built):
+    """prefetch_handle.begin/end (model_offload.py:904-991 hooks): the dense tensor is uploaded on its first begin and stays
+    resident -- later begins are free (same device storage), end releases nothing."""
+    from moe_infinity_b200.compat import prefetch_handle
+    h = prefetch_handle("/tmp/b2m_dense_unused", 0.5)
+    w = torch.randn(64, 32)
+    h.offload(w, 7)
+    placeholder = torch.zeros(1)
+    h.register(placeholder, 7)
+    h.begin(0, placeholder)
+    assert placeholder.is_cuda and torch.equal(placeholder.cpu(), w)
+    p0 = placeholder.data_ptr()
+    h.end(0, placeholder)
+    h.begin(1, placeholder)
+    assert placeholder.data_ptr() == p0          # no second upload
+    other = torch.zeros(1)
+    h.register(other, 7)                          # the same tensor id reached through another placeholder: same storage
+    h.begin(2, other)
+    assert other.data_ptr() == p0
