@@ -16,11 +16,13 @@ pin is made from outputs of the reference itself run in the dev container:
   (a) expert FFN (D1-D3): the reference's OWN core/parallel/expert_module.cpp is compiled as-is into
       oracle/_ref/ref_expert_module.so (oracle/ref_build/Makefile); tests/test_oracle_expert_ref.py demands bit equality
       of `expert_ffn` with it for all six expert types x three dtypes, live and through tests/golden/expert_ffn_ref.pt;
-  (b) routing / mask build / combine (A1-A5, G1-G2): the literal reference block files (mixtral.py, deepseek.py, MoEGate)
-      are executed on CPU through tests/shims/ref_loader.py; tests/test_oracle_golden.py demands bit equality with this
-      module and tests/golden/*.pt hold their outputs (tests/golden/make_golden.py);
-  (c) Switch routing (A6) is **parity unpinned**: HF 5.5's router signature differs from the 4.x one the reference
-      block expects, so the literal block cannot run here; its fixtures come from this restatement only.
+  (b) routing / mask build / combine (A1-A6, G1-G2): the literal reference block files (mixtral.py, deepseek.py, MoEGate,
+      switch_transformers.py) are executed on CPU through tests/shims/ref_loader.py -- from /root/reference, or from their
+      byte-compiled staging oracle/_ref/pyref where that tree does not exist; tests/test_oracle_golden.py demands bit equality
+      with this module and tests/golden/*.pt hold their outputs (tests/golden/make_golden.py).  The Switch block runs on a
+      4.x-order router shim (HF 5.5's router returns another tuple), which restates the transformers 4.x forward;
+  (c) cache policy: oracle/policy_oracle.py is pinned on a trace recorded from the reference's real engine
+      (tests/golden/policy_ref_trace.json, tools/ref_engine_harness.py --mode policy on a B200).
 
 Determinism choices (the reference itself is nondeterministic):
   * experts are combined in ascending expert id (reference: thread completion order,
