@@ -42,7 +42,7 @@ std::string g_create_error;
 // ---- run-time switches: read ONCE per process, here and nowhere else in this file.  Every default is the setting that
 // measured best on a B200 (DESIGN.md §6 has the A/B numbers); the others stay selectable for re-measurement.
 struct Switches {
-  bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, timeline, fused_ffn;
+  bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, ep_mrows, timeline, fused_ffn;
   long long nt256_min_avg;
   static bool off(const char* n) { const char* v = getenv(n); return v && v[0] == '0'; }   // default on
   static bool on(const char* n) { const char* v = getenv(n); return v && v[0] == '1'; }    // default off
@@ -57,6 +57,7 @@ struct Switches {
         early_a(!off("B2M_EARLY_A")),             // down GEMM prefetches weights under the gate/up GEMM's tail
         streamk(!off("B2M_STREAMK")),             // stream-K partition of the split-K down GEMM
         ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
+        ep_mrows(!off("B2M_EP_MROWS")),
         ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
         timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
         fused_ffn(on("B2M_FUSED_FFN")),           // (only in -DB2M_ENABLE_FUSED_FFN builds) gate/up + down GEMMs in one persistent kernel: measured
@@ -196,6 +197,8 @@ struct b2m_ctx {
     CUtensorMap tm_recv[5];             // the direct receive area as the token operand of the gate/up GEMM: [E*cap rows][H]
     void* d_hmid = nullptr;             // direct mode intermediate [E*cap rows][I] (local, same row indexing as the receive area)
     CUtensorMap tm_hmid[5];
+    int m_rows = 0;                     // weight rows per gate/up tile in direct mode (0 = not planned yet), see plan_ep_m_rows
+    CUtensorMap tm_gate_r, tm_up_r;     // gate/up weight maps with a box of m_rows rows
   } p2p;
   int* d_offsets_src = nullptr;  // [E+1]
   int* d_ticket = nullptr;       // CTA arrival counter of the small-T gate/top-k kernel
@@ -1708,7 +1711,7 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   if (r) return r;
   r = check_layer(c, layer);
   if (r) return r;
-  const b2m_ctx::P2P& q = c->p2p;
+  b2m_ctx::P2P& q = c->p2p;
   const b2m_config& f = c->cfg;
   if (T_local < 1 || T_local * f.top_k > q.cap) return fail(c, B2M_EINVAL, "T_local=%d: T_local*top_k exceeds cap=%d", T_local, q.cap);
   if (!out) return fail(c, B2M_EINVAL, "out is null");
@@ -1809,7 +1812,28 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   // The tile list is static here, so the grid can be sized to it: with 448 tiles (4 experts x 112) on 148 CTAs the last 4
   // tiles run alone and are limited by what one SM can ingest (~120 GB/s; measured 17 us of a 162 us kernel,
   // profiles/r02_ep2_timeline_before.log); 112 CTAs x 4 tiles each finish together at the full HBM rate.
-  const int up_tiles = std::min(El, T_total * f.top_k) * ((s.I + 127) / 128);   // expected: every local expert active, one token tile
+  // Weight rows per tile: 128-row tiles cut I = 14336 into 112 tiles per expert, which leaves 36 of 148 SMs idle when a rank
+  // owns one expert (N = 8) and a 128-row tile is bound by what one SM ingests (profiles/r02_ep8_timeline.log).  Tiles of
+  // m_rows = roundup8(El*I / (SMs * rounds)) rows (104 -> 138 tiles per expert) put every SM to work; the MMA stays M = 128.
+  if (!q.m_rows) {
+    q.m_rows = 128;
+    if (sw().ep_mrows && s.dual) {
+      const long long rows_total = (long long)El * s.I;
+      const long long rounds = (rows_total + 128LL * c->num_sms - 1) / (128LL * c->num_sms);
+      int mr = (int)((rows_total + c->num_sms * rounds - 1) / (c->num_sms * rounds));
+      mr = std::min(128, (mr + 7) & ~7);
+      while (mr < 128 && (long long)El * ((s.I + mr - 1) / mr) > c->num_sms * rounds) mr += 8;
+      if (mr >= 64 && mr < 128) {
+        CUtensorMap unused;
+        r = build_arena_maps_box(c, &c->arena, (uint32_t)mr, &q.tm_gate_r, &q.tm_up_r, &unused);
+        if (r) return r;
+        q.m_rows = mr;
+      }
+    }
+  }
+  const bool mrows = q.m_rows < 128 && !sw().fused_ffn;   // (the opt-in fused kernel keeps the 128-row maps)
+  if (mrows) up.m_rows = q.m_rows;
+  const int up_tiles = std::min(El, T_total * f.top_k) * ((s.I + q.m_rows - 1) / q.m_rows);   // expected: every local expert active, one token tile
   const int up_rounds = (up_tiles + c->num_sms - 1) / c->num_sms;
   const int up_grid = std::max(1, std::min(c->num_sms, (up_tiles + up_rounds - 1) / up_rounds));
 #ifdef B2M_ENABLE_FUSED_FFN
@@ -1821,7 +1845,8 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
   } else
 #endif
   {
-    CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, c->arena.tm_gate, c->arena.tm_up, q.tm_recv[ni], up, up_grid, st));
+    CK(c, launch_grouped_gemm_tc(f.dtype, nt, s.dual, mrows ? q.tm_gate_r : c->arena.tm_gate, mrows ? q.tm_up_r : c->arena.tm_up,
+                                 q.tm_recv[ni], up, up_grid, st));
     CK(c, launch_grouped_gemm_tc(f.dtype, nt, false, c->arena.tm_down, c->arena.tm_down, q.tm_hmid[ni], dn, c->num_sms, st));
     c->stats.kernel_launches += 2;
   }

@@ -55,6 +55,7 @@ struct GemmParams {
   // area itself.  Every local expert owns a region of ep_rows = nranks*cap rows (its worst case); the source ranks claim rows
   // in it from the front with (remote) atomics on ep_cnt[local expert], so the rows of an expert are contiguous and the tile
   // width follows the actual count -- no regroup kernel, no host involvement.
+  int m_rows;                // 0 = 128; else weight rows per tile (A maps carry that box), see gemm_body
   int ep_rows;               // 0 = off; else rows per expert region
   int ep_first;              // first global expert id owned by this rank
   int ep_el;                 // experts per rank

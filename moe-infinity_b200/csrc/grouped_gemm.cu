@@ -124,7 +124,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtenso
   const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   // dual_m: the two A tiles are rows [m0, m0+128) and [m0+128, m0+256) of the SAME matrix sharing one token tile
   // (doubles the arithmetic intensity of the down projection at prefill; the kernel is L2->SM operand-bandwidth bound)
-  const int m_step = (DUAL && p.dual_m) ? 2 * BLOCK_M : BLOCK_M;
+  // m_rows (EP region mode, MC == 1): weight rows a tile really covers (a multiple of 8, <= 128; the A tensor maps carry a box of
+  // that many rows).  The MMA still runs M = 128; the tail rows of the stage hold stale bytes and their accumulator lanes are
+  // dropped in the epilogue.  Lets the host cut I rows into as many tiles as there are SMs (14336 / 104 = 138 <= 148).
+  const int m_rows = (MC == 1 && !p.dual_m && p.m_rows > 0) ? p.m_rows : BLOCK_M;
+  const int m_step = (DUAL && p.dual_m) ? 2 * BLOCK_M : m_rows;
   const int m_tiles = (p.M + m_step - 1) / m_step;
 
   // ---- per-phase setup ------------------------------------------------------------
@@ -215,7 +219,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtenso
           uint8_t* sA0 = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* sA1 = sA0 + A_TILE_BYTES;
           uint8_t* sB = sA0 + (DUAL ? 2 : 1) * A_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], (DUAL ? 2 : 1) * m_rows * BLOCK_K * 2 + Cfg::B_TILE_BYTES);
           // decode: weights are streamed exactly once -> evict-first.  Several n-tiles per expert (prefill): the same
           // weight tile is re-read by every n-tile -> keep it in L2.  Tokens are re-read by every m-tile: keep.
           const uint64_t wh = ((p.ep_rows > 0 ? cnts[t.e] : offs[t.e + 1] - offs[t.e]) <= NT) ? CACHE_EVICT_FIRST : CACHE_EVICT_NORMAL;
@@ -325,7 +329,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtenso
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
       const int m = t.m0 + r;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < p.M && r < m_rows;
       float bias0 = 0.f, bias1 = 0.f;   // bias experts: one value per weight row = per TMEM lane
       if (p.bias_base) {
         const uint16_t* bp = reinterpret_cast<const uint16_t*>(p.bias_base) + (size_t)t.slot * p.bias_slot_elems + p.bias_off;
