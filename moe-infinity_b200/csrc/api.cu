@@ -43,6 +43,7 @@ std::string g_create_error;
 // measured best on a B200 (DESIGN.md §6 has the A/B numbers); the others stay selectable for re-measurement.
 struct Switches {
   bool nt256, nt256_up, pdl, early_k3, rows_by_gate, pdl_k3, dyn_n, early_a, streamk, ep_early_combine, ep_direct, ep_mrows, timeline, fused_ffn;
+  int ep_l2pf_mb;
   long long nt256_min_avg;
   static bool off(const char* n) { const char* v = getenv(n); return v && v[0] == '0'; }   // default on
   static bool on(const char* n) { const char* v = getenv(n); return v && v[0] == '1'; }    // default off
@@ -58,6 +59,7 @@ struct Switches {
         streamk(!off("B2M_STREAMK")),             // stream-K partition of the split-K down GEMM
         ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
         ep_mrows(!off("B2M_EP_MROWS")),
+        ep_l2pf_mb(getenv("B2M_EP_L2PF_MB") ? atoi(getenv("B2M_EP_L2PF_MB")) : 64),
         ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
         timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
         fused_ffn(on("B2M_FUSED_FFN")),           // (only in -DB2M_ENABLE_FUSED_FFN builds) gate/up + down GEMMs in one persistent kernel: measured
@@ -932,6 +934,7 @@ static int route_impl(b2m_ctx* c, int layer, const void* x, const void* router_i
     p.ep_dispatch = 1;
     p.tl = c->tl_next;
     p.ep = c->ep_direct_next ? ep_p2p_params_direct(c) : ep_p2p_params(c);
+    if (c->ep_direct_next && sw().ep_l2pf_mb > 0 && !pdl_enabled()) p.pdl_edge = 1;   // lets the gate/up GEMM's CTAs arrive (and prefetch) early
     if (c->ep_direct_next) p.ep_fused = 1;   // one launch: gate/top-k + row claim (remote atomics) + row stores + signal
     p.y_zero = nullptr;        // the regroup kernel (direct mode: the owner's gate/up GEMM) clears the accumulator
   }
@@ -1830,6 +1833,12 @@ int b2m_ep_p2p_layer(b2m_ctx* c, int layer, const void* x, const void* router_in
         q.m_rows = mr;
       }
     }
+  }
+  {
+    // L2 prefetch budget (MB, both GEMMs) spread over the tiles each kernel expects to own: k-blocks per tile
+    const double up_kb_bytes = (double)El * ((s.I + q.m_rows - 1) / q.m_rows) * (s.dual ? 2 : 1) * q.m_rows * 128.0;
+    up.ep_l2pf = !pdl_enabled() ? std::max(0, (int)(sw().ep_l2pf_mb * 1e6 / up_kb_bytes)) : 0;
+    if (up.ep_l2pf > 0) up.pdl_edge = 1;   // resident behind the routing kernel (which has an edge behind the previous combine)
   }
   const bool mrows = q.m_rows < 128 && !sw().fused_ffn;   // (the opt-in fused kernel keeps the 128-row maps)
   if (mrows) up.m_rows = q.m_rows;

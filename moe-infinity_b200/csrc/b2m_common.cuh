@@ -111,6 +111,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
 
 // multicast variant: the box lands at the same shared-memory offset in every CTA of `cta_mask` and completes bytes on
 // the mbarrier at the same offset in each of them
+// L2 prefetch of one box (a hint: no shared memory, no barrier, nothing to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1, int c2,
                                                uint16_t cta_mask, uint64_t hint) {
   asm volatile(

@@ -56,6 +56,7 @@ struct GemmParams {
   // in it from the front with (remote) atomics on ep_cnt[local expert], so the rows of an expert are contiguous and the tile
   // width follows the actual count -- no regroup kernel, no host involvement.
   int m_rows;                // 0 = 128; else weight rows per tile (A maps carry that box), see gemm_body
+  int ep_l2pf;               // direct mode: k-blocks of every expected weight tile to prefetch into L2 before the flag wait
   int ep_rows;               // 0 = off; else rows per expert region
   int ep_first;              // first global expert id owned by this rank
   int ep_el;                 // experts per rank
@@ -167,6 +168,7 @@ struct RouteParams {
                              // kernel only copies rows (no redundant ranking in each of its CTAs)
   int offsets_early;         // small-T path: the last gate/top-k CTA already publishes counts/offsets (so the gate/up GEMM can
                              // start fetching weights while the permute kernel is still gathering rows)
+  int pdl_edge;              // ep_fused: launch with a programmatic edge behind the previous layer's combine (the kernel waits before any access)
   int ep_fused;              // ep_dispatch in direct mode with T <= #SMs: the gate/top-k kernel also permutes + dispatches (one launch)
   int* ready;                // ep_fused: word the last gate/top-k CTA releases (value = local dispatch epoch + 1) once the row maps are out
   int ep_dispatch;           // 1 (T <= 256 only): gathered rows go straight to the owning ranks' buffers (ep)

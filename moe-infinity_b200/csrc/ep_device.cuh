@@ -8,6 +8,13 @@ namespace b2m {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Flag store of a release SEQUENCE: the caller has issued one __threadfence_system() after its last payload store; the flag
+// stores to the N peers are then relaxed, so they leave back to back.  (N st.release.sys in a row cost N NVLink round trips:
+// each one is a system fence that waits for the previous peer's flag store to be acknowledged -- measured ~20 us of a 129 us
+// layer at N = 8, profiles/r02e_ep8_timeline.json.)
+__device__ __forceinline__ void st_relaxed_sys(int* p, int v) {
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -19,12 +26,11 @@ __device__ __forceinline__ void p2p_signal(const EpParams& p, int which /*0 disp
   if (threadIdx.x != 0) return;
   __threadfence_system();          // ... which makes them visible system-wide (fences are cumulative): one fence per CTA
   if (atomicAdd(p.done_ctr + which, 1) != (int)gridDim.x - 1) return;
-  __threadfence_system();          // last arriver: the other CTAs' (fenced) stores happen-before everything below
   p.done_ctr[which] = 0;
   const int e = p.epoch[which] + 1;
   p.epoch[which] = e;
-  for (int r = 0; r < p.nranks; ++r)                          // st.release orders the stores above before the flag
-    st_release_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
+  __threadfence_system();          // last arriver: the other CTAs' (fenced) stores happen-before the flags (fence cumulativity)
+  for (int r = 0; r < p.nranks; ++r) st_relaxed_sys((which ? p.peer_back_flag[r] : p.peer_recv_flag[r]) + p.rank, e);
 }
 // Wait until every source rank's flag reached this rank's own epoch (all ranks issue the same number of exchanges).
 __device__ __forceinline__ void p2p_wait(const EpParams& p, int which, int epoch_word = -1) {

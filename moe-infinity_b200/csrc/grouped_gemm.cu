@@ -148,10 +148,28 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA0, const CUtenso
     }
     fence_barrier_init();
   }
+  // Expert parallel (direct mode): this kernel's CTAs are resident while the routing kernel is still exchanging rows with the peers
+  // and the previous layer's combine waits for its owners -- HBM is idle for ~30 us per layer (profiles/r02e_ep8_timeline.json).
+  // Each CTA asks the TMA unit to pull the first ep_l2pf k-blocks of the weight tiles it will most likely own (one token tile
+  // per local expert: tile = le * m_tiles + m) into L2.  A hint only: a wrong guess costs bandwidth, never correctness.  The slot
+  // table is older than any predecessor in the stream.
+  if (p.ep_l2pf > 0 && p.ep_rows > 0 && warp == 0 && lane == 0 && (int)blockIdx.x < ctas && MC == 1) {
+    const int npf = p.ep_l2pf < kblocks ? p.ep_l2pf : kblocks;
+    for (int tile = blockIdx.x; tile < p.ep_el * m_tiles; tile += ctas) {
+      const int slot = p.slot_of[p.ep_first + tile / m_tiles];
+      const int m0 = (tile % m_tiles) * m_step;
+      if (slot < 0) continue;
+      for (int kb = 0; kb < npf; ++kb) {
+        tma_prefetch_3d(&tmA0, kb * BLOCK_K, m0, slot);
+        if (DUAL) tma_prefetch_3d(&tmA1, kb * BLOCK_K, m0, slot);
+      }
+    }
+  }
   // everything above is on-chip; from here on we touch memory earlier kernels produced.  In early_a mode (down projection
   // launched with a programmatic edge behind the gate/up GEMM) only the token-tile loads depend on the predecessor: the
   // producer prefetches weight tiles first and waits later; the routing tables read below are older than the predecessor.
   if (!p.early_a && dep_mode == DEP_PDL) pdl_wait();
+  if (p.pdl_edge && dep_mode == DEP_PDL) pdl_launch();
   if (p.single_n >= 0) {
     if (threadIdx.x == 0) { offs[0] = 0; offs[1] = p.single_n; slots[0] = p.single_slot; }
   } else if (p.ep_rows > 0) {
@@ -409,12 +427,12 @@ __device__ __forceinline__ void gemm_finish(const GemmParams& p, uint32_t tmem_b
     // combine kernels read the rows in place over NVLink
     __threadfence_system();
     if (atomicAdd(p.ep_done_ctr, 1) == (int)gridDim.x - 1) {
-      __threadfence_system();
       *p.ep_done_ctr = 0;
       for (int le = 0; le < p.ep_el; ++le) p.ep_cnt[le] = 0;   // every CTA has read the counts: regions are free for the next layer
       const int e = *p.ep_done_epoch + 1;
       *p.ep_done_epoch = e;
-      for (int r = 0; r < p.ep_nranks; ++r) st_release_sys(p.ep_peer_done_flag[r] + p.ep_rank, e);   // release orders the stores above
+      __threadfence_system();   // the other CTAs' fenced outputs and the counter reset happen-before the flags; the flag stores
+      for (int r = 0; r < p.ep_nranks; ++r) st_relaxed_sys(p.ep_peer_done_flag[r] + p.ep_rank, e);   // themselves go out back to back
     }
   }
   if (MC > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast / commit into its shared memory
@@ -448,7 +466,10 @@ grouped_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   __shared__ uint32_t s_tmem;
   uint8_t* smem = smem_aligned(smem_raw);
   if (p.tl && threadIdx.x == 0) tl_min(p.tl);
-  pdl_launch();
+  // pdl_edge: this grid may be resident long before its predecessor finishes (expert parallel: the gate/up GEMM arrives behind the
+  // routing kernel to prefetch weights into L2).  Its successor reads state the predecessor publishes (dispatch epoch, row
+  // counters) in ITS prologue, so it must not be released before this grid has passed its own wait: gemm_body triggers then.
+  if (!p.pdl_edge) pdl_launch();
   const uint32_t tmem_base = tmem_setup(&s_tmem, Cfg::TMEM_COLS);
   GridBar nobar{nullptr, 0};
   gemm_body<NT, DUAL, DT, MC>(tmA0, tmA1, tmB, p, smem, tmem_base, DEP_PDL, nobar, (int)gridDim.x);

@@ -73,7 +73,7 @@ __device__ float gate_dot_warp(const RouteParams& p, int t, int e) {
   float acc = 0.f;
   if (p.gate_dtype == DT_F32) {
     const float* w = reinterpret_cast<const float*>(p.gate_w) + (size_t)e * p.H;
-#pragma unroll 4
+#pragma unroll 16
     for (int h = lane * 8; h < p.H; h += 256) {
       const uint4 xv = *reinterpret_cast<const uint4*>(x + h);
       const float4 w0 = *reinterpret_cast<const float4*>(w + h), w1 = *reinterpret_cast<const float4*>(w + h + 4);
@@ -84,7 +84,7 @@ __device__ float gate_dot_warp(const RouteParams& p, int t, int e) {
     }
   } else {
     const uint16_t* w = reinterpret_cast<const uint16_t*>(p.gate_w) + (size_t)e * p.H;
-#pragma unroll 4
+#pragma unroll 16
     for (int h = lane * 8; h < p.H; h += 256) {
       const uint4 xv = *reinterpret_cast<const uint4*>(x + h);
       const uint4 wv = *reinterpret_cast<const uint4*>(w + h);
@@ -1007,7 +1007,7 @@ cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
   if (p.dtype == DT_F32 && (!p.logits || p.ep_dispatch)) return cudaErrorInvalidValue;   // fp32 models: router logits/scores come in
   if (p.T == 0) return cudaMemsetAsync(p.offsets, 0, sizeof(int) * (p.E + 1), st);
   if (p.T <= FUSED_MAX_T) {
-    cudaError_t e = launch_pdl(gate_topk_small_kernel, dim3(p.T), dim3(RT_THREADS), 0, st, p);
+    cudaError_t e = launch_cluster(gate_topk_small_kernel, dim3(p.T), dim3(RT_THREADS), 0, st, 1, p.ep_fused && p.pdl_edge, p);
     if (e != cudaSuccess || p.ep_fused) return e;      // ep_fused: that kernel also permuted and dispatched the rows
     return launch_pdl(permute_small_kernel, dim3(small_permute_grid(p)), dim3(RT_THREADS), 0, st, p);
   }
