@@ -59,7 +59,7 @@ struct Switches {
         streamk(!off("B2M_STREAMK")),             // stream-K partition of the split-K down GEMM
         ep_early_combine(!off("B2M_EP_EARLY_COMBINE")),
         ep_mrows(!off("B2M_EP_MROWS")),
-        ep_l2pf_mb(getenv("B2M_EP_L2PF_MB") ? atoi(getenv("B2M_EP_L2PF_MB")) : 64),
+        ep_l2pf_mb(getenv("B2M_EP_L2PF_MB") ? atoi(getenv("B2M_EP_L2PF_MB")) : 0),   // L2 prefetch of gate/up weights behind programmatic edges: N=2 7.94 vs 7.93, N=4 4.78 vs 4.79 ms/step -> opt-in
         ep_direct(!off("B2M_EP_DIRECT")),         // four-launch expert-parallel layer
         timeline(on("B2M_TIMELINE")),             // device timestamps of the expert-parallel layer (diagnostics)
         fused_ffn(on("B2M_FUSED_FFN")),           // (only in -DB2M_ENABLE_FUSED_FFN builds) gate/up + down GEMMs in one persistent kernel: measured
