@@ -512,6 +512,15 @@ int pump(b2m_ctx* c) {
 
 int upload_row_if_dirty(b2m_ctx* c, int layer, cudaStream_t st) {
   if (!c->row_dirty[layer]) return B2M_OK;
+  {
+    // a dirty row while the stream is being captured would bake a copy from the reused pinned staging ring into the graph:
+    // every replay would then upload whatever the ring holds at that time
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();   // (legacy stream beside a capture: not ours to judge)
+    else if (cs != cudaStreamCaptureStatusNone)
+      return fail(c, B2M_ESTATE, "layer %d's expert->slot row changed and the stream is capturing: run the step once eagerly "
+                  "(all experts of the graph resident) before capturing it", layer);
+  }
   const int E = c->cfg.num_experts;
   int* stage = c->h_stage + (size_t)c->stage_pos * E;
   c->stage_pos = (c->stage_pos + 1) % STAGE_RING;

@@ -120,7 +120,9 @@ class SyncSwitchTransformersSparseMLP(nn.Module):
         if not _is_fast(self.expert_executor):
             raise RuntimeError("SyncSwitchTransformersSparseMLP needs the CUDA executor")
         B, S, D = hidden_states.shape
-        router_logits = F.linear(hidden_states.to(torch.float32), self.classifier.weight.to(torch.float32))
+        bias = self.classifier.bias                       # config.router_bias (HF 4.x Top1Router: self.classifier(hidden_states))
+        router_logits = F.linear(hidden_states.to(torch.float32), self.classifier.weight.to(torch.float32),
+                                 None if bias is None else bias.to(torch.float32))
         out = self.expert_executor.moe_forward(self.layer_id, hidden_states.reshape(-1, D), router_logits=router_logits,
                                                seq_len=S)
         eng = self.expert_executor.expert_dispatcher.engine if hasattr(self.expert_executor.expert_dispatcher, "engine") \

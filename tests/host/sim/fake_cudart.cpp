@@ -89,6 +89,13 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = reinterp
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+// test hook: pretend every stream is (not) being captured
+static int g_fake_capturing = 0;
+extern "C" void fake_set_capturing(int on) { g_fake_capturing = on; }
+cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) {
+  *s = g_fake_capturing ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+  return cudaSuccess;
+}
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(malloc(8)); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }

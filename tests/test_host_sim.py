@@ -418,6 +418,21 @@ def test_errors_are_reported_not_fatal_on_cpu(sim):
     assert sim.b2m_ctx_destroy(None) in (0, L.B2M_EINVAL)
 
 
+def test_dirty_slot_row_refuses_stream_capture_on_cpu(sim):
+    """A changed expert->slot row is uploaded from a reused pinned staging ring; captured into a graph that copy would replay
+    stale bytes.  The library refuses instead (the decode graph is captured after one eager step)."""
+    c = Ctx(sim, num_slots=4)
+    c.register_all(0)
+    lg = np.zeros((3, c.E), dtype=np.float32)
+    sim.fake_set_capturing(1)
+    try:
+        assert c.forward(0, lg) == L.B2M_ESTATE and "capturing" in c.err()
+    finally:
+        sim.fake_set_capturing(0)
+    assert c.forward(0, lg) == 0, c.err()
+    c.close()
+
+
 def test_fp32_experts_take_the_cuda_core_path_on_cpu(sim):
     """dtype int 1 (expert_module.h:21): 4-byte blobs, CUDA-core fp32 GEMMs with whole-K tiles, fp32 combine; the fused
     gate is refused (router logits come in), a mask row with more than top_k experts raises the sticky error."""
