@@ -34,6 +34,7 @@ extern "C" {
 #define B2M_ENOMEM (-3)    /* no evictable HBM slot / allocation failure */
 #define B2M_ESTATE (-4)    /* call not valid in this state (e.g. expert not registered) */
 #define B2M_EUNSUPPORTED (-5)
+#define B2M_EIO (-6)       /* disk tier: open/read failed or a file is shorter than its index entry */
 
 /* dtype ints == reference core/parallel/expert_module.h:20-23 */
 #define B2M_DTYPE_BF16 0
@@ -300,6 +301,45 @@ int b2m_trace_read(b2m_ctx* ctx, int what, int index, void* host_out);
  * start / peers' flags seen / end, [8,10] down GEMM start / end (after "done" is published), [12,13,14] combine start /
  * owners' flags seen / end.  Synchronises the device. */
 int b2m_timeline_read(b2m_ctx* ctx, unsigned long long* host_out, int n_layers);
+
+/* ---- disk tier: reader of the reference's on-disk tensor store, `<prefix>/archer_index` +
+ * `<prefix>/archer_param_<n>` (archer_tensor_index.cpp:101-132, archer_tensor_handle.cpp:53-86).  Replaces
+ * ArcherTensorHandle::ReadTensor (archer_tensor_handle.cpp:189-201) -> ArcherPrioAioHandle::Read
+ * (archer_prio_aio_handle.cpp:37-70): there a synchronous call served by ONE worker thread in 1 MiB preads, with
+ * high-priority requests overtaking low-priority ones between blocks (Schedule, :123-169).  Here: asynchronous tickets, a
+ * pool of worker threads, the same two-level priority at block granularity, O_DIRECT for 4096-aligned blocks and buffered
+ * reads for the rest (and on file systems without O_DIRECT).  Host code only: usable without a GPU.
+ *   b2m_store_open        num_threads <= 0: 8; block_bytes <= 0: 4 MiB; flags: B2M_STORE_NO_ODIRECT
+ *   b2m_store_tensor      index entry of a tensor id (any out pointer may be NULL)
+ *   b2m_store_blob_bytes  size of the concatenation of tensors `ids` (the expert blob, model_topology.cpp:429-431)
+ *   b2m_store_read_async  read the tensors back to back (exact sizes, no alignment padding) into dst
+ *   b2m_store_read_range_async  bytes [blob_off, blob_off+len) of that concatenation into dst (one staging chunk)
+ *   b2m_store_poll        1 done, 0 pending, B2M_EIO failed (the ticket stays valid)
+ *   b2m_store_wait        blocks until the request is complete and retires the ticket; B2M_EIO with a message on failure
+ *   b2m_store_stats       out4 = {bytes read, O_DIRECT blocks, buffered blocks, requests}
+ *   b2m_store_close       serves what is queued, joins the workers, closes the files */
+#define B2M_STORE_NO_ODIRECT 1
+typedef struct b2m_store b2m_store;
+int b2m_store_open(const char* prefix, int num_threads, int block_bytes, int flags, b2m_store** out);
+int b2m_store_close(b2m_store* store);
+const char* b2m_store_last_error(b2m_store* store);
+int b2m_store_count(b2m_store* store);
+int b2m_store_tensor(b2m_store* store, uint32_t id, uint32_t* file_id, int64_t* offset, uint64_t* nbytes);
+int b2m_store_blob_bytes(b2m_store* store, const uint32_t* ids, int n, uint64_t* total);
+int b2m_store_read_async(b2m_store* store, const uint32_t* ids, int n, void* dst, uint64_t dst_bytes, int high_prio,
+                         uint64_t* ticket);
+int b2m_store_read_range_async(b2m_store* store, const uint32_t* ids, int n, uint64_t blob_off, uint64_t len, void* dst,
+                               int high_prio, uint64_t* ticket);
+int b2m_store_poll(b2m_store* store, uint64_t ticket);
+int b2m_store_wait(b2m_store* store, uint64_t ticket);
+int b2m_store_stats(b2m_store* store, uint64_t out4[4]);
+/* An expert whose weights stay on the store (host DRAM smaller than the model): a miss reads the blob chunk by chunk into a
+ * small pinned staging ring and copies each chunk to its HBM slot while the next ones are being read (the reference stages
+ * disk -> pinned host -> device one whole tensor at a time, archer_tensor_handle.cpp:189-201 + model_topology.cpp:150-185).
+ * `ids` are the expert's tensor ids in blob order (the list register_expert receives, model_offload.py:851-853); their sizes
+ * must add up to the expert's blob size.  The store must outlive the context.  Chunk size: B2M_DISK_CHUNK_BYTES in the
+ * environment at context creation (default 32 MiB). */
+int b2m_register_expert_on_store(b2m_ctx* ctx, int layer, int expert, b2m_store* store, const uint32_t* ids, int n);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,9 @@ enum ExpertState : int { ST_UNREGISTERED = 0, ST_HOST = 1, ST_LOADING = 2, ST_RE
 
 struct Expert {
   const uint8_t* host = nullptr;
+  b2m_store* store = nullptr;   // disk tier: the blob stays on the store (b2m_register_expert_on_store); tensor ids in blob order
+  std::vector<uint32_t> ids;
+  bool backed() const { return host != nullptr || store != nullptr; }   // can be evicted and staged again
   int state = ST_UNREGISTERED;
   int slot = -1;
   bool pinned = false;
@@ -162,6 +165,13 @@ struct b2m_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool shared_in_flight = false;                 // b2m_moe_forward already launched this call's shared-expert GEMMs
   cudaEvent_t ev_ring[EVENT_RING] = {nullptr};
+  // disk tier staging: pinned chunks that take a store-backed expert from the reader to the copy engine (see issue_copy)
+  static constexpr int DISK_RING = 3;
+  uint8_t* disk_bounce[DISK_RING] = {nullptr};
+  cudaEvent_t disk_ev[DISK_RING] = {nullptr};
+  bool disk_ev_pending[DISK_RING] = {false};
+  size_t disk_chunk = 32u << 20;
+  uint64_t disk_bytes = 0;
   int ev_pos = 0;
 
   // prefetch scheduler
@@ -370,7 +380,7 @@ int pick_victim(b2m_ctx* c, const std::vector<int>& in_use, bool allow_protected
     for (int l = 0; l < L; ++l) {
       const int id = l * E + e;
       const Expert& x = c->experts[id];
-      if (x.state != ST_RESIDENT || x.pinned || x.host == nullptr) continue;
+      if (x.state != ST_RESIDENT || x.pinned || !x.backed()) continue;
       if (!allow_protected && c->protected_set.count(id)) continue;
       if (std::find(in_use.begin(), in_use.end(), id) != in_use.end()) continue;
       if (x.visits < best_visits) { best = id; best_visits = x.visits; }
@@ -396,7 +406,7 @@ int pick_victim_next_use(b2m_ctx* c, const std::vector<int>& in_use, bool allow_
     for (int e = 0; e < E; ++e) {
       const int id = l * E + e;
       const Expert& x = c->experts[id];
-      if (x.state != ST_RESIDENT || x.pinned || x.host == nullptr) continue;
+      if (x.state != ST_RESIDENT || x.pinned || !x.backed()) continue;
       if (!allow_protected && c->protected_set.count(id)) continue;
       if (std::find(in_use.begin(), in_use.end(), id) != in_use.end()) continue;
       const float s = next_use_score(l, c->cur_layer, L, x.freq);
@@ -458,17 +468,71 @@ int acquire_slot_on_demand(b2m_ctx* c, const std::vector<int>& in_use) {
   return s;
 }
 
+// Disk tier: stage a store-backed expert into its HBM slot.  The blob is cut into chunks; up to DISK_RING - 1 chunk reads are
+// in flight at the reader (many threads, O_DIRECT) while the previous chunk is on its way to the device, so the disk, the
+// staging memory and the host->device link work at the same time.  The host thread blocks for the reads (as the reference's
+// ReadTensor does, archer_tensor_handle.cpp:189-201) but not for the copies.  A staging chunk is reused once the copy that
+// read it has completed (event per chunk).
+int copy_from_store(b2m_ctx* c, Expert& x, uint8_t* dst, cudaStream_t st, bool on_demand) {
+  const size_t bytes = c->arena.shape.bytes;
+  const size_t chunk = c->disk_chunk;
+  const int nchunks = (int)((bytes + chunk - 1) / chunk);
+  for (int b = 0; b < b2m_ctx::DISK_RING; ++b) {
+    if (!c->disk_bounce[b]) CK(c, cudaHostAlloc((void**)&c->disk_bounce[b], chunk, cudaHostAllocDefault));
+    if (!c->disk_ev[b]) CK(c, cudaEventCreateWithFlags(&c->disk_ev[b], cudaEventDisableTiming));
+  }
+  uint64_t tk[b2m_ctx::DISK_RING] = {0};
+  bool tk_live[b2m_ctx::DISK_RING] = {false};
+  int rc = B2M_OK;
+  auto submit = [&](int ci) -> int {
+    const int b = ci % b2m_ctx::DISK_RING;
+    if (c->disk_ev_pending[b]) {
+      CK(c, cudaEventSynchronize(c->disk_ev[b]));
+      c->disk_ev_pending[b] = false;
+    }
+    const size_t off = (size_t)ci * chunk;
+    int r = b2m_store_read_range_async(x.store, x.ids.data(), (int)x.ids.size(), off, std::min(chunk, bytes - off), c->disk_bounce[b],
+                                       on_demand ? 1 : 0, &tk[b]);
+    if (r) return fail(c, r, "disk tier: %s", b2m_store_last_error(x.store));
+    tk_live[b] = true;
+    return B2M_OK;
+  };
+  const int ahead = b2m_ctx::DISK_RING - 1;
+  for (int ci = 0; ci < std::min(ahead, nchunks) && !rc; ++ci) rc = submit(ci);
+  for (int ci = 0; ci < nchunks && !rc; ++ci) {
+    const int b = ci % b2m_ctx::DISK_RING;
+    const size_t off = (size_t)ci * chunk;
+    const int r = b2m_store_wait(x.store, tk[b]);
+    tk_live[b] = false;
+    if (r) { rc = fail(c, r, "disk tier: %s", b2m_store_last_error(x.store)); break; }
+    cudaError_t e = cudaMemcpyAsync(dst + off, c->disk_bounce[b], std::min(chunk, bytes - off), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(c->disk_ev[b], st);
+    if (e != cudaSuccess) { rc = fail(c, B2M_ECUDA, "disk tier copy: %s", cudaGetErrorString(e)); break; }
+    c->disk_ev_pending[b] = true;
+    if (ci + ahead < nchunks) rc = submit(ci + ahead);
+  }
+  for (int b = 0; b < b2m_ctx::DISK_RING; ++b)   // error path: no reader thread may still write into the staging ring
+    if (tk_live[b]) b2m_store_wait(x.store, tk[b]);
+  if (rc) return rc;
+  c->stats.h2d_bytes += bytes;
+  c->disk_bytes += bytes;
+  return B2M_OK;
+}
+
 int issue_copy(b2m_ctx* c, int id, int slot, cudaStream_t st, bool do_copy) {
   Expert& x = c->experts[id];
   Slot& sl = c->slots[slot];
   if (sl.last_use_ev >= 0) CK(c, cudaStreamWaitEvent(st, c->ev_ring[sl.last_use_ev], 0));
   uint8_t* dst = c->arena.base + (size_t)slot * c->arena.slot_bytes;
-  if (do_copy) {
+  if (do_copy && x.host) {
     const size_t bytes = c->arena.shape.bytes;
     const size_t chunk = c->cfg.h2d_chunk_bytes > 0 ? (size_t)c->cfg.h2d_chunk_bytes : bytes;
     for (size_t off = 0; off < bytes; off += chunk)
       CK(c, cudaMemcpyAsync(dst + off, x.host + off, std::min(chunk, bytes - off), cudaMemcpyHostToDevice, st));
     c->stats.h2d_bytes += bytes;
+  } else if (do_copy) {
+    int r = copy_from_store(c, x, dst, st, st != c->prefetch_stream);
+    if (r) { c->free_slots.push_back(slot); return r; }   // the expert stays on the store; its slot goes back
   }
   if (!x.ready) CK(c, cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
   CK(c, cudaEventRecord(x.ready, st));
@@ -739,6 +803,10 @@ int b2m_ctx_create(const b2m_config* cfg, b2m_ctx** out) {
   CKC(cudaStreamCreateWithPriority(&c->fetch_stream, cudaStreamNonBlocking, hi));
   CKC(cudaStreamCreateWithPriority(&c->prefetch_stream, cudaStreamNonBlocking, lo));
   for (int i = 0; i < EVENT_RING; ++i) CKC(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+  if (const char* e = getenv("B2M_DISK_CHUNK_BYTES")) {   // disk tier staging chunk (a multiple of 4096 keeps the reads O_DIRECT-aligned)
+    const long long v = atoll(e);
+    if (v >= 4096) c->disk_chunk = ((size_t)v + 4095) & ~(size_t)4095;
+  }
   CKC(cudaStreamCreateWithFlags(&c->shared_stream, cudaStreamNonBlocking));
   CKC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -779,6 +847,10 @@ int b2m_ctx_destroy(b2m_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (int i = 0; i < EVENT_RING; ++i) if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
+  for (int b = 0; b < b2m_ctx::DISK_RING; ++b) {
+    if (c->disk_bounce[b]) cudaFreeHost(c->disk_bounce[b]);
+    if (c->disk_ev[b]) cudaEventDestroy(c->disk_ev[b]);
+  }
   delete c;
   return B2M_OK;
 }
@@ -791,6 +863,27 @@ int b2m_register_expert(b2m_ctx* c, int layer, int expert, const void* host_blob
     return fail(c, B2M_EINVAL, "expert blob is %zu bytes, expected %zu", bytes, c->arena.shape.bytes);
   Expert& x = c->experts[(size_t)layer * c->cfg.num_experts + expert];
   x.host = reinterpret_cast<const uint8_t*>(host_blob);
+  x.store = nullptr;
+  x.ids.clear();
+  if (x.state == ST_UNREGISTERED) x.state = ST_HOST;
+  return B2M_OK;
+}
+
+int b2m_register_expert_on_store(b2m_ctx* c, int layer, int expert, b2m_store* store, const uint32_t* ids, int n) {
+  int r = check_layer(c, layer);
+  if (r) return r;
+  if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
+  if (!store || !ids || n < 1) return fail(c, B2M_EINVAL, "b2m_register_expert_on_store needs a store and the expert's tensor ids");
+  uint64_t total = 0;
+  r = b2m_store_blob_bytes(store, ids, n, &total);
+  if (r) return fail(c, r, "disk tier: %s", b2m_store_last_error(store));
+  if (total != c->arena.shape.bytes)
+    return fail(c, B2M_EINVAL, "the expert's tensors hold %llu bytes on the store, expected %zu", (unsigned long long)total,
+                c->arena.shape.bytes);
+  Expert& x = c->experts[(size_t)layer * c->cfg.num_experts + expert];
+  x.host = nullptr;
+  x.store = store;
+  x.ids.assign(ids, ids + n);
   if (x.state == ST_UNREGISTERED) x.state = ST_HOST;
   return B2M_OK;
 }
@@ -839,7 +932,7 @@ int b2m_make_resident(b2m_ctx* c, int layer, int expert, int flags, void* stream
     x.state = ST_HOST;
   }
   if (x.state == ST_HOST) {
-    if (!no_copy && !x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
+    if (!no_copy && !x.backed()) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
     std::vector<int> none;
     const int slot = acquire_slot(c, none, false);
     if (slot < 0) return fail(c, B2M_ENOMEM, "no evictable HBM slot for expert (%d,%d)", layer, expert);
@@ -853,7 +946,7 @@ int b2m_make_resident(b2m_ctx* c, int layer, int expert, int flags, void* stream
     x.ready_pending = false;
   }
   if (flags & 1) x.pinned = true;
-  if (!x.host) x.pinned = true;
+  if (!x.backed()) x.pinned = true;
   return B2M_OK;
 }
 
@@ -1176,7 +1269,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
       Expert& x = c->experts[id];
       const bool resident = x.state == ST_RESIDENT || x.state == ST_LOADING;
       if (!resident) {
-        if (!x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
+        if (!x.backed()) return fail(c, B2M_ESTATE, "expert (%d,%d) is neither resident nor backed by a host blob", id / E, id % E);
         if (c->ep_mode) return fail(c, B2M_ESTATE, "expert-parallel mode needs every local expert resident: (%d,%d) is not", id / E, id % E);
         // never evict an expert this call still has to run (reference: those nodes hold their mutex, :239)
         const int slot = on_demand ? acquire_slot_on_demand(c, remaining) : acquire_slot(c, remaining, false);
@@ -1254,7 +1347,7 @@ int b2m_run_experts_ex(b2m_ctx* c, int layer, int T, int phases, void* stream) {
     const int nxt = (layer + 1) % c->cfg.num_layers;
     std::vector<int> order;
     for (int e = 0; e < E; ++e)
-      if (c->h_look[e] > 0 && c->experts[(size_t)nxt * E + e].state == ST_HOST && c->experts[(size_t)nxt * E + e].host) order.push_back(e);
+      if (c->h_look[e] > 0 && c->experts[(size_t)nxt * E + e].state == ST_HOST && c->experts[(size_t)nxt * E + e].backed()) order.push_back(e);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->h_look[a] > c->h_look[b]; });
     r = pump(c);   // retire finished copies first
     if (r) return r;
@@ -1430,7 +1523,7 @@ int b2m_enqueue_prefetch(b2m_ctx* c, int layer, int expert) {
   if (expert < 0 || expert >= c->cfg.num_experts) return fail(c, B2M_EINVAL, "expert %d out of range", expert);
   const int id = layer * c->cfg.num_experts + expert;
   Expert& x = c->experts[id];
-  if (x.state == ST_UNREGISTERED || !x.host) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
+  if (x.state == ST_UNREGISTERED || !x.backed()) return fail(c, B2M_ESTATE, "expert (%d,%d) has no host blob", layer, expert);
   if (x.state == ST_HOST && std::find(c->pending.begin(), c->pending.end(), id) == c->pending.end())
     c->pending.push_back(id);   // dedupe (task_scheduler.cpp:86-104)
   return pump(c);
@@ -1448,7 +1541,7 @@ int b2m_prefetch_hint(b2m_ctx* c, int n, const int32_t* pairs, const float* scor
   for (int i = 0; i < n; ++i) {
     const int id = sorted[2 * i] * c->cfg.num_experts + sorted[2 * i + 1];
     Expert& x = c->experts[id];
-    if (x.state == ST_HOST && x.host) c->pending.push_back(id);
+    if (x.state == ST_HOST && x.backed()) c->pending.push_back(id);
   }
   return pump(c);
 }

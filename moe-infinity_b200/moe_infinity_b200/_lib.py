@@ -10,7 +10,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libb2m.so")
 
 # status codes (include/b2m.h)
-B2M_OK, B2M_EINVAL, B2M_ECUDA, B2M_ENOMEM, B2M_ESTATE, B2M_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+B2M_OK, B2M_EINVAL, B2M_ECUDA, B2M_ENOMEM, B2M_ESTATE, B2M_EUNSUPPORTED, B2M_EIO = 0, -1, -2, -3, -4, -5, -6
+STORE_NO_ODIRECT = 1
 DTYPE_BF16, DTYPE_F32, DTYPE_F16, DTYPE_FP8 = 0, 1, 2, 3
 EXPERT_SWITCH, EXPERT_SWITCH_GATED, EXPERT_NLLB, EXPERT_FSGPT, EXPERT_MIXTRAL, EXPERT_DEEPSEEK = 0, 1, 2, 3, 4, 5
 ROUTER_MIXTRAL, ROUTER_DEEPSEEK_GREEDY, ROUTER_DEEPSEEK_GROUP, ROUTER_SWITCH_TOP1 = 0, 1, 2, 3
@@ -95,6 +96,19 @@ SYMBOLS = [
     ("b2m_trace_update_predict", _I, [_VP, _I, _I, _I, _I, _VP]),
     ("b2m_trace_finish_seq", _I, [_VP, _I, _VP]),
     ("b2m_trace_read", _I, [_VP, _I, _I, _VP]),
+    # disk tier (host code: usable without a GPU)
+    ("b2m_store_open", _I, [C.c_char_p, _I, _I, _I, C.POINTER(_VP)]),
+    ("b2m_store_close", _I, [_VP]),
+    ("b2m_store_last_error", C.c_char_p, [_VP]),
+    ("b2m_store_count", _I, [_VP]),
+    ("b2m_store_tensor", _I, [_VP, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
+    ("b2m_store_blob_bytes", _I, [_VP, C.POINTER(C.c_uint32), _I, C.POINTER(C.c_uint64)]),
+    ("b2m_store_read_async", _I, [_VP, C.POINTER(C.c_uint32), _I, _VP, C.c_uint64, _I, C.POINTER(C.c_uint64)]),
+    ("b2m_store_read_range_async", _I, [_VP, C.POINTER(C.c_uint32), _I, C.c_uint64, C.c_uint64, _VP, _I, C.POINTER(C.c_uint64)]),
+    ("b2m_store_poll", _I, [_VP, C.c_uint64]),
+    ("b2m_store_wait", _I, [_VP, C.c_uint64]),
+    ("b2m_store_stats", _I, [_VP, C.POINTER(C.c_uint64)]),
+    ("b2m_register_expert_on_store", _I, [_VP, _I, _I, _VP, C.POINTER(C.c_uint32), _I]),
 ]
 
 _lib = None

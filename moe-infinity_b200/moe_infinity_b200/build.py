@@ -8,7 +8,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG_DIR), "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb2m.so")
-SOURCES = ["grouped_gemm.cu", "route.cu", "ep.cu", "f32_path.cu", "tracer.cu", "api.cu"]
+SOURCES = ["grouped_gemm.cu", "route.cu", "ep.cu", "f32_path.cu", "tracer.cu", "store_reader.cpp", "api.cu"]
 HEADERS = ["b2m_common.cuh", "b2m_internal.h", "tile_walker.cuh", "ep_device.cuh",
            os.path.join("..", "..", "include", "b2m.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

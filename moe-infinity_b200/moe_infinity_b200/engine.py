@@ -131,6 +131,16 @@ class MoEEngine:
         self._blobs[(layer, expert)] = blob
         self._ck(self.lib.b2m_register_expert(self._h, layer, expert, C.c_void_p(blob.data_ptr()), blob.numel()))
 
+    def register_expert_on_store(self, layer: int, expert: int, reader, tensor_ids: Sequence[int]):
+        """Disk-backed expert: its weights stay on the reference-format store behind `reader`
+        (`store.NativeStoreReader`); a miss streams them disk -> pinned staging ring -> HBM slot in chunks.  `tensor_ids` in
+        blob order (what the reference's `register_expert` receives, model_offload.py:851-853)."""
+        ids = (C.c_uint32 * len(tensor_ids))(*[int(t) for t in tensor_ids])
+        self._stores = getattr(self, "_stores", [])
+        self._stores.append(reader)                                    # the store must outlive the context
+        self._blobs.pop((layer, expert), None)
+        self._ck(self.lib.b2m_register_expert_on_store(self._h, layer, expert, reader.handle, ids, len(tensor_ids)))
+
     def make_resident(self, layer: int, expert: int, pin: bool = False):
         self._ck(self.lib.b2m_make_resident(self._h, layer, expert, 1 if pin else 0, C.c_void_p(_stream_ptr())))
 

@@ -12,6 +12,9 @@ A store written here is readable by the reference (`ArcherTensorHandle` ctor -> 
 tests/test_store_format.py checks both directions against the reference's own (compiled) index code.
 
 Host-side only: tensors are read into (pinned) host memory, from where `b2m_register_expert` takes over.
+`ArcherTensorStore` is the format in plain Python (writer + simple reader); `NativeStoreReader` is the product's reader
+(csrc/store_reader.cpp behind the C ABI: worker threads, O_DIRECT, asynchronous tickets, two priorities) and the handle
+`MoEEngine.register_expert_on_store` takes for experts that stay on disk.
 """
 from __future__ import annotations
 
@@ -223,3 +226,100 @@ class ArcherTensorStore:
 
     def ids(self) -> Iterable[int]:
         return sorted(self.index)
+
+
+class NativeStoreReader:
+    """`b2m_store_*` (include/b2m.h): the disk tier's reader.  What `ArcherTensorHandle::ReadTensor` ->
+    `ArcherPrioAioHandle::Read` is in the reference (archer_tensor_handle.cpp:189-201, archer_prio_aio_handle.cpp:37-70),
+    asynchronous and multi-threaded.  Needs libb2m.so but no GPU."""
+
+    def __init__(self, prefix: str, num_threads: int = 0, block_bytes: int = 0, odirect: bool = True):
+        import ctypes as C
+        from . import _lib as L
+        self._C, self._L, self._lib = C, L, L.load()
+        self._h = C.c_void_p()
+        rc = self._lib.b2m_store_open(os.fsencode(prefix.rstrip("/") or "/"), num_threads, block_bytes,
+                                      0 if odirect else L.STORE_NO_ODIRECT, C.byref(self._h))
+        if rc:
+            self._h = C.c_void_p()
+            raise IOError(f"b2m_store_open({prefix!r}) failed with {rc}"
+                          + (": no readable archer_index" if rc == L.B2M_EIO else ": corrupt archer_index"))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _ck(self, rc):
+        if rc < 0:
+            msg = self._lib.b2m_store_last_error(self._h)
+            raise (IOError if rc == self._L.B2M_EIO else ValueError)(f"store error {rc}: {msg.decode() if msg else ''}")
+        return rc
+
+    def _ids(self, tensor_ids):
+        arr = (self._C.c_uint32 * len(tensor_ids))(*[int(t) for t in tensor_ids])
+        return arr, len(tensor_ids)
+
+    def __len__(self):
+        return self._ck(self._lib.b2m_store_count(self._h))
+
+    def tensor(self, tensor_id: int):
+        """(file_id, offset, nbytes) of a tensor."""
+        C = self._C
+        f, o, n = C.c_uint32(), C.c_int64(), C.c_uint64()
+        self._ck(self._lib.b2m_store_tensor(self._h, int(tensor_id), C.byref(f), C.byref(o), C.byref(n)))
+        return f.value, o.value, n.value
+
+    def blob_bytes(self, tensor_ids: Sequence[int]) -> int:
+        arr, n = self._ids(tensor_ids)
+        tot = self._C.c_uint64()
+        self._ck(self._lib.b2m_store_blob_bytes(self._h, arr, n, self._C.byref(tot)))
+        return tot.value
+
+    def read_async(self, tensor_ids: Sequence[int], out: torch.Tensor, high_priority: bool = False,
+                   blob_offset: int = 0, nbytes: Optional[int] = None) -> int:
+        """Start reading the concatenation of `tensor_ids` (or bytes [blob_offset, +nbytes) of it) into the CPU tensor `out`
+        (keep it alive until `wait`); returns a ticket."""
+        if out.device.type != "cpu" or not out.is_contiguous():
+            raise ValueError("the destination must be a contiguous CPU tensor")
+        arr, n = self._ids(tensor_ids)
+        cap = out.numel() * out.element_size()
+        tk = self._C.c_uint64()
+        if blob_offset == 0 and nbytes is None:
+            self._ck(self._lib.b2m_store_read_async(self._h, arr, n, out.data_ptr(), cap, int(high_priority), self._C.byref(tk)))
+        else:
+            nbytes = self.blob_bytes(tensor_ids) - blob_offset if nbytes is None else nbytes
+            if nbytes > cap:
+                raise ValueError("destination too small")
+            self._ck(self._lib.b2m_store_read_range_async(self._h, arr, n, blob_offset, nbytes, out.data_ptr(),
+                                                         int(high_priority), self._C.byref(tk)))
+        return tk.value
+
+    def poll(self, ticket: int) -> bool:
+        return self._ck(self._lib.b2m_store_poll(self._h, ticket)) == 1
+
+    def wait(self, ticket: int) -> None:
+        self._ck(self._lib.b2m_store_wait(self._h, ticket))
+
+    def read_expert_blob(self, tensor_ids: Sequence[int], out: Optional[torch.Tensor] = None, pin: bool = False) -> torch.Tensor:
+        """Same result as `ArcherTensorStore.read_expert_blob`, through the native reader."""
+        total = self.blob_bytes(tensor_ids)
+        if out is None:
+            out = torch.empty(total, dtype=torch.uint8, pin_memory=pin)
+        self.wait(self.read_async(tensor_ids, out, high_priority=True))
+        return out
+
+    def stats(self) -> Dict[str, int]:
+        out = (self._C.c_uint64 * 4)()
+        self._ck(self._lib.b2m_store_stats(self._h, out))
+        return dict(bytes_read=out[0], direct_blocks=out[1], buffered_blocks=out[2], requests=out[3])
+
+    def close(self):
+        if self._h:
+            self._lib.b2m_store_close(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -38,10 +38,12 @@ def build() -> str | None:
     subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC",
                     "-cudart", "none", "-diag-suppress", "177", *inc, "-c", os.path.join(CSRC, "api.cu"), "-o", api_o],
                    check=True, capture_output=True)
-    for src, obj in ((os.path.join(HERE, "fake_kernels.cpp"), k_o), (os.path.join(HERE, "fake_cudart.cpp"), r_o)):
+    s_o = os.path.join(OUT, "store_reader.o")           # the product's disk-tier reader is host code: compiled as it is
+    for src, obj in ((os.path.join(HERE, "fake_kernels.cpp"), k_o), (os.path.join(HERE, "fake_cudart.cpp"), r_o),
+                     (os.path.join(CSRC, "store_reader.cpp"), s_o)):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", *inc, "-c", src, "-o", obj], check=True, capture_output=True)
     # -Bsymbolic: api.o must bind to THIS library's cuda* emulation even when a real libcudart (torch) is already loaded
-    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO, api_o, k_o, r_o], check=True, capture_output=True)
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO, api_o, k_o, r_o, s_o, "-lpthread"], check=True, capture_output=True)
     return SO
 
 

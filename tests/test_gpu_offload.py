@@ -252,3 +252,49 @@ def test_activation_aware_cache_with_lookahead_prefetch(lib_built):
     for ll in range(L):
         for e in range(E):
             assert plain.is_resident(ll, e) == orc.resident[ll * E + e]
+
+
+def test_disk_backed_experts_match_host_backed(lib_built, tmp_path, monkeypatch):
+    """SURVEY §8f N3, the disk tier: half of the experts stay on a reference-format store (written by store.py) and are
+    staged disk -> pinned chunk ring -> HBM slot on a miss (b2m_register_expert_on_store; reader: csrc/store_reader.cpp);
+    the hidden states must equal the all-resident run bit for bit and the cache bookkeeping must not notice the difference."""
+    from moe_infinity_b200.store import ArcherTensorStore, NativeStoreReader
+    monkeypatch.setenv("B2M_DISK_CHUNK_BYTES", str(10 * 4096))        # 196608-byte blobs: 5 chunks, crossing tensor ends
+    experts, gates = _model(21)
+    full = _engine(experts, gates, L * E)
+    host = _engine(experts, gates, 9)
+    st = ArcherTensorStore(str(tmp_path))
+    ids, tid = {}, 1000
+    for l in range(L):
+        for e in range(0, E, 2):
+            ids[(l, e)] = list(range(tid, tid + 3))
+            for w in experts[l][e]:                                     # (w1, w2, w3) in blob order
+                st.store_tensor(tid, w, flush=False)
+                tid += 1
+    st.flush()
+    rd = NativeStoreReader(str(tmp_path), num_threads=4, block_bytes=16384)
+    from moe_infinity_b200 import MoEEngine
+    disk = MoEEngine(num_layers=L, num_experts=E, hidden=H, inter=I, top_k=K, dtype=DT, max_tokens=64, num_slots=9)
+    for l in range(L):
+        for e in range(E):
+            if (l, e) in ids:
+                disk.register_expert_on_store(l, e, rd, ids[(l, e)])
+            else:
+                disk.register_expert(l, e, experts[l][e])
+        disk.set_gate(l, gates[l])
+    g = torch.Generator().manual_seed(4)
+    for step in range(6):
+        for l in range(L):
+            x = torch.randn(7, H, generator=g).to(DT).cuda()
+            a, b, c = full.forward(l, x), host.forward(l, x), disk.forward(l, x)
+            torch.cuda.synchronize()
+            assert torch.equal(a, c), f"step {step} layer {l}: disk-backed run differs from the resident run"
+            assert torch.equal(b, c)
+    sh, sd = host.stats(), disk.stats()
+    for k in ("dispatches", "hits", "misses", "evictions", "h2d_bytes"):
+        assert sh[k] == sd[k], k
+    assert sd["misses"] > 0 and sd["evictions"] > 0
+    rs = rd.stats()
+    assert rs["bytes_read"] > 0 and rs["bytes_read"] % (3 * H * I * 2) == 0
+    del disk
+    rd.close()

@@ -433,6 +433,76 @@ def test_dirty_slot_row_refuses_stream_capture_on_cpu(sim):
     c.close()
 
 
+def test_disk_backed_experts_stream_through_the_staging_ring_on_cpu(sim, tmp_path, monkeypatch):
+    """experts registered on a reference-format store are staged disk -> pinned chunk ring -> slot on a miss
+    (api.cu: copy_from_store over csrc/store_reader.cpp, both compiled as they are), mixed with host-backed experts; the
+    right bytes land in the right slots through evictions, and a read error is a return code, not an abort."""
+    import torch
+    from moe_infinity_b200.store import ArcherTensorStore
+    monkeypatch.setenv("B2M_DISK_CHUNK_BYTES", str(10 * 4096))          # 196608-byte blobs -> 5 chunks that cross tensor ends
+    c = Ctx(sim, L_=2, num_slots=3)
+    assert c.rc == 0
+    st = ArcherTensorStore(str(tmp_path))
+    rng = np.random.default_rng(5)
+    ids_of, want = {}, {}
+    tid = 100
+    for l in range(c.L):
+        for e in range(c.E):
+            parts = [rng.integers(0, 255, c.H * c.I * 2, dtype=np.uint8) for _ in range(3)]      # w1 | w2 | w3
+            want[(l, e)] = np.concatenate(parts)
+            if e % 2 == 0:                                                 # even experts live on the store ...
+                ids_of[(l, e)] = list(range(tid, tid + 3))
+                for p_ in parts:
+                    st.store_tensor(tid, torch.from_numpy(p_), flush=False)
+                    tid += 1
+    st.flush()
+    store = C.c_void_p()
+    assert sim.b2m_store_open(str(tmp_path).encode(), 3, 8192, 0, C.byref(store)) == 0
+    for (l, e), blob in want.items():
+        if (l, e) in ids_of:
+            arr = (C.c_uint32 * 3)(*ids_of[(l, e)])
+            assert sim.b2m_register_expert_on_store(c.h, l, e, store, arr, 3) == 0, c.err()
+        else:                                                              # ... odd ones in host memory
+            c.blobs[(l, e)] = blob
+            assert sim.b2m_register_expert(c.h, l, e, blob.ctypes.data, blob.nbytes) == 0, c.err()
+    bad = (C.c_uint32 * 2)(100, 101)
+    assert sim.b2m_register_expert_on_store(c.h, 0, 0, store, bad, 2) == L.B2M_EINVAL and "bytes on the store" in c.err()
+    bad = (C.c_uint32 * 1)(7)
+    assert sim.b2m_register_expert_on_store(c.h, 0, 0, store, bad, 1) == L.B2M_EINVAL and "not in the index" in c.err()
+
+    def route_to(experts):
+        lg = np.full((len(experts), c.E), -30.0, dtype=np.float32)
+        for t_, (a, b) in enumerate(experts):
+            lg[t_, a], lg[t_, b] = 5.0, 4.0
+        return lg
+
+    seen = 0
+    for step, (layer, pairs) in enumerate([(0, [(0, 1)]), (0, [(2, 3)]), (1, [(4, 6)]), (0, [(0, 2)]), (1, [(1, 4)]), (0, [(6, 7)])]):
+        assert c.forward(layer, route_to(pairs)) == 0, c.err()
+        for a in {x for p_ in pairs for x in p_}:
+            assert c.resident(layer, a)
+            assert np.array_equal(c.slot_bytes(layer, a), want[(layer, a)]), (step, layer, a)
+            seen += 1
+    s = c.stats()
+    assert s["evictions"] > 0 and s["misses"] >= 9
+    out4 = (C.c_uint64 * 4)()
+    assert sim.b2m_store_stats(store, out4) == 0
+    assert out4[0] > 0 and out4[0] % want[(0, 0)].nbytes == 0            # whole blobs came from the disk, in 5-chunk requests
+    assert out4[3] == 5 * (out4[0] // want[(0, 0)].nbytes)
+    # a store file that lost its tail: the miss fails with B2M_EIO, the expert is not marked resident, the context lives on
+    with open(tmp_path / "archer_param_0", "r+b") as f:
+        f.truncate(4096)
+    victim = next(e for e in (0, 2, 4, 6) if not c.resident(1, e))
+    other = next(e for e in (1, 3, 5, 7) if e != victim)
+    for _ in range(5):                                                     # (more failures than slots: none may leak)
+        assert c.forward(1, route_to([(victim, other)])) == L.B2M_EIO and "disk tier" in c.err()
+        assert not c.resident(1, victim)
+    assert c.forward(0, route_to([(1, 3)])) == 0, c.err()                  # host-backed experts still work
+    assert np.array_equal(c.slot_bytes(0, 1), want[(0, 1)])
+    c.close()
+    assert sim.b2m_store_close(store) == 0
+
+
 def test_fp32_experts_take_the_cuda_core_path_on_cpu(sim):
     """dtype int 1 (expert_module.h:21): 4-byte blobs, CUDA-core fp32 GEMMs with whole-K tiles, fp32 combine; the fused
     gate is refused (router logits come in), a mask row with more than top_k experts raises the sticky error."""
