@@ -61,11 +61,18 @@ _CURRENT_HANDLE: Optional["prefetch_handle"] = None     # the reference keeps ex
 class prefetch_handle:  # noqa: N801  (reference spelling)
     """py_archer_prefetch.cpp:11-80.  Host-DRAM tensor store + the residency/prefetch façade."""
 
-    def __init__(self, prefix: str, device_memory_ratio: float, persistent: bool = False):
+    def __init__(self, prefix: str, device_memory_ratio: float, persistent: bool = False, experts_on_disk: bool = False):
         global _CURRENT_HANDLE
         _CURRENT_HANDLE = self
         self.prefix = prefix
         self.device_memory_ratio = float(device_memory_ratio)
+        # experts_on_disk=True (implies persistent): expert tensors are NOT kept in host DRAM once registered; a cache miss
+        # streams them from the offload directory through the native reader (disk -> pinned staging ring -> HBM slot).  For
+        # models larger than host memory; the reference instead pins every expert in host DRAM at start-up
+        # (model_topology.cpp:517-537).
+        self.experts_on_disk = bool(experts_on_disk)
+        persistent = persistent or self.experts_on_disk
+        self._readers: List = []
         # persistent=True: `prefix` is an offload directory in the reference's on-disk format (store.py): `offload`
         # also writes there and a directory left by an earlier run (of this package or of the reference) is reused,
         # tensors being read back on first use.  Default: host DRAM only, nothing touches the disk.
@@ -87,6 +94,25 @@ class prefetch_handle:  # noqa: N801  (reference spelling)
         """Write the on-disk index once (the reference rewrites it inside every `offload`, O(n^2) in the tensor count)."""
         if self._store is not None:
             self._store.flush()
+
+    def _reader_for(self, tensor_ids: Sequence[int]):
+        """The native store reader that knows `tensor_ids` (its index is read when it is opened: tensors offloaded later
+        need a new one; earlier readers stay open because contexts hold on to them)."""
+        from .store import NativeStoreReader
+        if self._readers:
+            try:
+                self._readers[-1].blob_bytes(tensor_ids)
+                return self._readers[-1]
+            except ValueError:
+                pass
+        self.flush()
+        self._readers.append(NativeStoreReader(self.prefix))
+        return self._readers[-1]
+
+    def _shape_of(self, tensor_id: int):
+        if dict.__contains__(self._tensors, tensor_id):
+            return tuple(self._tensors[tensor_id].shape)
+        return tuple(self._store.index[int(tensor_id)].shape)
 
     def register(self, tensor: torch.Tensor, tensor_id: int):
         self._params[int(tensor_id)] = tensor
@@ -204,7 +230,7 @@ class expert_dispatcher:  # noqa: N801
         if self.engine is not None:
             self.engine.close()
         any_ids = next(iter(self._registered.values()))
-        inter, hidden = self.handle._tensors[int(any_ids[0])].shape   # first tensor is [I,H] for every supported expert type
+        inter, hidden = self.handle._shape_of(int(any_ids[0]))   # first tensor is [I,H] for every supported expert type
         ratio = self.handle.device_memory_ratio if self.handle else 0.0
         self.max_tokens = max_tokens
         self.engine = MoEEngine(num_layers=self.num_layers, num_experts=self.num_experts, hidden=hidden, inter=inter,
@@ -212,6 +238,14 @@ class expert_dispatcher:  # noqa: N801
                                 router=_ROUTER_OF_TYPE[self.expert_type], max_tokens=max_tokens,
                                 num_slots=self.num_slots, device_memory_ratio=ratio, **self.engine_kw)
         for (l, e), ids in self._registered.items():
+            self._register_in_engine(l, e, ids)
+
+    def _register_in_engine(self, l: int, e: int, ids: List[int]):
+        if self.handle.experts_on_disk:
+            self.engine.register_expert_on_store(l, e, self.handle._reader_for(ids), ids)
+            for t in ids:
+                dict.pop(self.handle._tensors, t, None)          # the host copy is no longer needed: it can be read again
+        else:
             self.engine.register_expert(l, e, [self.handle._tensors[int(t)] for t in ids])
 
     def _fit(self, k_needed: int, T: int):
@@ -235,7 +269,7 @@ class expert_dispatcher:  # noqa: N801
             self.handle._node_of[t] = (layer_idx, expert_idx)
         self._registered[(layer_idx, expert_idx)] = ids
         if self.engine is not None:
-            self.engine.register_expert(layer_idx, expert_idx, [self.handle._tensors[t] for t in ids])
+            self._register_in_engine(layer_idx, expert_idx, ids)
         elif self.top_k:
             self._build_engine(self.top_k, self.max_tokens)    # sizes known up front: build now (and register this expert)
 

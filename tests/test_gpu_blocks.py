@@ -148,3 +148,49 @@ def test_dense_parameter_begin_is_static_placement(lib_built):
     h.register(other, 7)                          # the same tensor id reached through another placeholder: same storage
     h.begin(2, other)
     assert other.data_ptr() == p0
+
+
+def test_reference_compat_objects_with_experts_on_disk(lib_built, tmp_path):
+    """Same call sequence as the reference's start-up (offload every tensor, register the experts by id), with
+    `experts_on_disk=True`: nothing stays in host DRAM, every miss streams from the offload directory.  The
+    per-expert outputs must be bit-identical to the host-DRAM handle's, through evictions (4 slots for 8 experts)."""
+    from moe_infinity_b200 import _lib as L
+    from moe_infinity_b200.compat import DistributedExpertExecutor, expert_dispatcher, prefetch_handle
+    c, fx = load_case("mixtral_mini_bf16")
+    E = c["E"]
+
+    def build(handle):
+        tid, ids = 0, {}
+        for e in range(E):
+            ids[e] = []
+            for w in c["experts"][e]:
+                handle.offload(w, tid)
+                ids[e].append(tid)
+                tid += 1
+        d = expert_dispatcher(E, 1, L.DTYPE_BF16, L.EXPERT_MIXTRAL, 8, handle=handle, top_k=c["k"], max_tokens=64, num_slots=4)
+        for e in range(E):
+            d.register_expert(0, e, ids[e])
+        ex = DistributedExpertExecutor()
+        ex.set_expert_dispatcher(d)
+        return ex, d
+
+    ex_host, _ = build(prefetch_handle(str(tmp_path / "unused"), 0.5))
+    h_disk = prefetch_handle(str(tmp_path / "offload"), 0.5, experts_on_disk=True)
+    ex_disk, d_disk = build(h_disk)
+    assert len(dict.keys(h_disk._tensors)) == 0                     # no expert tensor is held in host memory any more
+    assert h_disk.is_tensor_offloaded(0)                             # ... but it is still known to the store
+    r = O.mixtral_route(fx["router_logits"], c["k"], c["dtype"])
+    x = c["hidden"].reshape(-1, c["H"]).cuda()
+    mask = r.router_mask.cuda()
+    for rep in range(3):
+        for lo in (0, 4):                                             # two halves of the experts alternate -> evictions
+            m = torch.zeros_like(mask)
+            m[:, lo:lo + 4] = mask[:, lo:lo + 4]
+            a = ex_host.dispatch_local(x, m, 0)
+            b = ex_disk.dispatch_local(x, m, 0)
+            assert [t[2:] for t in a] == [t[2:] for t in b]
+            for (oa, _, e, _), (ob, _, _, _) in zip(a, b):
+                assert torch.equal(oa, ob), f"rep {rep} expert {e}"
+    st = d_disk.engine.stats()
+    assert st["evictions"] > 0
+    assert h_disk._readers and h_disk._readers[-1].stats()["bytes_read"] == st["misses"] * 3 * c["H"] * c["I"] * 2
