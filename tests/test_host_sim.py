@@ -797,20 +797,39 @@ def test_device_tracer_call_wiring_on_cpu(sim):
     c.close()
 
 
-def test_random_call_sequences_never_crash_on_cpu(sim):
+def test_random_call_sequences_never_crash_on_cpu(sim, tmp_path, monkeypatch):
     """Stateful fuzz of the C ABI's host logic: random (often invalid) calls in random order.  Every call must return a
     status code (0 or < 0 with a message), the cache invariants must hold after every step, and a valid forward must keep
     working afterwards.  (Run under ASan/UBSan during development: clean.)"""
     rng = np.random.default_rng(2024)
+    disk_total = 0
     for trial in range(6):
         Lr, E, k = int(rng.integers(1, 4)), int(rng.choice([2, 4, 8, 16])), 0
         k = int(rng.integers(1, min(E, 4) + 1))
         nslots = int(rng.integers(1, Lr * E + 3))
         chunk = int(rng.choice([0, 4096, 100000]))
+        monkeypatch.setenv("B2M_DISK_CHUNK_BYTES", str(int(rng.choice([4096, 12288, 1 << 20]))))
         c = Ctx(sim, L_=Lr, E=E, H=64, I=64, k=k, num_slots=nslots, max_tokens=32, h2d_chunk_bytes=chunk,
                 max_inflight_prefetch=int(rng.integers(0, 4)))
         assert c.rc == 0, c.err()
+        # a reference-format store holding one blob (3 tensors) per (layer, expert): some experts get registered on it
+        import torch
+        from moe_infinity_b200.store import ArcherTensorStore
+        sdir = tmp_path / f"store{trial}"
+        st_ = ArcherTensorStore(str(sdir))
+        on_disk = {}
+        for l_ in range(Lr):
+            for e_ in range(E):
+                parts = [rng.integers(0, 255, 64 * 64 * 2, dtype=np.uint8) for _ in range(3)]
+                on_disk[(l_, e_)] = np.concatenate(parts)
+                for j, p_ in enumerate(parts):
+                    st_.store_tensor((l_ * E + e_) * 3 + j, torch.from_numpy(p_), flush=False)
+        st_.flush()
+        store = C.c_void_p()
+        assert sim.b2m_store_open(str(sdir).encode(), 2, 4096, 0, C.byref(store)) == 0
         registered = set()
+        reg_count = {}
+        nocopy = set()
         x = np.zeros((40, 64), dtype=np.uint16)
         out = np.zeros((40, 64), dtype=np.uint16)
         last_T = None
@@ -820,12 +839,22 @@ def test_random_call_sequences_never_crash_on_cpu(sim):
             e = int(rng.integers(-1, E + 1))
             T = int(rng.integers(0, 36))
             rc = 0
-            if op <= 1:
+            if op <= 1 and rng.random() < 0.4:
+                base = (l * E + e) * 3 if rng.random() < 0.9 else 10 ** 6           # (sometimes ids the store does not have)
+                n_ids = 3 if rng.random() < 0.9 else 2
+                arr = (C.c_uint32 * 3)(*[(base + j) & 0xFFFFFFFF for j in range(3)])
+                rc = sim.b2m_register_expert_on_store(c.h, l, e, store, arr, n_ids)
+                if rc == 0:
+                    c.blobs[(l, e)] = on_disk[(l, e)]
+                    registered.add((l, e))
+                    reg_count[(l, e)] = reg_count.get((l, e), 0) + 1
+            elif op <= 1:
                 blob = rng.integers(0, 255, c.expert_bytes() if rng.random() < 0.9 else 10, dtype=np.uint8)
                 rc = sim.b2m_register_expert(c.h, l, e, blob.ctypes.data, blob.nbytes)
                 if rc == 0:
                     c.blobs[(l, e)] = blob
                     registered.add((l, e))
+                    reg_count[(l, e)] = reg_count.get((l, e), 0) + 1
             elif op <= 4:
                 lg = rng.standard_normal((max(T, 1), E)).astype(np.float32)
                 rc = sim.b2m_moe_forward(c.h, l, x.ctypes.data, lg.ctypes.data, 1, L.DTYPE_F32, T, 0, out.ctypes.data, None)
@@ -846,7 +875,10 @@ def test_random_call_sequences_never_crash_on_cpu(sim):
             elif op == 8:
                 rc = sim.b2m_prefetch_drain(c.h) if rng.random() < 0.5 else sim.b2m_prefetch_pump(c.h)
             elif op == 9:
-                rc = sim.b2m_make_resident(c.h, l, e, int(rng.integers(0, 4)), None)
+                fl = int(rng.integers(0, 4))
+                rc = sim.b2m_make_resident(c.h, l, e, fl, None)
+                if rc == 0 and fl & 2:
+                    nocopy.add((l, e))                               # slot claimed without a copy: contents are the caller's
             elif op == 10:
                 rc = sim.b2m_clear_expert_cache_counts(c.h)
             else:
@@ -864,5 +896,12 @@ def test_random_call_sequences_never_crash_on_cpu(sim):
                 b = c.slot_bytes(l, e)
                 assert b is not None
                 seen_slots.setdefault(b.ctypes.data, []).append((l, e))
+                if reg_count[(l, e)] == 1 and (l, e) not in nocopy:   # registered once (host blob or store): the slot holds those bytes
+                    assert np.array_equal(b, c.blobs[(l, e)]), (trial, l, e)
         assert all(len(v) == 1 for v in seen_slots.values()), "two experts share one HBM slot"
         c.close()
+        o4 = (C.c_uint64 * 4)()
+        assert sim.b2m_store_stats(store, o4) == 0
+        disk_total = disk_total + int(o4[0])
+        assert sim.b2m_store_close(store) == 0
+    assert disk_total > 0, "the fuzz never staged an expert from the store" 
