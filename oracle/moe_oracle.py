@@ -308,6 +308,8 @@ def make_experts(E: int, H: int, I: int, dtype: torch.dtype, seed: int, expert_t
             shapes = [(I, H), (I, H), (H, I)]          # gate, up, down
         elif expert_type == SWITCH_DENSE_ACT_DENSE:
             shapes = [(I, H), (H, I)]                  # wi, wo
+        elif expert_type in (NLLB_MOE_DENSE_ACT_DENSE, FSGPT_MOE_DENSE_ACT_DENSE):
+            shapes = [(I, H), (I,), (H, I), (H,)]      # fc1, fc1_bias, fc2, fc2_bias (named_parameters order)
         else:
             raise ValueError(expert_type)
         out.append([(torch.randn(s, generator=g) * std).to(dtype) for s in shapes])

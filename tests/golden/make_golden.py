@@ -46,6 +46,13 @@ SWITCH_CASES = {
 }
 
 
+NLLB_CASES = {
+    # name: (D, F, E, capacity, B, S, dtype, seed)      literal block only (HF's NllbMoeTop2Router does the routing)
+    "nllb_mini_bf16": (128, 256, 8, 64, 2, 12, torch.bfloat16, 41),
+    "nllb_capacity_f16": (128, 128, 8, 5, 1, 24, torch.float16, 42),     # capacity 5 of 24 tokens: HF drops the overflow
+}
+
+
 def checksum(tensors) -> float:
     s = 0.0
     for t in tensors:
@@ -162,6 +169,59 @@ def run_literal_switch(ns, D, Fd, E, cap, hidden, gate_w, experts):
     return out, logits, expert_index
 
 
+def nllb_config(D, Fd, E, cap):
+    from transformers import NllbMoeConfig
+    return NllbMoeConfig(d_model=D, encoder_ffn_dim=Fd, decoder_ffn_dim=Fd, num_experts=E, expert_capacity=cap,
+                         router_bias=False, router_dtype="float32", router_jitter_noise=0.0, moe_token_dropout=0.0,
+                         dropout=0.0, activation_dropout=0.0, activation_function="relu", second_expert_policy="all",
+                         normalize_router_prob_before_dropping=False, batch_prioritized_routing=False,
+                         moe_eval_capacity_token_fraction=-1.0)
+
+
+def run_literal_nllb(ns, D, Fd, E, cap, hidden, gate_w, experts):
+    """The literal SyncNllbMoeSparseMLP (nllb_moe.py:20-115) in eval mode; behind dispatch_local: the oracle's statement of
+    the engine's NllbMoeDenseActDense module (expert_module.cpp:79-129, pinned on the compiled reference module)."""
+    blk = ns.nllb.SyncNllbMoeSparseMLP(nllb_config(D, Fd, E, cap), Fd).to(hidden.dtype)
+    blk.eval()
+    with torch.no_grad():
+        blk.router.classifier.weight.copy_(gate_w)
+    ex = types.SimpleNamespace()
+    ex.dispatch_local = lambda h, m, lid: O.dispatch_local(h, m, experts, O.NLLB_MOE_DENSE_ACT_DENSE, lid)
+    blk.expert_executor, blk.layer_id = ex, 0
+    orig_to = torch.Tensor.to
+
+    def _to(self, *a, **kw):                      # the block's last lines move its auxiliary outputs to "cuda:0" (:111-114)
+        if a and isinstance(a[0], str) and a[0].startswith("cuda") and not torch.cuda.is_available():
+            return self
+        return orig_to(self, *a, **kw)
+    torch.Tensor.to = _to
+    try:
+        with torch.no_grad():
+            out, (router_probs, top1) = blk(hidden)
+    finally:
+        torch.Tensor.to = orig_to
+    return out, router_probs, top1
+
+
+def build_nllb(name):
+    D, Fd, E, cap, B, S, dtype, seed = NLLB_CASES[name]
+    experts = O.make_experts(E, D, Fd, dtype, seed, O.NLLB_MOE_DENSE_ACT_DENSE, std=0.05)
+    return dict(H=D, I=Fd, E=E, capacity=cap, B=B, S=S, dtype=dtype, seed=seed, experts=experts,
+                hidden=gen_hidden(B, S, D, dtype, seed),
+                gate=gen_gate(E, D, dtype, seed, std=2.0).float())      # fp32 values representable in the model dtype
+
+
+def make_nllb(ns):
+    for name in NLLB_CASES:
+        c = build_nllb(name)
+        out, probs, top1 = run_literal_nllb(ns, c["H"], c["I"], c["E"], c["capacity"], c["hidden"], c["gate"], c["experts"])
+        torch.save(dict(kind="nllb", source="literal",
+                        cfg={k: c[k] for k in ("H", "I", "E", "capacity", "B", "S", "seed")}, dtype=str(c["dtype"]),
+                        weight_checksum=checksum([w for e in c["experts"] for w in e]), hidden=c["hidden"],
+                        gate=c["gate"], router_probs=probs, top1=top1, out=out), os.path.join(HERE, name + ".pt"))
+        print(name, "literal ok; experts per token:", sorted(set((probs != 0).sum(-1).flatten().tolist())))
+
+
 def build_mixtral(name):
     H, I, E, k, B, S, dtype, seed = MIXTRAL_CASES[name]
     experts = O.make_experts(E, H, I, dtype, seed, O.MIXTRAL_MOE_DENSE_ACT_DENSE, std=0.05)
@@ -194,6 +254,9 @@ def build_switch(name):
 def main():
     import ref_loader
     ns = ref_loader.load() if ref_loader.available() else None
+    if sys.argv[1:] == ["nllb"]:                  # only the NLLB fixtures (the others are left untouched)
+        make_nllb(ns)
+        return
     if ns is None:
         print("WARNING: reference tree absent; fixtures will come from the oracle only")
     for name in MIXTRAL_CASES:

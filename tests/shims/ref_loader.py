@@ -121,6 +121,28 @@ def load():
                 return expert_index, router_probs, router_logits
         ms.SwitchTransformersTop1Router = SwitchTransformersTop1Router
 
+    # shim 6: HF 4.x contract of the NLLB router for the literal NLLB block (nllb_moe.py:53 unpacks two values; 4.x flattens
+    # the tokens before the classifier and returns (top_1_mask, router_probs); HF 5.x adds the logits as a third value)
+    try:
+        import transformers.models.nllb_moe.modeling_nllb_moe as mn
+        if not getattr(mn.NllbMoeTop2Router, "_b2m_4x_contract", False):
+            _NBase = mn.NllbMoeTop2Router
+
+            class NllbMoeTop2Router(_NBase):   # same name, same constructor
+                _b2m_4x_contract = True
+
+                def forward(self, hidden_states, padding_mask=None):
+                    self.input_dtype = hidden_states.dtype
+                    b, s_, h = hidden_states.shape
+                    hidden_states = hidden_states.reshape(b * s_, h).to(self.dtype)
+                    self._cast_classifier()
+                    router_logits = self.classifier(hidden_states)
+                    top_1_mask, router_probs = self.route_tokens(router_logits, self.input_dtype, padding_mask)
+                    return top_1_mask, router_probs
+            mn.NllbMoeTop2Router = NllbMoeTop2Router
+    except Exception:  # pragma: no cover - the NLLB block is optional
+        pass
+
     # byte-compiled staging only: HF's docstring decorators call inspect.getsource() on the decorated forward(); there is
     # no source text on the GPU box, so fall back to the default indentation (affects generated docstrings only)
     if not is_source_tree():
@@ -168,5 +190,9 @@ def load():
         ns.switch = importlib.import_module("moe_infinity.models.switch_transformers")   # needs memory.ExpertPredictor
     except Exception as e:  # pragma: no cover
         ns.switch_import_error = e
+    try:
+        ns.nllb = importlib.import_module("moe_infinity.models.nllb_moe")
+    except Exception as e:  # pragma: no cover
+        ns.nllb_import_error = e
     _loaded["ns"] = ns
     return ns

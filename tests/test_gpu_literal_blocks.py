@@ -1,4 +1,4 @@
-"""GPU: the reference's OWN, unmodified MoE blocks (moe_infinity/models/{mixtral,deepseek,switch_transformers}.py, loaded
+"""GPU: the reference's OWN, unmodified MoE blocks (moe_infinity/models/{mixtral,deepseek,switch_transformers,nllb_moe}.py, loaded
 through tests/shims/ref_loader.py from /root/reference or its byte-compiled staging oracle/_ref/pyref) running on a B200 on
 top of this repository's plugin objects, constructed exactly the way moe_infinity/runtime/model_offload.py constructs the
 reference's (`prefetch_handle(prefix, ratio)`, `expert_dispatcher(E, L, dtype, expert_type, num_threads)` -- five positional
@@ -133,3 +133,36 @@ def test_literal_switch_block_on_gpu(lib_built, name):
     assert stable.float().mean() > 0.9
     assert torch.equal(expert_index.cpu().flatten()[stable], fx["expert_index"].flatten()[stable])
     hidden_close(out, fx["out"], None, dt, "literal switch block")
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["nllb_mini_bf16", "nllb_capacity_f16"])
+def test_literal_nllb_block_on_gpu(lib_built, name):
+    """nllb_moe.py:20-115 (HF top-2 router on its 4.x contract, 3-D hidden states and masks handed to dispatch_local, bias
+    experts fc1|fc1_bias|fc2|fc2_bias, tokens dropped by the router's capacity pass through) on top of the plugin objects."""
+    import make_golden as G
+    from moe_infinity_b200 import _lib as L
+    ns = ref_loader.load()
+    if not hasattr(ns, "nllb"):
+        pytest.skip("the NLLB block could not be imported")
+    fx = torch.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
+    c = G.build_nllb(name)
+    assert torch.equal(c["hidden"], fx["hidden"])
+    dt = c["dtype"]
+    blk = ns.nllb.SyncNllbMoeSparseMLP(G.nllb_config(c["H"], c["I"], c["E"], c["capacity"]), c["I"]).to(dt)
+    blk.eval()
+    with torch.no_grad():
+        blk.router.classifier.weight.copy_(c["gate"])
+    blk.router.cuda()
+    _, d, ex = _plugin(c, L.EXPERT_NLLB, L.DTYPE_BF16 if dt == torch.bfloat16 else L.DTYPE_F16)
+    blk.expert_executor, blk.layer_id = ex, 0
+    with torch.no_grad():
+        out, (probs, top1) = blk(c["hidden"].cuda())
+    torch.cuda.synchronize()
+    assert out.shape == c["hidden"].shape and out.dtype == dt and out.is_cuda
+    T = c["B"] * c["S"]
+    # the router runs in fp32 on the GPU vs on the CPU for the fixture: keep the tokens whose combining weights agree exactly
+    same = (probs.cpu().reshape(T, -1) == fx["router_probs"].reshape(T, -1)).all(dim=-1)
+    assert same.float().mean() > 0.7
+    hidden_close(out.reshape(T, -1)[same.cuda()], fx["out"].reshape(T, -1)[same], None, dt, "literal nllb block")
+    assert torch.equal(top1.cpu()[same], fx["top1"][same])

@@ -127,3 +127,30 @@ def test_literal_switch_block_equals_oracle(name):
     assert torch.equal(l_out, o_out)
     fx = _load(name)
     assert fx["source"] == "literal" and torch.equal(fx["out"], l_out)
+
+
+@needs_reference
+@pytest.mark.parametrize("name", list(G.NLLB_CASES))
+def test_literal_nllb_block_reproduces_its_golden(name):
+    """The reference's own SyncNllbMoeSparseMLP (nllb_moe.py:20-115; HF's top-2 router on its 4.x contract) with the oracle's
+    NllbMoeDenseActDense behind dispatch_local reproduces the committed fixture bit for bit -- here and from the byte-compiled
+    staging -- and its output is the literal combine of the oracle's per-expert results (the part a plugin must get right)."""
+    if not hasattr(ref_loader.load(), "nllb"):
+        pytest.skip("the NLLB block could not be imported")
+    ns = ref_loader.load()
+    c = G.build_nllb(name)
+    out, probs, top1 = G.run_literal_nllb(ns, c["H"], c["I"], c["E"], c["capacity"], c["hidden"], c["gate"], c["experts"])
+    fx = _load(name)
+    assert fx["kind"] == "nllb" and torch.equal(fx["out"], out) and torch.equal(fx["router_probs"], probs)
+    assert torch.equal(fx["top1"], top1)
+    # restated combine: per expert, weights * output added in ascending expert order; untouched elements keep the input
+    x = c["hidden"].reshape(-1, c["H"])
+    w = probs.reshape(-1, c["E"])
+    acc = torch.zeros_like(x)
+    for o, _, e, _ in O.dispatch_local(x, w.bool(), c["experts"], O.NLLB_MOE_DENSE_ACT_DENSE):
+        idx = w[:, e].bool()
+        acc[idx] += torch.einsum("b,be->be", w[idx, e], o)
+    acc[acc == 0] = x[acc == 0]
+    assert torch.equal(acc.reshape(out.shape), out)
+    n = w.bool().sum(-1)
+    assert int(n.max()) == 2 and (name != "nllb_capacity_f16" or int(n.min()) < 2)      # the capacity case really drops
