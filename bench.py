@@ -245,7 +245,9 @@ def run_reference(args):
     experts = make_cpu_layer(cfg["E"], cfg["H"], cfg["I"], dtype, 1234)
     g = torch.Generator().manual_seed(7)
     gate = (torch.randn(cfg["E"], cfg["H"], generator=g) * 0.02).to(dtype)
-    xs = [torch.randn(1, BATCH, cfg["H"], generator=g).to(dtype) for _ in range(cfg["L"])]
+    # the arm's workload at N GPUs is the GPU arm's: weak scaling, batch 8 per GPU -> 8*N tokens per step through every layer
+    T = BATCH * max(1, args.gpus)
+    xs = [torch.randn(1, T, cfg["H"], generator=g).to(dtype) for _ in range(cfg["L"])]
     threads, t_layer, table = pick_cpu_threads(layer, xs[0], gate, experts, cfg["k"])
     # bound the whole run (steps + warm-up) to ~150 s: layers per timed step
     nrun = args.steps + max(1, args.warmup // 3)
@@ -261,19 +263,19 @@ def run_reference(args):
                 layer(xs[l], gate, experts, cfg["k"])
             times.append((time.perf_counter() - t0) * cfg["L"] / n_layers)
     step_s = sum(times) / len(times)
-    value = BATCH / step_s
+    value = T / step_s
     what = (f"every step = the {cfg['L']} full-size layers" if n_layers == cfg["L"] else
             f"every step = {n_layers} of the {cfg['L']} full-size layers, scaled x{cfg['L']}/{n_layers}")
-    sample = (f"{args.steps} steps x {n_layers} full-size Mixtral layers (2.8 GB bf16 weights each pass, T=8) on {threads} "
+    sample = (f"{args.steps} steps x {n_layers} full-size Mixtral layers (2.8 GB bf16 weights each pass, T={T}) on {threads} "
               f"threads of {os.cpu_count()} (thread sweep s/layer: {table})")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "p50_token_latency_ms": sorted(times)[len(times) // 2] * 1e3,
-        "config": {"workload": "Mixtral-8x7B MoE dispatch path, decode batch 8 (T=8), bf16, 32 layers x 8 experts top-2, "
-                               "H=4096 I=14336; the reference's CPU path (routing/combine restated from mixtral.py, expert "
-                               f"FFN kind '{kind}'); {what}", "inputs": "host memory", "global_batch": BATCH,
+        "config": {"workload": f"Mixtral-8x7B MoE dispatch path, decode batch 8 per GPU x {max(1, args.gpus)} (T={T}), bf16, 32 layers x 8 "
+                               "experts top-2, H=4096 I=14336; the reference's CPU path (routing/combine restated from mixtral.py, expert "
+                               f"FFN kind '{kind}'); {what}", "inputs": "host memory", "global_batch": T,
                    "layers": cfg["L"], "layers_timed_per_step": n_layers, "threads": threads},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
